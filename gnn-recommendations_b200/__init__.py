@@ -1,0 +1,14 @@
+"""gnn-recommendations hot path, B200-native (sm_100a).  See DESIGN.md.
+
+Drop-in surface (same names and signatures as the reference's ``src`` package):
+``LightGCN`` and friends, ``Trainer``, ``Evaluator``, ``BPRLoss`` and the graph-builder
+functions.  Everything numerical runs in libgr_b200.so (hand-written CUDA behind the C ABI in
+include/gr_b200.h); there is no CPU fallback.
+"""
+from . import _lib  # noqa: F401
+from .base import BaseRecommender  # noqa: F401
+from .graph_builder import (NormAdjCSR, as_csr, build_bipartite_graph, convert_to_torch_sparse,  # noqa: F401
+                            normalize_adjacency_matrix)
+from .lightgcn import LightGCN, lightgcn_propagate  # noqa: F401
+
+__version__ = "0.1.0"

@@ -1,0 +1,78 @@
+"""ctypes binding of libgr_b200.so (include/gr_b200.h).
+
+The product path has NO fallback: if the shared library is missing or a call fails,
+an exception is raised.  Build with ``python -c "import __graft_entry__ as g; g.build()"``
+or ``make -C gnn-recommendations_b200/csrc``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgr_b200.so")
+
+GR_OK = 0
+GR_SCALE_NONE, GR_SCALE_MUL, GR_SCALE_DIV = 0, 1, 2
+
+_p = C.c_void_p
+_i32, _i64, _f32, _sz = C.c_int32, C.c_int64, C.c_float, C.c_size_t
+
+# name -> (restype, argtypes); must list every symbol include/gr_b200.h declares
+SIGNATURES = {
+    "gr_version": (C.c_char_p, []),
+    "gr_error_string": (C.c_char_p, [C.c_int]),
+    "gr_last_cuda_error": (C.c_char_p, []),
+    "gr_device_info": (C.c_int, [C.POINTER(C.c_int)] * 3),
+    "gr_coo_sorted_to_csr": (C.c_int, [_p, _p, _p, _i64, _i64, _i64, _p, _p, _p, _p, _p]),
+    "gr_row_schedule_workspace_bytes": (_sz, [_i64]),
+    "gr_row_schedule": (C.c_int, [_p, _i64, _i32, _p, _p, _p, _sz, _p]),
+    "gr_build_csr_workspace_bytes": (_sz, [_i64, _i64, _i64, _i32]),
+    "gr_build_csr_pattern": (C.c_int, [_p, _p, _i64, _i64, _i64, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "gr_csr_normalize": (C.c_int, [_p, _p, _p, _p, _p, _i64, _i64, _i64, _i32, _p, _p, _p]),
+    "gr_spmm_csr_f32": (C.c_int, [_p, _p, _p, _p, _i32, _i64, _i32, _p, _i64, _p, _i64, _p, _i64, _p, _i64,
+                                  _f32, _i32, _p]),
+}
+
+
+class GrError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise GrError(
+                f"{LIB_PATH} not found: the CUDA library is required (no CPU fallback). "
+                "Run `python -c 'import __graft_entry__ as g; g.build()'`.")
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != GR_OK:
+        l = lib()
+        msg = l.gr_error_string(rc).decode()
+        if rc == -3:
+            msg += ": " + l.gr_last_cuda_error().decode()
+        raise GrError(f"{what} failed: {msg} (code {rc})")
+
+
+def ptr(t) -> int:
+    """Device pointer of a torch tensor (or None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr() -> int:
+    import torch
+
+    return torch.cuda.current_stream().cuda_stream

@@ -1,0 +1,317 @@
+"""Device-resident graph builder — the host-side mirror of the reference's
+``src/data/graph_builder.py`` (build_bipartite_graph :16-80, normalize_adjacency_matrix
+:83-144, convert_to_torch_sparse :147-174), over libgr_b200.so.
+
+The product of this module is :class:`NormAdjCSR`: the symmetric-normalised bipartite
+adjacency Â as 32-bit CSR in HBM (indptr int32[N+1], indices int32[nnz], vals f32[nnz],
+ascending columns within a row) plus the row schedule the SpMM kernels use.  The model
+classes accept either a ``NormAdjCSR`` or the torch sparse COO tensor the reference's
+``RecommendationDataset.get_torch_adjacency()`` delivers (converted on device, cached).
+"""
+from __future__ import annotations
+
+import os
+from collections import OrderedDict
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, lib, ptr, stream_ptr
+
+LONG_ROW_THRESHOLD = int(os.environ.get("GR_LONG_ROW_THRESHOLD", "1024"))
+_NORM_MODES = {"symmetric": 0, "row": 1, "none": 2}
+
+
+def _require_cuda(device) -> torch.device:
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise _lib.GrError("gnn-recommendations_b200 runs on CUDA devices only (no CPU fallback)")
+    return device
+
+
+class NormAdjCSR:
+    """Â in CSR on one GPU.  ``n_rows`` may be a row block of the full matrix (multi-GPU):
+    column ids are always global."""
+
+    is_sparse = True  # the reference models branch on adj_matrix.is_sparse (lightgcn.py:87)
+
+    def __init__(self, indptr, indices, vals, n_rows: int, n_cols: int, deg=None, symmetric: Optional[bool] = None,
+                 long_threshold: Optional[int] = None):
+        self.indptr, self.indices, self.vals = indptr, indices, vals
+        self.n_rows, self.n_cols = int(n_rows), int(n_cols)
+        self.nnz = int(indices.numel())
+        self.deg = deg
+        self.device = indptr.device
+        self._symmetric = symmetric
+        self._transpose: Optional["NormAdjCSR"] = None
+        self.row_order = None
+        self.n_long = 0
+        self.long_threshold = LONG_ROW_THRESHOLD if long_threshold is None else int(long_threshold)
+        self._schedule()
+
+    # ---- reference-API conveniences -----------------------------------------------------
+    @property
+    def shape(self) -> Tuple[int, int]:
+        return (self.n_rows, self.n_cols)
+
+    def size(self, dim: Optional[int] = None):
+        return self.shape if dim is None else self.shape[dim]
+
+    def to(self, device=None, *_, **__):
+        """``adj_matrix.to(self.device)`` (trainer.py:234, evaluator.py:77): already resident."""
+        if device is not None and torch.device(device).type == "cuda" and torch.device(device) != self.device and \
+                torch.device(device).index is not None:
+            raise _lib.GrError("NormAdjCSR cannot be moved between devices; rebuild it on the target GPU")
+        return self
+
+    def is_coalesced(self) -> bool:
+        return True
+
+    # ---- construction -----------------------------------------------------------------------
+    def _schedule(self) -> None:
+        l = lib()
+        n = self.n_rows
+        if n == 0:
+            return
+        ws_bytes = l.gr_row_schedule_workspace_bytes(n)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
+        self.row_order = torch.empty(n, dtype=torch.int32, device=self.device)
+        n_long = torch.zeros(1, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(l.gr_row_schedule(ptr(self.indptr), n, self.long_threshold, ptr(self.row_order), ptr(n_long),
+                                    ptr(ws), ws_bytes, stream_ptr()), "gr_row_schedule")
+        self.n_long = int(n_long.item())
+
+    @classmethod
+    def from_torch_coo(cls, adj: torch.Tensor) -> "NormAdjCSR":
+        """torch sparse COO (graph_builder.py:163-172 layout: int64 indices, f32 values,
+        row-major sorted, not flagged coalesced) -> CSR, on the tensor's device."""
+        if not adj.is_sparse:
+            raise ValueError("dense adjacency matrices are not supported; pass a torch sparse COO tensor")
+        device = _require_cuda(adj.device)
+        idx = adj._indices()
+        val = adj._values()
+        if val.dtype != torch.float32:
+            val = val.float()
+        n_rows, n_cols = int(adj.shape[0]), int(adj.shape[1])
+        nnz = int(val.numel())
+        rows = idx[0].contiguous()
+        cols = idx[1].contiguous()
+        val = val.contiguous()
+        l = lib()
+        indptr = torch.empty(n_rows + 1, dtype=torch.int32, device=device)
+        indices = torch.empty(nnz, dtype=torch.int32, device=device)
+        vals = torch.empty(nnz, dtype=torch.float32, device=device)
+        status = torch.zeros(1, dtype=torch.int32, device=device)
+        with torch.cuda.device(device):
+            check(l.gr_coo_sorted_to_csr(ptr(rows), ptr(cols), ptr(val), nnz, n_rows, n_cols, ptr(indptr),
+                                         ptr(indices), ptr(vals), ptr(status), stream_ptr()), "gr_coo_sorted_to_csr")
+            st = int(status.item())
+            if st & 2:
+                raise ValueError("adjacency indices out of range")
+            if st & 1:
+                # rows not sorted: stable sort by row keeps the storage order inside each row
+                order = torch.sort(rows, stable=True).indices
+                rows, cols, val = rows[order], cols[order], val[order]
+                status.zero_()
+                check(l.gr_coo_sorted_to_csr(ptr(rows), ptr(cols), ptr(val), nnz, n_rows, n_cols, ptr(indptr),
+                                             ptr(indices), ptr(vals), ptr(status), stream_ptr()),
+                      "gr_coo_sorted_to_csr")
+                if int(status.item()):
+                    raise _lib.GrError("COO -> CSR conversion failed after sorting")
+        return cls(indptr, indices, vals, n_rows, n_cols)
+
+    @classmethod
+    def from_pairs(cls, user, item, n_users: int, n_items: int, normalization: str = "symmetric",
+                   self_loop: bool = False, device="cuda", dis_lut: Optional[np.ndarray] = None) -> "NormAdjCSR":
+        """(user,item) pairs -> Â on the device (graph_builder.py:16-144).  Bit-exact with
+        scipy: duplicates are summed, degrees clamped to >= 1, values formed as
+        fl(fl(dis[r]*a)*dis[c]) from a host look-up table of numpy's own
+        ``np.power(float32(deg), -0.5)`` (numpy's f32 pow is not correctly rounded)."""
+        if normalization not in _NORM_MODES:
+            raise ValueError(f"Неизвестный тип нормализации: {normalization}")
+        device = _require_cuda(device)
+        user = torch.as_tensor(user, dtype=torch.int64).to(device, non_blocking=True).contiguous()
+        item = torch.as_tensor(item, dtype=torch.int64).to(device, non_blocking=True).contiguous()
+        if user.numel() != item.numel():
+            raise ValueError("user and item must have the same length")
+        n_pairs = int(user.numel())
+        n = n_users + n_items
+        total = 2 * n_pairs + (n if self_loop else 0)
+        l = lib()
+        ws_bytes = l.gr_build_csr_workspace_bytes(n_pairs, n_users, n_items, int(self_loop))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
+        indptr = torch.empty(n + 1, dtype=torch.int32, device=device)
+        indices = torch.empty(total, dtype=torch.int32, device=device)
+        mult = torch.empty(total, dtype=torch.float32, device=device)
+        deg = torch.empty(n, dtype=torch.int32, device=device)
+        nnz_d = torch.zeros(1, dtype=torch.int64, device=device)
+        maxdeg_d = torch.zeros(1, dtype=torch.int32, device=device)
+        status = torch.zeros(1, dtype=torch.int32, device=device)
+        with torch.cuda.device(device):
+            check(l.gr_build_csr_pattern(ptr(user), ptr(item), n_pairs, n_users, n_items, int(self_loop),
+                                         ptr(indptr), ptr(indices), ptr(mult), ptr(deg), ptr(nnz_d), ptr(maxdeg_d),
+                                         ptr(status), ptr(ws), ws_bytes, stream_ptr()), "gr_build_csr_pattern")
+            nnz, max_deg, st = int(nnz_d.item()), int(maxdeg_d.item()), int(status.item())
+            if st & 2:
+                raise ValueError("user/item id out of range")
+            del ws
+            mode = _NORM_MODES[normalization]
+            if dis_lut is None:
+                dis_lut = degree_lut(max_deg, -0.5 if mode == 0 else -1.0)
+            if len(dis_lut) <= max_deg and mode != 2:
+                raise ValueError(f"dis_lut has {len(dis_lut)} entries, max degree is {max_deg}")
+            lut = torch.from_numpy(np.ascontiguousarray(dis_lut, dtype=np.float32)).to(device)
+            indices = indices[:nnz].clone() if nnz < total else indices
+            vals = torch.empty(nnz, dtype=torch.float32, device=device)
+            check(l.gr_csr_normalize(ptr(indptr), ptr(indices), ptr(mult), ptr(deg), ptr(lut), int(lut.numel()),
+                                     n, nnz, mode, ptr(vals), ptr(status), stream_ptr()), "gr_csr_normalize")
+            if int(status.item()) & 4:
+                raise _lib.GrError("degree exceeds the look-up table")
+        return cls(indptr, indices, vals, n, n, deg=deg, symmetric=(mode != 1))
+
+    # ---- views --------------------------------------------------------------------------------
+    def row_ids(self) -> torch.Tensor:
+        counts = (self.indptr[1:] - self.indptr[:-1]).long()
+        return torch.repeat_interleave(torch.arange(self.n_rows, device=self.device), counts)
+
+    def to_torch_coo(self) -> torch.Tensor:
+        """convert_to_torch_sparse layout (graph_builder.py:163-172), on the device."""
+        idx = torch.stack([self.row_ids(), self.indices.long()])
+        return torch.sparse_coo_tensor(idx, self.vals, (self.n_rows, self.n_cols))
+
+    def to_scipy(self):
+        import scipy.sparse as sp
+
+        return sp.csr_matrix((self.vals.cpu().numpy(), self.indices.cpu().numpy(), self.indptr.cpu().numpy()),
+                             shape=self.shape).tocoo()
+
+    def transpose(self) -> "NormAdjCSR":
+        """Âᵀ for the backward pass; Â itself when it is symmetric (the default
+        'symmetric' normalisation: val[r,c] = fl(dis[r]*dis[c]) is bitwise symmetric)."""
+        if self._symmetric:
+            return self
+        if self._transpose is None:
+            rows = self.row_ids()
+            cols = self.indices.long()
+            order = torch.sort(cols, stable=True).indices        # plumbing: once per adjacency
+            t = NormAdjCSR.from_torch_coo(torch.sparse_coo_tensor(
+                torch.stack([cols[order], rows[order]]), self.vals[order], (self.n_cols, self.n_rows)))
+            if self._symmetric is None and self.n_rows == self.n_cols and t.nnz == self.nnz and \
+                    torch.equal(t.indptr, self.indptr) and torch.equal(t.indices, self.indices) and \
+                    torch.equal(t.vals, self.vals):
+                self._symmetric = True
+                return self
+            self._symmetric = False
+            self._transpose = t
+        return self._transpose
+
+    # ---- the kernel -----------------------------------------------------------------------------
+    def spmm(self, x: torch.Tensor, y: Optional[torch.Tensor] = None, addend: Optional[torch.Tensor] = None,
+             out: Optional[torch.Tensor] = None, scale: float = 1.0, scale_mode: int = _lib.GR_SCALE_NONE,
+             want_y: bool = True) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
+        """t = Â x;  y = t (if want_y);  out = scale_op(addend + t) (if out/addend given)."""
+        if x.dtype != torch.float32 or x.dim() != 2 or x.stride(1) != 1:
+            raise ValueError("x must be a row-major float32 matrix")
+        if x.shape[0] != self.n_cols:
+            raise ValueError(f"x has {x.shape[0]} rows, adjacency has {self.n_cols} columns")
+        d = int(x.shape[1])
+        if want_y and y is None:
+            y = torch.empty((self.n_rows, d), dtype=torch.float32, device=self.device)
+        if not want_y:
+            y = None
+        if out is None and (addend is not None or scale_mode != _lib.GR_SCALE_NONE):
+            out = torch.empty((self.n_rows, d), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(lib().gr_spmm_csr_f32(
+                ptr(self.indptr), ptr(self.indices), ptr(self.vals), ptr(self.row_order), self.n_long, self.n_rows,
+                d, ptr(x), x.stride(0),
+                ptr(y), y.stride(0) if y is not None else 0,
+                ptr(addend), addend.stride(0) if addend is not None else 0,
+                ptr(out), out.stride(0) if out is not None else 0,
+                float(scale), int(scale_mode), stream_ptr()), "gr_spmm_csr_f32")
+        return y, out
+
+
+def degree_lut(max_deg: int, power: float) -> np.ndarray:
+    """``np.power(max(deg,1).astype(float32), power)`` for deg = 0..max_deg — the host numpy is
+    the source of Â's values in the reference (graph_builder.py:114-119, 130)."""
+    deg = np.maximum(np.arange(max_deg + 1, dtype=np.float32), np.float32(1.0))
+    lut = np.power(deg, power)
+    lut[np.isinf(lut)] = 0.0
+    return lut.astype(np.float32)
+
+
+# --------------------------------------------------------------------------------------------
+# cache: the reference rebuilds the torch adjacency every epoch / validate / evaluate
+# (trainer.py:233, 293; evaluator.py:76) and passes the same object to the model for every
+# step in between.
+# --------------------------------------------------------------------------------------------
+_CACHE: "OrderedDict[tuple, tuple]" = OrderedDict()
+_CACHE_SIZE = 4
+
+
+def as_csr(adj_matrix) -> NormAdjCSR:
+    if isinstance(adj_matrix, NormAdjCSR):
+        return adj_matrix
+    if adj_matrix is None:
+        raise ValueError("adj_matrix is None")
+    if not isinstance(adj_matrix, torch.Tensor):
+        raise TypeError(f"unsupported adjacency type: {type(adj_matrix)}")
+    if not adj_matrix.is_sparse:
+        raise ValueError("dense adjacency matrices are not supported; pass a torch sparse COO tensor")
+    if adj_matrix.device.type != "cuda":
+        raise _lib.GrError("adjacency must live on a CUDA device (call .to(device) first, as the reference "
+                           "Trainer does)")
+    idx, val = adj_matrix._indices(), adj_matrix._values()
+    key = (idx.data_ptr(), val.data_ptr(), int(val.numel()), tuple(adj_matrix.shape), str(adj_matrix.device))
+    hit = _CACHE.get(key)
+    if hit is not None:
+        _CACHE.move_to_end(key)
+        return hit[0]
+    csr = NormAdjCSR.from_torch_coo(adj_matrix)
+    _CACHE[key] = (csr, adj_matrix)          # keep the tensor alive so its pointers stay unique
+    while len(_CACHE) > _CACHE_SIZE:
+        _CACHE.popitem(last=False)
+    return csr
+
+
+# --------------------------------------------------------------------------------------------
+# reference-named entry points (same argument meaning as src/data/graph_builder.py)
+# --------------------------------------------------------------------------------------------
+class BipartiteGraph:
+    """Un-normalised interactions held on the device; what build_bipartite_graph returns here
+    (the reference returns a scipy COO of ones)."""
+
+    def __init__(self, user, item, n_users, n_items, self_loop, device):
+        self.user, self.item = user, item
+        self.n_users, self.n_items, self.self_loop, self.device = n_users, n_items, self_loop, device
+        self.shape = (n_users + n_items, n_users + n_items)
+
+
+def build_bipartite_graph(interactions, n_users: int, n_items: int, user_col: str = "userId",
+                          item_col: str = "itemId", self_loop: bool = False, device="cuda") -> BipartiteGraph:
+    """graph_builder.py:16-80.  ``interactions``: DataFrame with user/item columns, or a
+    (user, item) tuple of arrays/tensors."""
+    if isinstance(interactions, tuple):
+        u, i = interactions
+    else:
+        u = interactions[user_col].to_numpy(dtype=np.int64, copy=False)
+        i = interactions[item_col].to_numpy(dtype=np.int64, copy=False)
+    device = _require_cuda(device)
+    u = torch.as_tensor(u, dtype=torch.int64).to(device)
+    i = torch.as_tensor(i, dtype=torch.int64).to(device)
+    return BipartiteGraph(u, i, n_users, n_items, self_loop, device)
+
+
+def normalize_adjacency_matrix(adj: BipartiteGraph, normalization: str = "symmetric") -> NormAdjCSR:
+    """graph_builder.py:83-144."""
+    return NormAdjCSR.from_pairs(adj.user, adj.item, adj.n_users, adj.n_items, normalization, adj.self_loop,
+                                 adj.device)
+
+
+def convert_to_torch_sparse(adj: NormAdjCSR) -> torch.Tensor:
+    """graph_builder.py:147-174 (device-resident result)."""
+    return adj.to_torch_coo()

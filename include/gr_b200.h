@@ -1,0 +1,121 @@
+/*
+ * gr_b200.h — C ABI of libgr_b200.so: the B200 (sm_100a) hot path of
+ * timur1arkhipov/gnn-recommendations.
+ *
+ * The reference is pure Python: its "operator interface" for this path is a set of
+ * call sites into torch / scipy.  Each entry point below names the reference call
+ * site (file:line under /root/reference/gnn-recommendations/) it replaces.  The
+ * Python classes in gnn-recommendations_b200/ bind these with ctypes; INTEGRATION.md
+ * shows the stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host;
+ *   - `stream` is a cudaStream_t passed as void*;
+ *   - functions return GR_OK (0) or a negative GR_ERR_* code, never throw, never
+ *     allocate device memory (callers pass outputs and workspace), never synchronise
+ *     the stream;
+ *   - all matrices are row-major fp32; `ld*` are leading dimensions in floats and must
+ *     be multiples of 4 (16-byte rows); base pointers must be 16-byte aligned;
+ *   - integer outputs (CSR structure, negatives, top-K ids) are bit-exact with the
+ *     reference; fp32 outputs follow the reference's summation order where stated.
+ */
+#ifndef GR_B200_H
+#define GR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GR_OK 0
+#define GR_ERR_INVALID (-1)     /* bad argument (null pointer, negative size, misalignment) */
+#define GR_ERR_UNSUPPORTED (-2) /* feature dimension / option not compiled in                */
+#define GR_ERR_CUDA (-3)        /* a CUDA runtime call failed (see gr_last_cuda_error)        */
+#define GR_ERR_WORKSPACE (-4)   /* workspace too small                                       */
+#define GR_ERR_OVERFLOW (-5)    /* nnz or N does not fit the 32-bit CSR                      */
+
+#define GR_SCALE_NONE 0
+#define GR_SCALE_MUL 1 /* out = (addend + A x) * scale  — torch.mean multiplies by 1/count  */
+#define GR_SCALE_DIV 2 /* out = (addend + A x) / scale                                        */
+
+const char *gr_version(void);
+const char *gr_error_string(int code);
+/* cudaGetErrorString of the last failing CUDA call made by this thread inside the library. */
+const char *gr_last_cuda_error(void);
+/* sm count and compute capability of the current device. */
+int gr_device_info(int *sm_count_host, int *cc_major_host, int *cc_minor_host);
+
+/* ------------------------------------------------------------------------------------------
+ * Graph builder
+ * ------------------------------------------------------------------------------------------ */
+
+/* Replaces the implicit COO->CSR conversion inside torch.sparse.mm for the adjacency the
+ * reference hands to every model (src/data/graph_builder.py:147-174 produces int64 COO,
+ * row-major sorted; src/models/baselines/lightgcn.py:88 consumes it).  Storage order within
+ * a row is preserved (it is the summation order).  `status` (device int32[1], zeroed by the
+ * caller) receives a bit mask: 1 = rows not non-decreasing, 2 = index out of range. */
+int gr_coo_sorted_to_csr(const int64_t *rows, const int64_t *cols, const float *vals, int64_t nnz,
+                         int64_t n_rows, int64_t n_cols, int32_t *indptr /* n_rows+1 */,
+                         int32_t *indices /* nnz */, float *out_vals /* nnz, may alias vals */,
+                         int32_t *status, void *stream);
+
+/* Replaces build_bipartite_graph + normalize_adjacency_matrix (src/data/graph_builder.py:16-80,
+ * 83-144): (user,item) int64 pairs -> canonical CSR of [[0,R],[R^T,0]] (+ I when self_loop),
+ * rows/columns numbered users first.  Two phases, because the values come from a HOST look-up
+ * table of numpy's np.power(float32(deg), -0.5) that can only be sized once the maximum
+ * degree is known (numpy's f32 pow is not correctly rounded, so the device cannot recompute it):
+ *
+ *   gr_build_csr_pattern: keys (row << b | col) -> stable LSD radix sort -> duplicates merged
+ *       (scipy's tocsr SUMS them: `mult` holds the multiplicity) -> indptr / indices / deg
+ *       (row sums, integer) / nnz_out (device int64[1]) / max_deg_out (device int32[1]).
+ *       `indices` and `mult` need room for 2*n_pairs (+ N with self loops) entries.
+ *       status bit 2: id out of range.
+ *   gr_csr_normalize: vals[k] = fl(fl(lut[deg[r]] * mult[k]) * lut[deg[c]])   mode 0 'symmetric'
+ *                              = fl(lut[deg[r]] * mult[k])                     mode 1 'row'
+ *                              = mult[k]                                       mode 2 'none'
+ *       (the left-to-right order of `d_mat @ adj @ d_mat`, graph_builder.py:126); lut[0] is the
+ *       value for the clamped degree max(0,1).  status bit 4: degree outside the table. */
+size_t gr_build_csr_workspace_bytes(int64_t n_pairs, int64_t n_users, int64_t n_items, int32_t self_loop);
+int gr_build_csr_pattern(const int64_t *user, const int64_t *item, int64_t n_pairs, int64_t n_users,
+                         int64_t n_items, int32_t self_loop, int32_t *indptr /* N+1 */, int32_t *indices,
+                         float *mult, int32_t *deg /* N */, int64_t *nnz_out, int32_t *max_deg_out,
+                         int32_t *status, void *workspace, size_t workspace_bytes, void *stream);
+int gr_csr_normalize(const int32_t *indptr, const int32_t *indices, const float *mult, const int32_t *deg,
+                     const float *lut, int64_t lut_len, int64_t n_rows, int64_t nnz, int32_t mode, float *vals,
+                     int32_t *status, void *stream);
+
+/* Row schedule for gr_spmm_csr_f32: `row_order` = rows sorted by descending length
+ * (longest-processing-time-first), `n_long_out` (device int32[1]) = how many of them have
+ * >= long_threshold entries and go to the CTA-cooperative path.  `keys` is caller scratch of
+ * n_rows int64.  Ties keep ascending row id. */
+size_t gr_row_schedule_workspace_bytes(int64_t n_rows);
+int gr_row_schedule(const int32_t *indptr, int64_t n_rows, int32_t long_threshold, int32_t *row_order,
+                    int32_t *n_long_out, void *workspace, size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Propagation
+ * ------------------------------------------------------------------------------------------ */
+
+/* Replaces torch.sparse.mm(adj, x) (lightgcn.py:88, ngcf.py:70, orthogonal_bundle/model.py:172,
+ * kgtore.py:310) and, through the epilogue, torch.stack/mean over layers (lightgcn.py:94-95).
+ *
+ *   t[r,:]   = fma-chain over the row's entries in storage order, from a zero accumulator
+ *              (bit-identical to the CPU torch.sparse.mm the reference runs)
+ *   y[r,:]   = t[r,:]                                   if y   != NULL
+ *   out[r,:] = scale_op(addend ? addend[r,:] + t : t)   if out != NULL
+ *
+ * `row_order` may be NULL (natural order, n_long ignored).  Rows row_order[0..n_long) are
+ * processed one CTA per row with the gathered x rows staged through shared memory by
+ * cp.async; the rest one row per (sub-)warp with 128-bit gathers.  d in {32,64,128,256}.
+ * n_rows may be a row block of a larger matrix (column ids index x, not y). */
+int gr_spmm_csr_f32(const int32_t *indptr, const int32_t *indices, const float *vals,
+                    const int32_t *row_order, int32_t n_long, int64_t n_rows, int32_t d, const float *x,
+                    int64_t ldx, float *y, int64_t ldy, const float *addend, int64_t lda, float *out,
+                    int64_t ldo, float scale, int32_t scale_mode, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GR_B200_H */

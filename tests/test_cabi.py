@@ -1,0 +1,77 @@
+"""CPU-only checks of the drop-in boundary: the C-ABI library loads and exports every symbol
+include/gr_b200.h declares; the Python classes keep the reference's API and error behaviour."""
+import ctypes
+import inspect
+import os
+import re
+import sys
+
+import pytest
+import torch
+
+import gnn_recommendations_b200 as g
+from conftest import REFERENCE, REPO
+
+
+def declared_symbols():
+    text = open(os.path.join(REPO, "include", "gr_b200.h"), encoding="utf-8").read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(gr_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    names = declared_symbols()
+    assert len(names) >= 8
+    handle = ctypes.CDLL(g._lib.LIB_PATH)
+    for n in names:
+        assert hasattr(handle, n), f"{n} declared in include/gr_b200.h but not exported"
+    assert set(names) == set(g._lib.SIGNATURES), set(names) ^ set(g._lib.SIGNATURES)
+
+
+def test_version_and_error_strings():
+    l = g._lib.lib()
+    assert b"sm_100a" in l.gr_version()
+    assert l.gr_error_string(0) == b"ok"
+    assert b"invalid" in l.gr_error_string(-1)
+
+
+def test_no_oracle_import_in_product():
+    pkg = os.path.join(REPO, "gnn-recommendations_b200")
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                src = open(os.path.join(root, f), encoding="utf-8").read()
+                assert "oracle" not in src.lower(), f"{f} mentions the oracle"
+
+
+def test_lightgcn_api_and_errors():
+    m = g.LightGCN(7, 5, embedding_dim=64, n_layers=3, init_scale=0.1)
+    assert list(m.state_dict()) == ["user_embedding.weight", "item_embedding.weight"]
+    assert m.get_parameters_count() == 12 * 64
+    with pytest.raises(ValueError):
+        m.get_all_embeddings(None)
+    with pytest.raises(ValueError):
+        m.predict(torch.tensor([0]), torch.tensor([0]))
+    with pytest.raises(ValueError):
+        g.as_csr(torch.zeros(3, 3))            # dense adjacency rejected
+    cpu_adj = torch.sparse_coo_tensor(torch.tensor([[0], [1]]), torch.tensor([1.0]), (12, 12))
+    with pytest.raises(g._lib.GrError):
+        m(cpu_adj)                               # no CPU fallback
+
+
+def sig(cls):
+    return [(p.name, p.default) for p in inspect.signature(cls.__init__).parameters.values()]
+
+
+@pytest.mark.reference
+def test_constructor_signatures_and_same_seed_parameters():
+    sys.path.insert(0, REFERENCE)
+    from src.models import LightGCN as RefLightGCN
+
+    assert sig(RefLightGCN) == sig(g.LightGCN)
+    torch.manual_seed(42)
+    a = RefLightGCN(50, 40, 64, 3, 0.1)
+    torch.manual_seed(42)
+    b = g.LightGCN(50, 40, 64, 3, 0.1)
+    for (ka, va), (kb, vb) in zip(a.state_dict().items(), b.state_dict().items()):
+        assert ka == kb and torch.equal(va, vb)

@@ -1,0 +1,234 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and the golden
+fixtures of the reference.  Integer/index results bit-exact; LightGCN embeddings bit-exact;
+gradients within 1e-5 relative."""
+import hashlib
+
+import numpy as np
+import pytest
+import torch
+
+import gnn_recommendations_b200 as g
+from gnn_recommendations_b200 import _lib
+from oracle import coracle
+from oracle import pyoracle as po
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def bits(a):
+    return np.ascontiguousarray(a).view(np.uint32)
+
+
+@pytest.fixture(scope="module")
+def tiny_ref(tiny):
+    return po.build_norm_adj(tiny["train_u"], tiny["train_i"], int(tiny["n_users"]), int(tiny["n_items"]))
+
+
+@pytest.fixture(scope="module")
+def tiny_csr(tiny):
+    return g.NormAdjCSR.from_pairs(tiny["train_u"], tiny["train_i"], int(tiny["n_users"]), int(tiny["n_items"]),
+                                   device=DEV, dis_lut=tiny["dis_lut"])
+
+
+def assert_csr_equal(csr, ref):
+    assert np.array_equal(csr.indptr.cpu().numpy().astype(np.int64), ref["indptr"])
+    assert np.array_equal(csr.indices.cpu().numpy(), ref["indices"])
+    assert np.array_equal(bits(csr.vals.cpu().numpy()), bits(ref["vals"]))
+
+
+# ------------------------------------------------------------------------- graph builder
+def test_build_from_pairs_bit_exact_vs_golden(tiny, tiny_csr):
+    assert np.array_equal(tiny_csr.indices.cpu().numpy(), tiny["adj_col"])
+    assert np.array_equal(bits(tiny_csr.vals.cpu().numpy()), bits(tiny["adj_val"]))
+    assert np.array_equal(tiny_csr.row_ids().cpu().numpy(), tiny["adj_row"].astype(np.int64))
+    assert np.array_equal(tiny_csr.deg.cpu().numpy(), tiny["deg"].astype(np.int32))
+
+
+def test_build_row_normalisation(tiny):
+    csr = g.NormAdjCSR.from_pairs(tiny["train_u"], tiny["train_i"], int(tiny["n_users"]), int(tiny["n_items"]),
+                                  normalization="row", device=DEV, dis_lut=tiny["dinv_lut"])
+    assert np.array_equal(bits(csr.vals.cpu().numpy()), bits(tiny["adjrow_val"]))
+
+
+def test_build_duplicates_isolated_and_empty():
+    u = np.array([0, 0, 1, 0]); i = np.array([0, 0, 0, 0])
+    assert_csr_equal(g.NormAdjCSR.from_pairs(u, i, 2, 2, device=DEV), po.build_norm_adj(u, i, 2, 2))
+    e = np.zeros(0, dtype=np.int64)
+    csr = g.NormAdjCSR.from_pairs(e, e, 3, 2, device=DEV)
+    assert csr.nnz == 0 and csr.indptr.cpu().tolist() == [0] * 6
+    with pytest.raises(ValueError):
+        g.NormAdjCSR.from_pairs(np.array([5]), np.array([0]), 2, 2, device=DEV)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_build_random_graphs_vs_oracle(seed):
+    rng = np.random.default_rng(seed)
+    nu, ni, e = int(rng.integers(1, 400)), int(rng.integers(1, 300)), int(rng.integers(1, 20000))
+    u = rng.integers(0, nu, e); i = rng.integers(0, ni, e)       # with duplicates, with isolated nodes
+    assert_csr_equal(g.NormAdjCSR.from_pairs(u, i, nu, ni, device=DEV), po.build_norm_adj(u, i, nu, ni))
+
+
+def test_coo_to_csr_paths(tiny_ref):
+    coo = po.to_torch_coo(tiny_ref).to(DEV)
+    assert_csr_equal(g.NormAdjCSR.from_torch_coo(coo), tiny_ref)
+    assert g.as_csr(coo) is g.as_csr(coo)                          # cached by content pointers
+    # unsorted rows: storage order inside a row must be preserved
+    perm = torch.randperm(coo._values().numel(), generator=torch.Generator().manual_seed(1)).to(DEV)
+    shuffled = torch.sparse_coo_tensor(coo._indices()[:, perm], coo._values()[perm], coo.shape)
+    csr = g.NormAdjCSR.from_torch_coo(shuffled)
+    assert np.array_equal(csr.indptr.cpu().numpy().astype(np.int64), tiny_ref["indptr"])
+    bad = torch.sparse_coo_tensor(torch.tensor([[0], [99]]), torch.tensor([1.0]), (4, 4)).to(DEV)
+    with pytest.raises((ValueError, RuntimeError)):
+        g.NormAdjCSR.from_torch_coo(bad)
+
+
+def test_row_schedule_is_lpt(tiny_csr):
+    lens = (tiny_csr.indptr[1:] - tiny_csr.indptr[:-1]).cpu().numpy()
+    order = tiny_csr.row_order.cpu().numpy()
+    assert sorted(order.tolist()) == list(range(tiny_csr.n_rows))
+    expect = np.lexsort((np.arange(len(lens)), -lens))
+    assert np.array_equal(order, expect)
+    assert tiny_csr.n_long == int((lens >= tiny_csr.long_threshold).sum())
+
+
+# ------------------------------------------------------------------------- SpMM
+@pytest.mark.parametrize("d", [32, 64, 128, 256])
+@pytest.mark.parametrize("long_threshold", [1 << 30, 16, 1])
+def test_spmm_bit_exact(tiny_ref, d, long_threshold):
+    csr = g.NormAdjCSR(torch.from_numpy(tiny_ref["indptr"].astype(np.int32)).to(DEV),
+                       torch.from_numpy(tiny_ref["indices"]).to(DEV), torch.from_numpy(tiny_ref["vals"]).to(DEV),
+                       tiny_ref["n"], tiny_ref["n"], long_threshold=long_threshold)
+    x = torch.randn(tiny_ref["n"], d, generator=torch.Generator().manual_seed(d))
+    want = coracle.spmm_fmaf(tiny_ref["indptr"], tiny_ref["indices"], tiny_ref["vals"], x.numpy())
+    y, _ = csr.spmm(x.to(DEV))
+    assert np.array_equal(bits(y.cpu().numpy()), bits(want))
+    # epilogue: out = (addend + t) / 4, y not stored
+    add = torch.randn(tiny_ref["n"], d, generator=torch.Generator().manual_seed(7))
+    _, out = csr.spmm(x.to(DEV), addend=add.to(DEV), scale=4.0, scale_mode=_lib.GR_SCALE_DIV, want_y=False)
+    assert np.array_equal(bits(out.cpu().numpy()), bits((add.numpy() + want) / np.float32(4.0)))
+
+
+def test_spmm_natural_order_and_strided_views(tiny_ref):
+    csr = g.NormAdjCSR(torch.from_numpy(tiny_ref["indptr"].astype(np.int32)).to(DEV),
+                       torch.from_numpy(tiny_ref["indices"]).to(DEV), torch.from_numpy(tiny_ref["vals"]).to(DEV),
+                       tiny_ref["n"], tiny_ref["n"])
+    csr.row_order, csr.n_long = None, 0
+    big = torch.randn(tiny_ref["n"], 256, generator=torch.Generator().manual_seed(3)).to(DEV)
+    x = big[:, 64:128]                                           # ld = 256, d = 64
+    want = coracle.spmm_fmaf(tiny_ref["indptr"], tiny_ref["indices"], tiny_ref["vals"], x.cpu().numpy())
+    outbuf = torch.zeros(tiny_ref["n"], 256, device=DEV)
+    csr.spmm(x, y=outbuf[:, 128:192])
+    assert np.array_equal(bits(outbuf[:, 128:192].cpu().numpy()), bits(want))
+    assert float(outbuf[:, :128].abs().sum()) == 0.0 and float(outbuf[:, 192:].abs().sum()) == 0.0
+
+
+def test_spmm_hot_rows_power_law():
+    # one item adjacent to every user (row of length 5000) + ragged tails + empty rows
+    rng = np.random.default_rng(5)
+    nu, ni = 5000, 300
+    u = np.concatenate([np.arange(nu), rng.integers(0, nu, 40000)])
+    i = np.concatenate([np.zeros(nu, dtype=np.int64), (rng.pareto(1.0, 40000) * 3).astype(np.int64) % (ni - 10)])
+    ref = po.build_norm_adj(u, i, nu, ni)
+    for thr in (1024, 64):
+        csr = g.NormAdjCSR.from_pairs(u, i, nu, ni, device=DEV)
+        csr.long_threshold = thr
+        csr._schedule()
+        assert csr.n_long >= 1
+        for d in (64, 128):
+            x = torch.randn(ref["n"], d, generator=torch.Generator().manual_seed(d))
+            want = coracle.spmm_fmaf(ref["indptr"], ref["indices"], ref["vals"], x.numpy())
+            y, _ = csr.spmm(x.to(DEV))
+            assert np.array_equal(bits(y.cpu().numpy()), bits(want)), (thr, d)
+
+
+def test_spmm_argument_errors(tiny_csr):
+    with pytest.raises(_lib.GrError):
+        tiny_csr.spmm(torch.zeros(tiny_csr.n_cols, 48, device=DEV))      # unsupported d
+    with pytest.raises(ValueError):
+        tiny_csr.spmm(torch.zeros(3, 64, device=DEV))
+
+
+# ------------------------------------------------------------------------- LightGCN
+@pytest.mark.parametrize("tag,d,L", [("lightgcn", 64, 3), ("lightgcn_d128_l4", 128, 4)])
+def test_lightgcn_forward_bit_exact_vs_reference(tiny, tiny_csr, tag, d, L):
+    m = g.LightGCN(int(tiny["n_users"]), int(tiny["n_items"]), d, L, 0.1)
+    m.load_state_dict({"user_embedding.weight": torch.from_numpy(tiny[f"{tag}/user_embedding.weight"]),
+                       "item_embedding.weight": torch.from_numpy(tiny[f"{tag}/item_embedding.weight"])})
+    m.to(DEV)
+    with torch.no_grad():
+        ue, ie = m.get_all_embeddings(tiny_csr)
+    assert np.array_equal(bits(ue.cpu().numpy()), bits(tiny[f"{tag}/out_user"]))
+    assert np.array_equal(bits(ie.cpu().numpy()), bits(tiny[f"{tag}/out_item"]))
+    if tag == "lightgcn":
+        layers = torch.stack(m.get_layer_embeddings(tiny_csr)).cpu().numpy()
+        assert np.array_equal(bits(layers), bits(tiny["lightgcn/layers"]))
+        # the torch-COO entry the reference Trainer uses gives the same bits
+        coo = tiny_csr.to_torch_coo()
+        with torch.no_grad():
+            ue2, _ = m(coo)
+        assert torch.equal(ue, ue2)
+
+
+def test_lightgcn_step_gradients_vs_reference(tiny, tiny_csr):
+    m = g.LightGCN(int(tiny["n_users"]), int(tiny["n_items"]), 64, 3, 0.1)
+    m.load_state_dict({"user_embedding.weight": torch.from_numpy(tiny["lightgcn/user_embedding.weight"]),
+                       "item_embedding.weight": torch.from_numpy(tiny["lightgcn/item_embedding.weight"])})
+    m.to(DEV)
+    us, ps, ns = (torch.from_numpy(tiny[f"batch0/{k}"]).to(DEV) for k in ("users", "pos", "neg"))
+    ue, ie = m.get_all_embeddings(tiny_csr)
+    loss = po.bpr_loss_reference(ue, ie, us, ps, ns)          # torch ops on the device, reference formula
+    loss.backward()
+    assert abs(float(loss) - float(tiny["step0/loss"])) <= 1e-5 * abs(float(tiny["step0/loss"]))
+    np.testing.assert_allclose(m.user_embedding.weight.grad.cpu().numpy(), tiny["step0/grad_user"],
+                               rtol=1e-5, atol=1e-10)
+    np.testing.assert_allclose(m.item_embedding.weight.grad.cpu().numpy(), tiny["step0/grad_item"],
+                               rtol=1e-5, atol=1e-10)
+
+
+def test_nonsymmetric_backward_uses_transpose(tiny):
+    csr = g.NormAdjCSR.from_pairs(tiny["train_u"], tiny["train_i"], int(tiny["n_users"]), int(tiny["n_items"]),
+                                  normalization="row", device=DEV)
+    ref = po.build_norm_adj(tiny["train_u"], tiny["train_i"], int(tiny["n_users"]), int(tiny["n_items"]), "row")
+    m = g.LightGCN(int(tiny["n_users"]), int(tiny["n_items"]), 64, 2, 0.1).to(DEV)
+    uw, iw = m.user_embedding.weight.detach().cpu(), m.item_embedding.weight.detach().cpu()
+    ue, ie = m(csr)
+    (ue.sum() * 2 + (ie * ie).sum()).backward()
+    ruw, riw = uw.clone().requires_grad_(True), iw.clone().requires_grad_(True)
+    rue, rie = po.lightgcn_forward(po.to_torch_coo(ref), ruw, riw, 2)
+    (rue.sum() * 2 + (rie * rie).sum()).backward()
+    assert torch.equal(ue.detach().cpu(), rue.detach())
+    torch.testing.assert_close(m.user_embedding.weight.grad.cpu(), ruw.grad, rtol=1e-5, atol=1e-8)
+    torch.testing.assert_close(m.item_embedding.weight.grad.cpu(), riw.grad, rtol=1e-5, atol=1e-8)
+
+
+# ------------------------------------------------------------------------- C1 shape (full size)
+def test_c1_graph_and_forward_vs_reference_hashes(c1gold, c1split):
+    tu, ti = c1split["train"]
+    nu, ni = c1split["n_users"], c1split["n_items"]
+    csr = g.NormAdjCSR.from_pairs(tu, ti, nu, ni, device=DEV, dis_lut=c1gold["dis_lut"])
+    assert csr.nnz == int(c1gold["nnz"])
+    assert sha(csr.row_ids().cpu().numpy().astype(np.int32)) == str(c1gold["sha_adj_row"])
+    assert sha(csr.indices.cpu().numpy()) == str(c1gold["sha_adj_col"])
+    assert sha(csr.vals.cpu().numpy()) == str(c1gold["sha_adj_val"])
+    # weights: numpy PCG64 (platform independent), as in make_golden.np_init
+    rng = np.random.default_rng(42)
+    uw = (rng.standard_normal((nu, 64)) * 0.1).astype(np.float32)
+    iw = (rng.standard_normal((ni, 64)) * 0.1).astype(np.float32)
+    m = g.LightGCN(nu, ni, 64, 3, 0.1)
+    m.load_state_dict({"user_embedding.weight": torch.from_numpy(uw), "item_embedding.weight": torch.from_numpy(iw)})
+    m.to(DEV)
+    with torch.no_grad():
+        ue, ie = m(csr)
+    assert sha(ue.cpu().numpy()) == str(c1gold["sha_out_user"])
+    assert sha(ie.cpu().numpy()) == str(c1gold["sha_out_item"])
+    # size-independent property: linearity of the propagation in x (exact for scaling by 2)
+    with torch.no_grad():
+        x0 = torch.cat([m.user_embedding.weight, m.item_embedding.weight])
+        a = g.lightgcn_propagate(csr, x0, 3)
+        b = g.lightgcn_propagate(csr, x0 * 2.0, 3)
+    assert torch.equal(a * 2.0, b)
