@@ -1,0 +1,103 @@
+"""Row-partitioned propagation across the GPUs of one box (no reference
+counterpart — the reference is single-process).
+
+Rows of Â are split into G contiguous blocks balanced by nnz.  Rank g owns the embedding rows
+of its block; every layer is one exchange (all-gather of the layer's rows over NVLink) followed
+by a local SpMM on the rank's row block.  Blocks are padded to a common height H so the gathered
+matrix is a dense [G*H, d] buffer and the all-gather is in place with equal chunks; column ids
+are remapped once to that padded numbering.  Per (row, feature) the arithmetic is the same fmaf
+chain as on one GPU, so the G-GPU result is bit-identical to the 1-GPU result.
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from .graph_builder import NormAdjCSR
+
+
+class RowPartition:
+    def __init__(self, indptr: torch.Tensor, world_size: int):
+        """``indptr``: the full matrix's row pointer (any device)."""
+        ip = indptr.detach().to("cpu", torch.int64).numpy()
+        n = len(ip) - 1
+        nnz = int(ip[-1])
+        # cut after the row where the running nnz (+1 per row so empty rows spread too) crosses k/G
+        weight = ip[1:] + np.arange(1, n + 1)
+        total = nnz + n
+        cuts = [0]
+        for k in range(1, world_size):
+            cuts.append(int(np.searchsorted(weight, total * k / world_size, side="left")) + 1)
+        cuts.append(n)
+        cuts = np.maximum.accumulate(np.minimum(np.asarray(cuts, dtype=np.int64), n))
+        self.bounds = cuts                                   # G+1 row boundaries
+        self.world_size = world_size
+        self.n = n
+        self.block_rows = int(max(1, np.diff(cuts).max()))
+        self.block_rows = (self.block_rows + 3) // 4 * 4
+        self.padded_rows = self.block_rows * world_size
+
+    def rows_of(self, rank: int):
+        return int(self.bounds[rank]), int(self.bounds[rank + 1])
+
+    def to_padded(self, ids: torch.Tensor) -> torch.Tensor:
+        """global node id -> position in the padded [G*H] numbering."""
+        b = torch.as_tensor(self.bounds, device=ids.device)
+        owner = torch.searchsorted(b[1:].contiguous(), ids.long(), right=True)
+        return owner * self.block_rows + (ids.long() - b[owner])
+
+    def local_csr(self, full: NormAdjCSR, rank: int) -> NormAdjCSR:
+        r0, r1 = self.rows_of(rank)
+        lo, hi = int(full.indptr[r0].item()), int(full.indptr[r1].item())
+        indptr = (full.indptr[r0:r1 + 1] - lo).to(torch.int32).contiguous()
+        indices = self.to_padded(full.indices[lo:hi]).to(torch.int32).contiguous()
+        vals = full.vals[lo:hi].contiguous()
+        return NormAdjCSR(indptr, indices, vals, r1 - r0, self.padded_rows, long_threshold=full.long_threshold)
+
+    def scatter_rows(self, x_full: torch.Tensor, rank: int) -> torch.Tensor:
+        r0, r1 = self.rows_of(rank)
+        return x_full[r0:r1]
+
+
+def _all_gather_rows(buf: torch.Tensor, rank: int, block_rows: int, group=None) -> None:
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        mine = buf[rank * block_rows:(rank + 1) * block_rows]
+        dist.all_gather_into_tensor(buf, mine, group=group)
+
+
+def lightgcn_propagate_sharded(local: NormAdjCSR, part: RowPartition, rank: int, x0_local: torch.Tensor,
+                               n_layers: int, group=None,
+                               spmm: Optional[Callable] = None) -> torch.Tensor:
+    """mean_{l<=L} Â^l x0 for this rank's rows.  ``x0_local``: [rows_of(rank), d].  ``spmm`` is
+    injectable for the CPU (gloo) tests of the partition / exchange logic; the product path is
+    the CUDA kernel."""
+    n_local, d = x0_local.shape
+    H = part.block_rows
+    dev = x0_local.device
+    off = rank * H
+    if spmm is None:
+        def spmm(x, y, addend, out, scale, mode):
+            local.spmm(x, y=y, addend=addend, out=out, scale=scale, scale_mode=mode, want_y=y is not None)
+    bufs = [torch.zeros((part.padded_rows, d), dtype=torch.float32, device=dev) for _ in range(min(2, max(1, n_layers)))]
+    bufs[0][off:off + n_local].copy_(x0_local)
+    if n_layers == 0:
+        return x0_local.clone()
+    acc = torch.empty_like(x0_local)
+    out = torch.empty_like(x0_local)
+    cur = 0
+    for l in range(n_layers):
+        _all_gather_rows(bufs[cur], rank, H, group)
+        last = l == n_layers - 1
+        addend = x0_local if l == 0 else acc
+        if last:
+            spmm(bufs[cur], None, addend, out, float(n_layers + 1), _lib.GR_SCALE_DIV)
+        else:
+            nxt = (cur + 1) % len(bufs)
+            spmm(bufs[cur], bufs[nxt][off:off + n_local], addend, acc, 1.0, _lib.GR_SCALE_NONE)
+            cur = nxt
+    return out

@@ -48,6 +48,8 @@ class NormAdjCSR:
         self._transpose: Optional["NormAdjCSR"] = None
         self.row_order = None
         self.n_long = 0
+        self.timings = None      # set to a list to collect (start, end) CUDA events per SpMM launch
+        self.launches = 0        # kernels launched by spmm() so far
         self.long_threshold = LONG_ROW_THRESHOLD if long_threshold is None else int(long_threshold)
         self._schedule()
 
@@ -225,6 +227,11 @@ class NormAdjCSR:
         if out is None and (addend is not None or scale_mode != _lib.GR_SCALE_NONE):
             out = torch.empty((self.n_rows, d), dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
+            ev = None
+            if self.timings is not None:
+                ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                ev[0].record()
+            self.launches += 1 + (1 if (self.n_long > 0 and self.row_order is not None) else 0)
             check(lib().gr_spmm_csr_f32(
                 ptr(self.indptr), ptr(self.indices), ptr(self.vals), ptr(self.row_order), self.n_long, self.n_rows,
                 d, ptr(x), x.stride(0),
@@ -232,6 +239,9 @@ class NormAdjCSR:
                 ptr(addend), addend.stride(0) if addend is not None else 0,
                 ptr(out), out.stride(0) if out is not None else 0,
                 float(scale), int(scale_mode), stream_ptr()), "gr_spmm_csr_f32")
+            if ev is not None:
+                ev[1].record()
+                self.timings.append(ev)
         return y, out
 
 

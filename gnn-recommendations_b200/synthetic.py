@@ -159,3 +159,19 @@ def synth_pairs_device(n_users: int, n_items: int, n_edges: int, seed: int, devi
             mask[drop] = False
             keys = keys[mask]
     return keys // n_items, keys % n_items
+
+
+def synth_pairs_host(n_users: int, n_items: int, n_edges: int, seed: int = 42):
+    """numpy twin of :func:`synth_pairs_device` (same law, no split) for CPU-side baselines."""
+    rng = np.random.default_rng(seed)
+    ucdf = _power_law_cdf(n_users, 0.6)
+    icdf = _power_law_cdf(n_items, 0.8)
+    keys = np.empty(0, dtype=np.int64)
+    while len(keys) < n_edges:
+        need = n_edges - len(keys)
+        m = int(need * 1.25) + 4096
+        keys = np.unique(np.concatenate([keys, _draw(rng, ucdf, m) * n_items + _draw(rng, icdf, m)]))
+        if len(keys) > n_edges:
+            keep = np.sort(rng.permutation(len(keys))[:n_edges])
+            keys = keys[keep]
+    return keys // n_items, keys % n_items
