@@ -83,6 +83,11 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src,
     asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem_src), "l"(pol)
                  : "memory");
 }
+__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gmem_src, uint64_t pol) {
+    unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+    asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 4, %2;" ::"r"(s), "l"(gmem_src), "l"(pol)
+                 : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {

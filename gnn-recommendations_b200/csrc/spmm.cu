@@ -150,105 +150,132 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) spmm_warp_rows(const SpmmAr
 }
 
 // ---------------------------------------------------------------------------------------------
-// long rows: one CTA per row, cp.async ring in shared memory
+// long rows: one CTA per row, warp-specialised cp.async pipeline through shared memory
+//
+//   4 producer warps  : per 64-entry chunk, copy the 64 gathered x rows (cp.async 16 B) into a
+//                       ring stage; producer 0 also streams the row's (col,val) arrays into a
+//                       second small ring 16 chunks ahead (cp.async 4 B), so gathers never wait
+//                       on the index stream.
+//   d/32 consumer warps: one feature per lane, run the fmaf chain out of shared memory
+//                       (conflict-free 128 B reads, values broadcast as float4).
+//   one __syncthreads per chunk hands a landed stage to the consumers and a drained one back.
 // ---------------------------------------------------------------------------------------------
-constexpr int kChunk = 32;  // neighbours per ring stage
-
 template <int D>
 struct LongCfg {
-    static constexpr int STAGES = D <= 128 ? 8 : 6;
-    static constexpr int STAGE_FLOATS = kChunk * D;
-    static constexpr size_t SMEM = (size_t)STAGES * (STAGE_FLOATS * 4 + kChunk * 4);
+    static constexpr int CONS = D / 32;
+    static constexpr int PROD = 4;
+    static constexpr int THREADS = (CONS + PROD) * 32;
+    static constexpr int CHUNK = 64;
+    static constexpr int STAGE_BYTES = CHUNK * D * 4;
+    static constexpr int STAGES = D <= 64 ? 8 : (D == 128 ? 6 : 3);
+    static constexpr int IDX_RING = 32;   // chunks of (col,val) resident in shared memory
+    static constexpr int IDX_AHEAD = 16;  // index chunks are requested this far ahead of their gathers
+    static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 2 * (size_t)IDX_RING * CHUNK * 4;
+    static_assert(STAGES - 1 <= IDX_AHEAD && STAGES + IDX_AHEAD + 1 <= IDX_RING, "index ring too small");
 };
 
 template <int D>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 1) spmm_long_rows(const SpmmArgs a) {
+__global__ void __launch_bounds__(LongCfg<D>::THREADS, 1) spmm_long_rows(const SpmmArgs a) {
     using L = LongCfg<D>;
-    constexpr int STAGES = L::STAGES;
-    constexpr int F4 = D / 4;
-    constexpr int CONS = D / 32;                      // consumer warps, one feature per lane
-    constexpr int NB_PER_WARP = kChunk / kWarpsPerCta;  // 4 neighbours per warp per stage
-    constexpr int ITEMS = (NB_PER_WARP * F4) / 32;    // 16-byte copies per lane per stage
-    constexpr unsigned kFull = 0xffffffffu;
-    static_assert(CONS >= 1 && CONS <= kWarpsPerCta, "feature dim");
-    static_assert(ITEMS >= 1, "feature dim");
+    constexpr int STAGES = L::STAGES, CH = L::CHUNK, F4 = D / 4, CONS = L::CONS, PROD = L::PROD;
+    constexpr int IR = L::IDX_RING, IA = L::IDX_AHEAD;
+    constexpr int NB = CH / PROD;            // entries per producer warp per chunk
+    constexpr int ITEMS = (NB * F4) / 32;    // 16-byte copies per producer lane per chunk
+    static_assert(ITEMS >= 1 && (NB * F4) % 32 == 0, "feature dim");
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float4 *xs = reinterpret_cast<float4 *>(smem_raw);                            // [STAGES][32][F4]
-    float *vs = reinterpret_cast<float *>(smem_raw + (size_t)STAGES * L::STAGE_FLOATS * 4);  // [STAGES][32]
+    float4 *xs = reinterpret_cast<float4 *>(smem_raw);                                  // [STAGES][CH][F4]
+    int *cs = reinterpret_cast<int *>(smem_raw + (size_t)STAGES * L::STAGE_BYTES);      // [IR][CH]
+    float *vs = reinterpret_cast<float *>(cs + IR * CH);                                // [IR][CH]
 
     const uint64_t pol_s = policy_evict_first(), pol_g = policy_evict_last();
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
+    const bool is_cons = warp < CONS;
+    const int p = warp - CONS;  // producer index, < 0 for consumers
     const int r = a.row_order[a.order_begin + blockIdx.x];
     const int start = a.indptr[r];
     const int len = a.indptr[r + 1] - start;
-    const int nchunks = (len + kChunk - 1) / kChunk;
+    const int nchunks = (len + CH - 1) / CH;
     const int *ci = a.indices + start;
     const float *cv = a.vals + start;
 
-    auto fetch = [&](int chunk, int &col, float &val) {
-        col = -1;
-        val = 0.f;
-        if (lane < NB_PER_WARP) {
-            const int idx = chunk * kChunk + warp * NB_PER_WARP + lane;
-            if (idx < len) {
-                col = ld_stream_i32(ci + idx, pol_s);
-                val = ld_stream_f32(cv + idx, pol_s);
+    auto issue_idx = [&](int chunk) {
+        if (p == 0 && chunk < nchunks) {
+            const int slot = chunk % IR;
+#pragma unroll
+            for (int t = 0; t < CH / 32; ++t) {
+                const int e = lane + 32 * t;
+                const int idx = chunk * CH + e;
+                if (idx < len) {
+                    cp_async4(cs + slot * CH + e, ci + idx, pol_s);
+                    cp_async4(vs + slot * CH + e, cv + idx, pol_s);
+                }
             }
         }
     };
-    auto issue = [&](int chunk, int col, float val) {
-        if (chunk < nchunks) {
+    auto issue_data = [&](int chunk) {
+        if (p >= 0 && chunk < nchunks) {
             const int stage = chunk % STAGES;
-            if (lane < NB_PER_WARP) vs[stage * kChunk + warp * NB_PER_WARP + lane] = val;
+            const int slot = chunk % IR;
+            const int nvalid = min(CH, len - chunk * CH);
 #pragma unroll
             for (int t = 0; t < ITEMS; ++t) {
                 const int item = lane + 32 * t;
-                const int nb = item / F4;
+                const int e = p * NB + item / F4;
                 const int f = item % F4;
-                const int cc = __shfl_sync(kFull, col, nb);
-                if (cc >= 0)
-                    cp_async16(xs + ((size_t)stage * kChunk + warp * NB_PER_WARP + nb) * F4 + f,
-                               a.x + (long long)cc * a.ldx4 + f, pol_g);
+                if (e < nvalid) {
+                    const int cc = cs[slot * CH + e];
+                    cp_async16(xs + ((size_t)stage * CH + e) * F4 + f, a.x + (long long)cc * a.ldx4 + f, pol_g);
+                }
             }
         }
-        cp_async_commit();
     };
 
-    // prologue: fetch the (col,val) of the first STAGES-1 chunks together, then fill the ring
-    int pc[STAGES - 1];
-    float pv[STAGES - 1];
+    // prologue: the first IA index chunks, then the first STAGES-1 data stages
+    for (int k = 0; k < IA; ++k) issue_idx(k);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
 #pragma unroll
-    for (int s = 0; s < STAGES - 1; ++s) fetch(s, pc[s], pv[s]);
-#pragma unroll
-    for (int s = 0; s < STAGES - 1; ++s) issue(s, pc[s], pv[s]);
-    int ncol;
-    float nval;
-    fetch(STAGES - 1, ncol, nval);
+    for (int s = 0; s < STAGES - 1; ++s) {
+        issue_data(s);
+        issue_idx(s + IA);
+        cp_async_commit();
+    }
 
     float acc = 0.f;
     for (int c = 0; c < nchunks; ++c) {
-        cp_async_wait<STAGES - 2>();  // this thread's copies of chunk c have landed
-        __syncthreads();              // everyone's have; everyone is done reading chunk c-1
-        issue(c + STAGES - 1, ncol, nval);  // refills the stage chunk c-1 used
-        fetch(c + STAGES, ncol, nval);
-        if (warp < CONS) {
+        cp_async_wait<STAGES - 2>();  // this thread's copies for chunk c (and its index chunk) landed
+        __syncthreads();              // everyone's did; consumers are done with chunk c-1
+        if (!is_cons) {
+            issue_data(c + STAGES - 1);  // refills the stage chunk c-1 used
+            issue_idx(c + STAGES - 1 + IA);
+        }
+        cp_async_commit();
+        if (is_cons) {
             const int stage = c % STAGES;
-            const float *xr = reinterpret_cast<const float *>(xs + (size_t)stage * kChunk * F4) + warp * 32 + lane;
-            const float *vr = vs + stage * kChunk;
-            const int n = min(kChunk, len - c * kChunk);
-            if (n == kChunk) {
+            const float *xr = reinterpret_cast<const float *>(xs + (size_t)stage * CH * F4) + warp * 32 + lane;
+            const float4 *vr = reinterpret_cast<const float4 *>(vs + (c % IR) * CH);
+            const int n = min(CH, len - c * CH);
+            if (n == CH) {
 #pragma unroll
-                for (int k = 0; k < kChunk; ++k) acc = __fmaf_rn(vr[k], xr[k * D], acc);
+                for (int k4 = 0; k4 < CH / 4; ++k4) {
+                    const float4 v = vr[k4];
+                    acc = __fmaf_rn(v.x, xr[(4 * k4 + 0) * D], acc);
+                    acc = __fmaf_rn(v.y, xr[(4 * k4 + 1) * D], acc);
+                    acc = __fmaf_rn(v.z, xr[(4 * k4 + 2) * D], acc);
+                    acc = __fmaf_rn(v.w, xr[(4 * k4 + 3) * D], acc);
+                }
             } else {
-                for (int k = 0; k < n; ++k) acc = __fmaf_rn(vr[k], xr[k * D], acc);
+                const float *v1 = reinterpret_cast<const float *>(vr);
+                for (int k = 0; k < n; ++k) acc = __fmaf_rn(v1[k], xr[k * D], acc);
             }
         }
     }
     cp_async_wait<0>();
 
-    if (warp < CONS) {
+    if (is_cons) {
         const int f = warp * 32 + lane;
         if (a.y) reinterpret_cast<float *>(a.y + (long long)r * a.ldy4)[f] = acc;
         if (a.out) {
@@ -307,7 +334,7 @@ static int launch(const SpmmArgs &base, int n_long, long long n_rows, int slot, 
         SpmmArgs la = base;
         la.order_begin = 0;
         la.order_end = n_long;
-        spmm_long_rows<D><<<n_long, kWarpsPerCta * 32, L::SMEM, side->stream>>>(la);
+        spmm_long_rows<D><<<n_long, L::THREADS, L::SMEM, side->stream>>>(la);
         GR_LAUNCH_CHECK();
         GR_CUDA_CHECK(cudaEventRecord(side->join, side->stream));
     }
