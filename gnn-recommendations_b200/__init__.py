@@ -10,5 +10,11 @@ from .base import BaseRecommender  # noqa: F401
 from .graph_builder import (NormAdjCSR, as_csr, build_bipartite_graph, convert_to_torch_sparse,  # noqa: F401
                             normalize_adjacency_matrix)
 from .lightgcn import LightGCN, lightgcn_propagate  # noqa: F401
+from .dataset import InteractionDataset  # noqa: F401
+from .evaluator import Evaluator, full_rank_topk  # noqa: F401
+from .losses import BPRLoss, bpr_fused  # noqa: F401
+from .metrics import compute_metrics_from_topk  # noqa: F401
+from .sampler import BprSampler  # noqa: F401
+from .trainer import Trainer  # noqa: F401
 
 __version__ = "0.1.0"

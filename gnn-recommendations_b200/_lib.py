@@ -32,6 +32,15 @@ SIGNATURES = {
     "gr_csr_normalize": (C.c_int, [_p, _p, _p, _p, _p, _i64, _i64, _i64, _i32, _p, _p, _p]),
     "gr_spmm_csr_f32": (C.c_int, [_p, _p, _p, _p, _i32, _i64, _i32, _p, _i64, _p, _i64, _p, _i64, _p, _i64,
                                   _f32, _i32, _p]),
+    "gr_sample_bpr_batch": (_i64, [_p, _p, _p, _p, _p, _i64, _i64, _i64, _p, _p, _p, _p, _p]),
+    "gr_bpr_workspace_bytes": (_sz, [_i64]),
+    "gr_bpr_fused": (C.c_int, [_p, _i64, _i64, _i64, _p, _p, _p, _i64, _i32, _f32, _p, _i64, _p, _p, _sz, _p]),
+    "gr_score_topk_workspace_bytes": (_sz, [_i64, _i32, _i32]),
+    "gr_score_topk_partial": (C.c_int, [_p, _i64, _p, _i64, _i32, _p, _i64, _i64, _i64, _p, _p, _i32, _i32,
+                                        _p, _p, _p]),
+    "gr_topk_merge": (C.c_int, [_p, _p, _i32, _i64, _i32, _p, _p, _p]),
+    "gr_score_topk": (C.c_int, [_p, _i64, _p, _i64, _i32, _p, _i64, _i64, _p, _p, _i32, _i32, _p, _p, _p, _sz,
+                                _p]),
 }
 
 

@@ -1,0 +1,118 @@
+"""Full-ranking evaluator — drop-in for src/evaluation/evaluator.py (Evaluator :27-124).
+
+The per-2048-user ``U @ I.T`` / python mask loop / ``torch.topk`` of the reference
+(evaluator.py:96-106) is one fused kernel (gr_score_topk): no score matrix, seen items masked
+from a CSR, lists in canonical order (score desc, item id asc).  The python ``iterrows`` builders
+of the ground truth / seen sets (evaluator.py:126-184) are vectorised.  The O(N^2) over-smoothing
+metrics the reference appends (evaluator.py:118-122) are analysis-only and not computed here.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from ._lib import check, lib, ptr, stream_ptr
+from .metrics import compute_metrics_from_topk
+
+
+def _pairs(data):
+    """DataFrame (userId,itemId) or list of dicts -> two int64 arrays (evaluator.py:168-183)."""
+    if data is None:
+        return np.zeros(0, np.int64), np.zeros(0, np.int64)
+    if isinstance(data, list):
+        u = [int(r.get("userId", r.get("user_id"))) for r in data]
+        i = [int(r.get("itemId", r.get("item_id"))) for r in data]
+        return np.asarray(u, dtype=np.int64), np.asarray(i, dtype=np.int64)
+    if isinstance(data, tuple):
+        return np.asarray(data[0], dtype=np.int64), np.asarray(data[1], dtype=np.int64)
+    return data["userId"].to_numpy(dtype=np.int64), data["itemId"].to_numpy(dtype=np.int64)
+
+
+def ground_truth_dict(data) -> Dict[int, List[int]]:
+    u, i = _pairs(data)
+    gt: Dict[int, List[int]] = {}
+    for a, b in zip(u.tolist(), i.tolist()):
+        gt.setdefault(a, []).append(b)
+    return gt
+
+
+def seen_csr(eval_users: Sequence[int], n_users: int, *pair_sets):
+    """Per eval row, the sorted unique item ids of the union of the given (user,item) sets."""
+    eval_users = np.asarray(eval_users, dtype=np.int64)
+    row_of = np.full(n_users, -1, dtype=np.int64)
+    row_of[eval_users] = np.arange(len(eval_users))
+    us = np.concatenate([p[0] for p in pair_sets]) if pair_sets else np.zeros(0, np.int64)
+    its = np.concatenate([p[1] for p in pair_sets]) if pair_sets else np.zeros(0, np.int64)
+    rows = row_of[us]
+    keep = rows >= 0
+    rows, its = rows[keep], its[keep]
+    n_it = int(its.max()) + 1 if len(its) else 1
+    key = np.unique(rows * n_it + its)
+    rows, its = key // n_it, key % n_it
+    indptr = np.zeros(len(eval_users) + 1, dtype=np.int64)
+    np.cumsum(np.bincount(rows, minlength=len(eval_users)), out=indptr[1:])
+    return indptr, its.astype(np.int32)
+
+
+def choose_splits(n_eval: int, n_items: int) -> int:
+    tiles = max(1, (n_eval + 63) // 64)
+    want = (2 * 148 + tiles - 1) // tiles
+    return int(max(1, min(want, 16, (n_items + 511) // 512)))
+
+
+def full_rank_topk(user_emb: torch.Tensor, item_emb: torch.Tensor, eval_users, seen_indptr, seen_items, k: int,
+                   n_splits: Optional[int] = None, return_scores: bool = False):
+    """Top-k item ids [n_eval, k] (int64, device) for the given eval users; canonical order."""
+    dev = user_emb.device
+    if dev.type != "cuda":
+        raise RuntimeError("full_rank_topk needs CUDA tensors (no CPU fallback)")
+    if user_emb.stride(1) != 1 or item_emb.stride(1) != 1:
+        user_emb, item_emb = user_emb.contiguous(), item_emb.contiguous()
+    eval_users = torch.as_tensor(eval_users, dtype=torch.int64).to(dev).contiguous()
+    n_eval, n_items, d = int(eval_users.numel()), int(item_emb.shape[0]), int(user_emb.shape[1])
+    if seen_indptr is not None:
+        seen_indptr = torch.as_tensor(seen_indptr, dtype=torch.int64).to(dev).contiguous()
+        seen_items = torch.as_tensor(seen_items, dtype=torch.int32).to(dev).contiguous()
+        if seen_items.numel() == 0:
+            seen_items = torch.zeros(1, dtype=torch.int32, device=dev)
+    n_splits = choose_splits(n_eval, n_items) if n_splits is None else int(n_splits)
+    ids = torch.empty((n_eval, k), dtype=torch.int64, device=dev)
+    scores = torch.empty((n_eval, k), dtype=torch.float32, device=dev)
+    l = lib()
+    ws_bytes = l.gr_score_topk_workspace_bytes(n_eval, k, n_splits)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        check(l.gr_score_topk(ptr(user_emb), user_emb.stride(0), ptr(item_emb), item_emb.stride(0), d,
+                              ptr(eval_users), n_eval, n_items, ptr(seen_indptr), ptr(seen_items), k, n_splits,
+                              ptr(ids), ptr(scores), ptr(ws), ws_bytes, stream_ptr()), "gr_score_topk")
+    return (ids, scores) if return_scores else ids
+
+
+class Evaluator:
+    def __init__(self, k_values: List[int] = [10, 20], device: Optional[torch.device] = None):
+        self.k_values = k_values
+        self.device = torch.device("cuda" if device is None else device)
+
+    def evaluate(self, model, dataset, test_data=None) -> Dict[str, float]:
+        model.eval()
+        if test_data is None:
+            test_data = dataset.test_data
+        with torch.no_grad():
+            adj = dataset.get_torch_adjacency(normalized=True).to(self.device)
+            user_emb, item_emb = model.get_all_embeddings(adj)
+            ground_truth = ground_truth_dict(test_data)
+            eval_users = sorted(ground_truth.keys())
+            if not eval_users:
+                return {}
+            max_k = max(self.k_values) if self.k_values else 10
+            # seen = train ∪ valid (evaluator.py:126-156)
+            ip, it = seen_csr(eval_users, user_emb.shape[0], _pairs(dataset.train_data), _pairs(dataset.valid_data))
+            topk = full_rank_topk(user_emb, item_emb, eval_users, ip, it, max_k).cpu()
+        return compute_metrics_from_topk(topk, eval_users, ground_truth, dataset.n_items, self.k_values)
+
+    def evaluate_batch(self, model, users, items, adj_matrix) -> torch.Tensor:
+        model.eval()
+        with torch.no_grad():
+            return model.predict(users, items, adj_matrix)

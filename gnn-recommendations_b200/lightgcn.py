@@ -81,9 +81,15 @@ class LightGCN(BaseRecommender):
     def _x0(self) -> torch.Tensor:
         return torch.cat([self.user_embedding.weight, self.item_embedding.weight], dim=0)
 
+    def propagate(self, adj_matrix) -> torch.Tensor:
+        """The final [N, d] embedding matrix (users first) before the user/item split — what
+        the fused BPR kernel and the sharded evaluators consume."""
+        if adj_matrix is None:
+            raise ValueError("adj_matrix должен быть передан для LightGCN")
+        return _LightGCNPropagate.apply(self._x0(), as_csr(adj_matrix), self.n_layers)
+
     def forward(self, adj_matrix) -> Tuple[torch.Tensor, torch.Tensor]:
-        csr = as_csr(adj_matrix)
-        x = _LightGCNPropagate.apply(self._x0(), csr, self.n_layers)
+        x = self.propagate(adj_matrix)
         user_emb, item_emb = torch.split(x, [self.n_users, self.n_items], dim=0)
         return user_emb, item_emb
 

@@ -1,0 +1,63 @@
+"""BPR batch sampler — drop-in for Trainer._sample_batch (src/training/trainer.py:146-197).
+
+The reference draws from torch's global CPU generator (one ``torch.randint`` for the B indices,
+then 1..11 scalar ``torch.randint`` calls per sample in a Python loop: 81.8 ms per 512-batch).
+This sampler consumes the SAME mt19937 stream — it reads the generator state with
+``torch.get_rng_state()``, runs the loop in C (libgr_b200.so: gr_sample_bpr_batch) and writes the
+advanced state back — so indices are bit-identical for a given ``torch.manual_seed`` and any
+later consumer of the global generator sees the stream where the reference would have left it.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from ._lib import GrError, lib
+
+_STATE_BYTES = 5056          # at::CPUGeneratorImplState
+_OFF_LEFT, _OFF_NEXT, _OFF_MT = 8, 16, 24
+
+
+class BprSampler:
+    def __init__(self, train_user, train_item, n_users: int, n_items: int):
+        self.train_user = np.ascontiguousarray(train_user, dtype=np.int64)
+        self.train_item = np.ascontiguousarray(train_item, dtype=np.int64)
+        if self.train_user.shape != self.train_item.shape:
+            raise ValueError("train_user / train_item length mismatch")
+        self.n_users, self.n_items = int(n_users), int(n_items)
+        # per-user sorted positive sets (trainer.py:169-172), CSR
+        order = np.lexsort((self.train_item, self.train_user))
+        self.pos_indptr = np.zeros(self.n_users + 1, dtype=np.int64)
+        np.cumsum(np.bincount(self.train_user, minlength=self.n_users), out=self.pos_indptr[1:])
+        self.pos_items = np.ascontiguousarray(self.train_item[order], dtype=np.int32)
+
+    def __len__(self):
+        return len(self.train_user)
+
+    def sample(self, batch_size: int, generator_state: torch.Tensor | None = None):
+        """Returns (users, pos, neg) int64 numpy arrays of length min(batch_size, n_train); neg is
+        one negative per sample (the reference's [B,1] column).  Uses and advances torch's global
+        CPU generator unless an explicit state tensor (as from torch.get_rng_state()) is given,
+        which is then advanced in place."""
+        own_state = generator_state is None
+        st = torch.get_rng_state() if own_state else generator_state
+        if st.numel() != _STATE_BYTES or st.dtype != torch.uint8:
+            raise GrError("unexpected torch CPU generator state layout")
+        buf = st.numpy()
+        b = min(int(batch_size), len(self.train_user))
+        users = np.empty(b, dtype=np.int64)
+        pos = np.empty(b, dtype=np.int64)
+        neg = np.empty(b, dtype=np.int64)
+        base = buf.ctypes.data
+        rc = lib().gr_sample_bpr_batch(
+            C.c_void_p(base + _OFF_MT), C.c_void_p(base + _OFF_LEFT), C.c_void_p(base + _OFF_NEXT),
+            self.train_user.ctypes.data, self.train_item.ctypes.data, len(self.train_user), self.n_items, b,
+            self.pos_indptr.ctypes.data, self.pos_items.ctypes.data,
+            users.ctypes.data, pos.ctypes.data, neg.ctypes.data)
+        if rc < 0:
+            raise GrError(f"gr_sample_bpr_batch failed (code {rc})")
+        if own_state:
+            torch.set_rng_state(st)
+        return users, pos, neg

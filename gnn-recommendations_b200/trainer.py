@@ -1,0 +1,269 @@
+"""Trainer — drop-in for src/training/trainer.py (Trainer :28-615).
+
+Same constructor, config keys, defaults and public methods (train, train_epoch, validate,
+save_checkpoint, load_checkpoint); the hot loop bodies run on the B200 kernels:
+
+  _sample_batch   C sampler on torch's own mt19937 stream (bit-identical indices)   trainer.py:146-197
+  train_epoch     per step: full-graph propagation (SpMM kernels) -> fused BPR kernel (gathers,
+                  B x B loss, gradient scatter) -> backward SpMMs -> clip_grad_norm_ -> Adam
+                  (the last two stay stock torch, as in the reference)                  trainer.py:199-281
+  validate        fused score + mask(train) + top-K kernel, K = max of validation_metrics   trainer.py:283-347
+
+The loss is accumulated on the device in float64 (the same double additions the reference does
+with ``loss.item()``) and read back once per epoch instead of once per step.
+"""
+from __future__ import annotations
+
+import time
+from pathlib import Path
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.optim as optim
+
+from .evaluator import _pairs, full_rank_topk, ground_truth_dict, seen_csr
+from .losses import BPRLoss, bpr_fused
+from .metrics import compute_metrics_from_topk
+from .sampler import BprSampler
+
+
+class Trainer:
+    def __init__(self, model, dataset, config: Dict, device: Optional[torch.device] = None):
+        self.model, self.dataset, self.config = model, dataset, config
+        self.model_name = config.get("model_name")
+        self.dataset_name = config.get("dataset_name")
+        self.device = torch.device("cuda") if device is None else torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("gnn-recommendations_b200.Trainer needs a CUDA device (no CPU fallback)")
+        self.model.to(self.device)
+        self._maybe_warm_start_embeddings()
+
+        lr = float(config.get("learning_rate", 0.001))
+        wd = float(config.get("weight_decay", 1e-4))
+        self.batch_size = int(config.get("batch_size", 2048))
+        self.epochs = int(config.get("epochs", 300))
+        self.eval_every = int(config.get("eval_every", 10))
+        self.negative_samples = int(config.get("negative_samples", 1))
+        self.optimizer = optim.Adam(self.model.parameters(), lr=lr, weight_decay=wd)
+        self.use_scheduler = config.get("use_scheduler", True)
+        self.warmup_epochs = int(config.get("warmup_epochs", 5))
+        self.base_lr = lr
+        self.scheduler = (optim.lr_scheduler.CosineAnnealingLR(self.optimizer, T_max=self.epochs - self.warmup_epochs,
+                                                               eta_min=lr * 0.01) if self.use_scheduler else None)
+        self.loss_fn = BPRLoss()
+        self.max_grad_norm = float(config.get("max_grad_norm", 1.0))
+        self.early_stopping = config.get("early_stopping", {})
+        self.patience = int(self.early_stopping.get("patience", 20))
+        self.min_delta = float(self.early_stopping.get("min_delta", 0.0001))
+        self.validation_metrics = config.get("validation_metrics", ["recall@10", "ndcg@10"])
+        self.early_stopping_metric = config.get("early_stopping_metric", "recall@10")
+        self.current_epoch, self.best_metric, self.best_epoch, self.patience_counter = 0, 0.0, 0, 0
+        self.train_losses: List[float] = []
+        self.valid_metrics: List[Dict[str, float]] = []
+        self.checkpoint_dir = Path(config.get("checkpoint_dir", "results/checkpoints"))
+        self.checkpoint_dir.mkdir(parents=True, exist_ok=True)
+        self._sampler: Optional[BprSampler] = None
+        self.step_times_ms: List[float] = []
+
+    # ------------------------------------------------------------------ data access
+    def _train_arrays(self) -> Tuple[np.ndarray, np.ndarray]:
+        train_data = self.dataset.train_data
+        if train_data is None:
+            train_file = self.dataset.processed_data_path / "train.txt"
+            if not train_file.exists():
+                raise ValueError("Train данные не найдены!")
+            import pandas as pd
+
+            train_data = pd.read_csv(train_file, sep="\t", header=None, names=["userId", "itemId"])
+        return _pairs(train_data)
+
+    def _get_sampler(self) -> BprSampler:
+        if self._sampler is None:       # trainer.py:169-172 builds its positive sets once, too
+            u, i = self._train_arrays()
+            self._sampler = BprSampler(u, i, self.model.n_users, self.dataset.n_items)
+        return self._sampler
+
+    def _sample_batch(self, train_data=None, n_items: Optional[int] = None):
+        """(users, pos_items, neg_items[B, 1]) on the device, bit-identical to the reference."""
+        if self.negative_samples != 1:
+            raise ValueError("negative_samples != 1 is shape-invalid in the reference's BPR loss "
+                             "([B] - [B, n_neg] broadcast, losses.py:44)")
+        u, p, n = self._get_sampler().sample(self.batch_size)
+        dev = self.device
+        return (torch.from_numpy(u).to(dev, non_blocking=True), torch.from_numpy(p).to(dev, non_blocking=True),
+                torch.from_numpy(n).to(dev, non_blocking=True).view(-1, 1))
+
+    # ------------------------------------------------------------------ training
+    def _propagated(self, adj) -> torch.Tensor:
+        if hasattr(self.model, "propagate"):
+            return self.model.propagate(adj)
+        user_emb, item_emb = self.model.get_all_embeddings(adj)
+        return torch.cat([user_emb, item_emb], dim=0)
+
+    def train_epoch(self) -> float:
+        self.model.train()
+        sampler = self._get_sampler()
+        adj = self.dataset.get_torch_adjacency(normalized=True).to(self.device)
+        n_batches_total = len(sampler) // self.batch_size + 1          # trainer.py:237
+        total = torch.zeros((), dtype=torch.float64, device=self.device)
+        n_batches = 0
+        for _ in range(n_batches_total):
+            users, pos, neg = self._sample_batch()
+            if users.numel() == 0:
+                continue
+            x = self._propagated(adj)
+            loss = bpr_fused(x, self.model.n_users, users, pos, neg)
+            if hasattr(self.model, "get_regularization_loss"):
+                loss = loss + self.model.get_regularization_loss()
+            self.optimizer.zero_grad()
+            loss.backward()
+            if self.max_grad_norm > 0:
+                torch.nn.utils.clip_grad_norm_(self.model.parameters(), self.max_grad_norm)
+            self.optimizer.step()
+            total += loss.detach().double()
+            n_batches += 1
+        return float(total.item()) / n_batches if n_batches > 0 else 0.0
+
+    # ------------------------------------------------------------------ validation
+    @staticmethod
+    def _parse_k_values(metrics_list: List[str]) -> List[int]:
+        ks = set()
+        for m in metrics_list:
+            if "@" in m:
+                try:
+                    ks.add(int(m.split("@")[-1]))
+                except ValueError:
+                    continue
+        return sorted(ks)
+
+    def validate(self) -> Dict[str, float]:
+        self.model.eval()
+        with torch.no_grad():
+            adj = self.dataset.get_torch_adjacency(normalized=True).to(self.device)
+            user_emb, item_emb = self.model.get_all_embeddings(adj)
+            valid_data = self.dataset.valid_data
+            if valid_data is None:
+                valid_file = self.dataset.processed_data_path / "valid.txt"
+                if not valid_file.exists():
+                    return {}
+                import pandas as pd
+
+                valid_data = pd.read_csv(valid_file, sep="\t", header=None, names=["userId", "itemId"])
+            ground_truth = ground_truth_dict(valid_data)
+            eval_users = sorted(ground_truth.keys())
+            if not eval_users:
+                return {}
+            k_values = self._parse_k_values(self.validation_metrics)
+            max_k = max(k_values) if k_values else 10
+            ip, it = seen_csr(eval_users, user_emb.shape[0], self._train_arrays())   # train only (:324)
+            topk = full_rank_topk(user_emb, item_emb, eval_users, ip, it, max_k).cpu()
+        return compute_metrics_from_topk(topk, eval_users, ground_truth, self.dataset.n_items,
+                                         k_values if k_values else [10])
+
+    # ------------------------------------------------------------------ warm start / export
+    def _maybe_warm_start_embeddings(self):
+        ws = self.config.get("warm_start", {})
+        if not ws or not ws.get("enabled", False):
+            return
+        apply_to = ws.get("apply_to")
+        if apply_to and self.model_name and apply_to != self.model_name:
+            return
+        path = ws.get("embeddings_path")
+        if not path:
+            raise ValueError("warm_start.enabled=true, but embeddings_path is not set")
+        ckpt = torch.load(path, map_location=self.device)
+        ue = ie = None
+        if isinstance(ckpt, dict):
+            if "user_embedding" in ckpt and "item_embedding" in ckpt:
+                ue, ie = ckpt["user_embedding"], ckpt["item_embedding"]
+            elif "model_state_dict" in ckpt:
+                sd = ckpt["model_state_dict"]
+                if "user_embedding.weight" in sd and "item_embedding.weight" in sd:
+                    ue, ie = sd["user_embedding.weight"], sd["item_embedding.weight"]
+        if ue is None or ie is None:
+            raise ValueError("Warm-start embeddings not found in file. "
+                             "Expected keys: user_embedding/item_embedding or model_state_dict.")
+        if not hasattr(self.model, "user_embedding") or not hasattr(self.model, "item_embedding"):
+            raise ValueError("Model does not expose user_embedding/item_embedding for warm-start.")
+        for name, got, want in (("user_embedding", ue, self.model.user_embedding.weight),
+                                ("item_embedding", ie, self.model.item_embedding.weight)):
+            if got.shape != want.shape:
+                raise ValueError(f"{name} shape mismatch: got {tuple(got.shape)}, expected {tuple(want.shape)}")
+        with torch.no_grad():
+            self.model.user_embedding.weight.copy_(ue.to(self.device))
+            self.model.item_embedding.weight.copy_(ie.to(self.device))
+
+    def _maybe_export_embeddings(self):
+        cfg = self.config.get("export_embeddings", {})
+        if not cfg or not cfg.get("enabled", False):
+            return
+        apply_to = cfg.get("apply_to")
+        if apply_to and self.model_name and apply_to != self.model_name:
+            return
+        path = cfg.get("path")
+        if not path:
+            raise ValueError("export_embeddings.enabled=true, but path is not set")
+        adj = self.dataset.get_torch_adjacency(normalized=True).to(self.device)
+        with torch.no_grad():
+            ue, ie = self.model.get_all_embeddings(adj)
+        payload = {"user_embedding": ue.detach().cpu(), "item_embedding": ie.detach().cpu(),
+                   "source_model": self.model_name, "dataset": self.dataset_name,
+                   "embedding_dim": int(ue.size(1)), "n_users": int(ue.size(0)), "n_items": int(ie.size(0))}
+        path = Path(path)
+        path.parent.mkdir(parents=True, exist_ok=True)
+        torch.save(payload, path)
+
+    def _get_orthogonality_metrics(self) -> Dict[str, float]:
+        if not hasattr(self.model, "get_orthogonality_metrics"):
+            return {}
+        with torch.no_grad():
+            m = self.model.get_orthogonality_metrics()
+        return {k: float(v.detach().cpu()) for k, v in m.items()}
+
+    # ------------------------------------------------------------------ outer loop
+    def train(self) -> Dict:
+        start = time.time()
+        for epoch in range(1, self.epochs + 1):
+            self.current_epoch = epoch
+            if epoch <= self.warmup_epochs:                      # linear warm-up (trainer.py:492-496)
+                for g in self.optimizer.param_groups:
+                    g["lr"] = self.base_lr * (epoch / self.warmup_epochs)
+            elif self.scheduler is not None:
+                self.scheduler.step()
+            train_loss = self.train_epoch()
+            self.train_losses.append(train_loss)
+            if epoch % self.eval_every == 0 or epoch == 1:
+                vm = self.validate()
+                self.valid_metrics.append(vm)
+                cur = vm.get(self.early_stopping_metric, 0.0)
+                print(f"Epoch {epoch:3d}/{self.epochs} | LR: {self.optimizer.param_groups[0]['lr']:.6f} | "
+                      f"Train Loss: {train_loss:.4f} | {self.early_stopping_metric}: {cur:.4f} | "
+                      f"NDCG@10: {vm.get('ndcg@10', 0.0):.4f}")
+                orth = self._get_orthogonality_metrics()
+                if orth:
+                    print("Orthogonality: " + " | ".join(f"{k}={v:.2e}" for k, v in orth.items()))
+                if cur > self.best_metric + self.min_delta:
+                    self.best_metric, self.best_epoch, self.patience_counter = cur, epoch, 0
+                    self.save_checkpoint(epoch, vm)
+                else:
+                    self.patience_counter += 1
+                if self.patience_counter >= self.patience:
+                    print(f"Early stopping at epoch {epoch}; best {self.best_metric:.4f} @ {self.best_epoch}")
+                    break
+        training_time = time.time() - start
+        self._maybe_export_embeddings()
+        return {"best_metric": self.best_metric, "best_epoch": self.best_epoch, "training_time": training_time,
+                "train_losses": self.train_losses, "valid_metrics": self.valid_metrics}
+
+    def save_checkpoint(self, epoch: int, metrics: Dict[str, float]):
+        torch.save({"epoch": epoch, "model_state_dict": self.model.state_dict(),
+                    "optimizer_state_dict": self.optimizer.state_dict(), "metrics": metrics,
+                    "best_metric": self.best_metric}, self.checkpoint_dir / f"checkpoint_epoch_{epoch}.pt")
+
+    def load_checkpoint(self, checkpoint_path: Path):
+        ckpt = torch.load(checkpoint_path, map_location=self.device)
+        self.model.load_state_dict(ckpt["model_state_dict"])
+        self.optimizer.load_state_dict(ckpt["optimizer_state_dict"])
+        self.current_epoch = ckpt["epoch"]
+        self.best_metric = ckpt.get("best_metric", 0.0)

@@ -115,6 +115,61 @@ int gr_spmm_csr_f32(const int32_t *indptr, const int32_t *indices, const float *
                     int64_t ldx, float *y, int64_t ldy, const float *addend, int64_t lda, float *out,
                     int64_t ldo, float scale, int32_t scale_mode, void *stream);
 
+/* ------------------------------------------------------------------------------------------
+ * BPR step
+ * ------------------------------------------------------------------------------------------ */
+
+/* HOST function.  Replaces Trainer._sample_batch (src/training/trainer.py:146-197) for
+ * negative_samples = 1: B indices with replacement, then per sample one negative draw plus up
+ * to 10 redraws while the draw is a known positive of that user (the 10th accepted unchecked).
+ * Consumes the mt19937 stream of torch's global CPU generator: mt_state (624 uint64 words),
+ * mt_left, mt_next are the fields of torch.get_rng_state() (at::mt19937 layout) and are advanced
+ * in place; torch.randint(0, n) == mt() % n.  pos_indptr/pos_items: per-user SORTED positives
+ * (trainer.py:169-172).  Returns the number of 32-bit draws consumed (>= 0) or GR_ERR_*. */
+int64_t gr_sample_bpr_batch(uint64_t *mt_state_host, int32_t *mt_left_host, uint64_t *mt_next_host,
+                            const int64_t *train_user_host, const int64_t *train_item_host, int64_t n_train,
+                            int64_t n_items, int64_t batch, const int64_t *pos_indptr_host,
+                            const int32_t *pos_items_host, int64_t *users_host, int64_t *pos_host,
+                            int64_t *neg_host);
+
+/* Replaces the step body of Trainer.train_epoch (trainer.py:257-264: gathers + row dots),
+ * BPRLoss.forward (src/training/losses.py:44-53, the [B] - [B,1] -> [B,B] broadcast form) and the
+ * autograd backward through both, in one cooperative kernel:
+ *   loss[0]  = mean_{i,j} softplus(n_i - p_j)
+ *   grad    += grad_scale * dloss/d emb        (rows of users/pos/neg; duplicates accumulate)
+ * emb / grad: [n_users + n_items, d] propagated embeddings, users first; grad must be zeroed by
+ * the caller.  workspace: gr_bpr_workspace_bytes(batch) bytes, zeroed once before first use. */
+size_t gr_bpr_workspace_bytes(int64_t batch);
+int gr_bpr_fused(const float *emb, int64_t ld, int64_t n_users, int64_t n_items, const int64_t *users,
+                 const int64_t *pos, const int64_t *neg, int64_t batch, int32_t d, float grad_scale, float *grad,
+                 int64_t ldg, float *loss, void *workspace, size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Full-ranking evaluation
+ * ------------------------------------------------------------------------------------------ */
+
+/* Replaces the score / mask / top-K loop (src/evaluation/evaluator.py:96-106,
+ * src/training/trainer.py:327-337): S = U_b I^T as k-sequential fmaf chains (bit-identical to the
+ * reference's CPU sgemm), seen items (CSR over eval rows, sorted GLOBAL item ids) -> -inf, top-k
+ * ordered by (score desc, item id asc).  No score matrix is materialised.  k <= 64, d % 16 == 0.
+ *
+ * gr_score_topk_partial: lists for the item id range [item_lo, item_hi) only (item_emb row 0 is
+ *   item_lo), split into n_splits sub-ranges -> part_scores / part_ids [n_splits][n_eval][k]
+ *   (short lists padded with id -1).  This is the per-GPU step of the item-sharded evaluation.
+ * gr_topk_merge: merges n_parts partial lists per row (ids disjoint) into the final top-k.
+ * gr_score_topk: both, on one GPU.  workspace: gr_score_topk_workspace_bytes(n_eval, k, n_splits). */
+size_t gr_score_topk_workspace_bytes(int64_t n_eval, int32_t k, int32_t n_splits);
+int gr_score_topk_partial(const float *user_emb, int64_t ldu, const float *item_emb, int64_t ldi, int32_t d,
+                          const int64_t *eval_users, int64_t n_eval, int64_t item_lo, int64_t item_hi,
+                          const int64_t *seen_indptr, const int32_t *seen_items, int32_t k, int32_t n_splits,
+                          float *part_scores, int32_t *part_ids, void *stream);
+int gr_topk_merge(const float *part_scores, const int32_t *part_ids, int32_t n_parts, int64_t n_eval, int32_t k,
+                  int64_t *out_ids, float *out_scores, void *stream);
+int gr_score_topk(const float *user_emb, int64_t ldu, const float *item_emb, int64_t ldi, int32_t d,
+                  const int64_t *eval_users, int64_t n_eval, int64_t n_items, const int64_t *seen_indptr,
+                  const int32_t *seen_items, int32_t k, int32_t n_splits, int64_t *topk_ids, float *topk_scores,
+                  void *workspace, size_t workspace_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

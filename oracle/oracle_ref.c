@@ -108,6 +108,17 @@ uint32_t oracle_mt_next(oracle_mt19937 *g) {
     return y;
 }
 
+/* torch.randint(0, range): one 32-bit draw for range < 2^28, else (hi << 32 | lo) % range. */
+static int64_t oracle_draw_below(oracle_mt19937 *g, int64_t range, int64_t *draws) {
+    if (range >= ((int64_t)1 << 28)) {
+        const uint64_t hi = oracle_mt_next(g), lo = oracle_mt_next(g);
+        *draws += 2;
+        return (int64_t)(((hi << 32) | lo) % (uint64_t)range);
+    }
+    *draws += 1;
+    return (int64_t)(oracle_mt_next(g) % (uint32_t)range);
+}
+
 /* Trainer._sample_batch (src/training/trainer.py:146-197), negative_samples = 1.
  * pos sets given as CSR over users with SORTED item ids.  Returns draws consumed. */
 static int in_sorted(const int32_t *a, int64_t n, int32_t v) {
@@ -121,21 +132,18 @@ int64_t oracle_sample_batch(oracle_mt19937 *g, const int64_t *train_u, const int
     int64_t draws = 0;
     if (batch > n_train) batch = n_train;
     for (int64_t b = 0; b < batch; ++b) {               /* indices = randint(0, len(train), (B,))  :162 */
-        const int64_t idx = oracle_mt_next(g) % (uint32_t)n_train;
+        const int64_t idx = oracle_draw_below(g, n_train, &draws);
         users[b] = train_u[idx];
         pos[b] = train_i[idx];
-        ++draws;
     }
     for (int64_t b = 0; b < batch; ++b) {               /* :174-187 */
         const int64_t u = users[b];
         const int32_t *ps = pos_items + pos_indptr[u];
         const int64_t np_ = pos_indptr[u + 1] - pos_indptr[u];
-        int64_t cand = oracle_mt_next(g) % (uint32_t)n_items;
-        ++draws;
+        int64_t cand = oracle_draw_below(g, n_items, &draws);
         for (int t = 0; t < 10; ++t) {
             if (!in_sorted(ps, np_, (int32_t)cand)) break;
-            cand = oracle_mt_next(g) % (uint32_t)n_items;
-            ++draws;
+            cand = oracle_draw_below(g, n_items, &draws);
         }
         neg[b] = cand;
     }

@@ -220,19 +220,23 @@ def gs_forward(adj_coo, user_w, item_w, conn_skew, conn_perm, local_skew, local_
 # --------------------------------------------------------------------------------------
 class TorchCpuMt19937:
     """The global CPU generator ``torch.manual_seed(seed)`` creates: std::mt19937
-    seeded with init_genrand(seed & 0xffffffff); ``torch.randint(0, n, ...)`` with
-    n < 2^32 consumes one 32-bit output per element and returns ``out % n``
-    (verified against torch in tests/test_oracle_golden.py)."""
+    seeded with init_genrand(seed & 0xffffffff); ``torch.randint(0, n, ...)`` consumes one
+    32-bit output per element and returns ``out % n`` for n < 2^28, and two outputs
+    (``(first << 32 | second) % n``) for n >= 2^28 (torch 2.11; verified against torch in
+    tests/test_oracle_golden.py)."""
 
     def __init__(self, seed: int):
         self._bg = np.random.MT19937()
         self._bg._legacy_seeding(int(seed) & 0xFFFFFFFF)
 
     def randint(self, n: int, size: int) -> np.ndarray:
+        if n >= 1 << 28:
+            raw = self._bg.random_raw(2 * size).astype(np.uint64)
+            return (((raw[0::2] << np.uint64(32)) | raw[1::2]) % np.uint64(n)).astype(np.int64)
         return (self._bg.random_raw(size).astype(np.uint64) % np.uint64(n)).astype(np.int64)
 
     def randint1(self, n: int) -> int:
-        return int(self._bg.random_raw() % n)
+        return int(self.randint(n, 1)[0])
 
 
 def sample_batch(rng: TorchCpuMt19937, train_u: np.ndarray, train_i: np.ndarray, n_items: int,

@@ -1,0 +1,196 @@
+"""GPU parity of the BPR step, the full-ranking top-K and the Trainer / Evaluator drop-ins against
+the reference's golden outputs and the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+import gnn_recommendations_b200 as g
+from gnn_recommendations_b200.evaluator import ground_truth_dict, seen_csr
+from oracle import coracle
+from oracle import pyoracle as po
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def dataset_from(tiny):
+    return g.InteractionDataset((tiny["train_u"], tiny["train_i"]), (tiny["valid_u"], tiny["valid_i"]),
+                                (tiny["test_u"], tiny["test_i"]), int(tiny["n_users"]), int(tiny["n_items"]),
+                                device=DEV)
+
+
+def lightgcn_from(tiny, tag="lightgcn", d=64, L=3):
+    m = g.LightGCN(int(tiny["n_users"]), int(tiny["n_items"]), d, L, 0.1)
+    m.load_state_dict({"user_embedding.weight": torch.from_numpy(tiny[f"{tag}/user_embedding.weight"]),
+                       "item_embedding.weight": torch.from_numpy(tiny[f"{tag}/item_embedding.weight"])})
+    return m.to(DEV)
+
+
+# ----------------------------------------------------------------------------- fused BPR kernel
+def test_bpr_fused_loss_and_gradient_vs_reference(tiny):
+    emb = torch.from_numpy(np.concatenate([tiny["lightgcn/out_user"], tiny["lightgcn/out_item"]])).to(DEV)
+    emb.requires_grad_(True)
+    us, ps, ns = (torch.from_numpy(tiny[f"batch0/{k}"]).to(DEV) for k in ("users", "pos", "neg"))
+    loss = g.bpr_fused(emb, int(tiny["n_users"]), us, ps, ns)
+    loss.backward()
+    ref = float(tiny["step0/loss"])
+    assert abs(float(loss) - ref) <= 1e-5 * abs(ref)
+    nu = int(tiny["n_users"])
+    np.testing.assert_allclose(emb.grad[:nu].cpu().numpy(), tiny["step0/gprop_user"], rtol=1e-4, atol=1e-9)
+    np.testing.assert_allclose(emb.grad[nu:].cpu().numpy(), tiny["step0/gprop_item"], rtol=1e-4, atol=1e-9)
+    # float64 closed form (tighter: independent of the reference's fp32 summation order)
+    l64, gU, gI, _, _ = po.bpr_closed_form(tiny["lightgcn/out_user"], tiny["lightgcn/out_item"], tiny["batch0/users"],
+                                           tiny["batch0/pos"], tiny["batch0/neg"])
+    assert abs(float(loss) - l64) <= 2e-6 * abs(l64)
+    np.testing.assert_allclose(emb.grad[:nu].cpu().numpy(), gU, rtol=2e-5, atol=1e-10)
+    np.testing.assert_allclose(emb.grad[nu:].cpu().numpy(), gI, rtol=2e-5, atol=1e-10)
+
+
+@pytest.mark.parametrize("b,d", [(1, 64), (7, 32), (512, 128), (2048, 256)])
+def test_bpr_fused_shapes_and_duplicates(b, d):
+    rng = np.random.default_rng(b)
+    nu, ni = 50, 40
+    emb = (rng.standard_normal((nu + ni, d)) * 0.3).astype(np.float32)
+    us, ps, ns = rng.integers(0, nu, b), rng.integers(0, ni, b), rng.integers(0, ni, b)   # heavy duplication
+    e = torch.from_numpy(emb).to(DEV).requires_grad_(True)
+    loss = g.bpr_fused(e, nu, torch.from_numpy(us), torch.from_numpy(ps), torch.from_numpy(ns).view(-1, 1))
+    (loss * 2.0).backward()                                   # upstream gradient is honoured
+    l64, gU, gI, _, _ = po.bpr_closed_form(emb[:nu], emb[nu:], us, ps, ns)
+    assert abs(float(loss) - l64) <= 1e-5 * abs(l64)
+    got = e.grad.cpu().numpy()
+    scale = max(np.abs(gU).max(), np.abs(gI).max())
+    np.testing.assert_allclose(got[:nu], 2 * gU, rtol=1e-4, atol=1e-5 * scale)
+    np.testing.assert_allclose(got[nu:], 2 * gI, rtol=1e-4, atol=1e-5 * scale)
+
+
+def test_bpr_fused_rejects_multiple_negatives():
+    e = torch.zeros(10, 64, device=DEV)
+    with pytest.raises(ValueError):
+        g.bpr_fused(e, 5, torch.zeros(4, dtype=torch.int64), torch.zeros(4, dtype=torch.int64),
+                    torch.zeros((4, 2), dtype=torch.int64))
+
+
+# ----------------------------------------------------------------------------- top-K
+def seen_from(tiny, with_valid=True):
+    sets = [(tiny["train_u"], tiny["train_i"])] + ([(tiny["valid_u"], tiny["valid_i"])] if with_valid else [])
+    return seen_csr(tiny["eval/users"], int(tiny["n_users"]), *sets)
+
+
+@pytest.mark.parametrize("n_splits", [1, 2, 3])
+def test_topk_bit_exact_vs_reference(tiny, n_splits):
+    ue, ie = torch.from_numpy(tiny["eval/user_emb"]).to(DEV), torch.from_numpy(tiny["eval/item_emb"]).to(DEV)
+    ip, it = seen_from(tiny)
+    ids, sc = g.full_rank_topk(ue, ie, tiny["eval/users"], ip, it, 20, n_splits=n_splits, return_scores=True)
+    assert np.array_equal(ids.cpu().numpy(), tiny["eval/topk20_canonical"])
+    # scores are the reference's scores bit-for-bit (k-sequential fmaf chain == CPU sgemm)
+    ref_scores = np.take_along_axis(tiny["eval/scores"], tiny["eval/topk20_canonical"], axis=1)
+    assert np.array_equal(sc.cpu().numpy().view(np.uint32), ref_scores.view(np.uint32))
+
+
+def test_topk_exact_ties_break_by_item_id(tiny):
+    ue = torch.from_numpy(tiny["eval/user_emb"]).to(DEV)
+    ie = torch.from_numpy(tiny["eval/tie_item_emb"]).to(DEV)
+    ip, it = seen_from(tiny)
+    for n_splits in (1, 2):
+        ids = g.full_rank_topk(ue, ie, tiny["eval/users"], ip, it, 20, n_splits=n_splits)
+        assert np.array_equal(ids.cpu().numpy(), tiny["eval/tie_topk20_canonical"])
+
+
+def test_topk_fewer_than_k_unmasked_items(tiny):
+    # a user who has seen all but 5 items: the list is completed with -inf entries in id order
+    ue, ie = torch.from_numpy(tiny["eval/user_emb"]).to(DEV), torch.from_numpy(tiny["eval/item_emb"]).to(DEV)
+    eu = tiny["eval/users"][:4]
+    ni = int(tiny["n_items"])
+    seen = {int(u): set() for u in eu}
+    for u, i in zip(np.concatenate([tiny["train_u"], tiny["valid_u"]]).tolist(),
+                    np.concatenate([tiny["train_i"], tiny["valid_i"]]).tolist()):
+        if u in seen:
+            seen[u].add(i)
+    seen[int(eu[0])] = set(range(ni)) - {3, 17, 42, 99, 150}
+    indptr, items = [0], []
+    for u in eu:
+        items += sorted(seen[int(u)])
+        indptr.append(len(items))
+    for n_splits in (1, 2):
+        ids = g.full_rank_topk(ue, ie, eu, np.asarray(indptr), np.asarray(items, dtype=np.int32), 20,
+                               n_splits=n_splits)
+        assert np.array_equal(ids.cpu().numpy(), tiny["eval/short_topk20_canonical"])
+
+
+@pytest.mark.parametrize("d,k,n_items", [(32, 1, 130), (64, 50, 1000), (128, 64, 257), (256, 10, 5000)])
+def test_topk_random_vs_c_oracle(d, k, n_items):
+    rng = np.random.default_rng(d + k)
+    nu = 150
+    ue = rng.standard_normal((nu, d)).astype(np.float32)
+    ie = rng.standard_normal((n_items, d)).astype(np.float32)
+    ie[rng.integers(0, n_items, 20)] = ie[0]                       # exact duplicates -> exact ties
+    eu = np.sort(rng.choice(nu, 100, replace=False))
+    indptr, items = [0], []
+    for _ in eu:
+        items += sorted(rng.choice(n_items, rng.integers(0, min(60, n_items - k)), replace=False).tolist())
+        indptr.append(len(items))
+    indptr, items = np.asarray(indptr), np.asarray(items, dtype=np.int32)
+    want = coracle.score_topk(ue, ie, eu, indptr, items, k)
+    ids = g.full_rank_topk(torch.from_numpy(ue).to(DEV), torch.from_numpy(ie).to(DEV), eu, indptr, items, k)
+    assert np.array_equal(ids.cpu().numpy(), want)
+    ids2 = g.full_rank_topk(torch.from_numpy(ue).to(DEV), torch.from_numpy(ie).to(DEV), eu, None, None, k)
+    assert np.array_equal(ids2.cpu().numpy(), coracle.score_topk(ue, ie, eu, None, None, k))
+
+
+def test_topk_c1_shape_vs_reference(c1gold, c1split):
+    """Full C1 size: graph build -> propagation -> top-20, end to end on the GPU, must reproduce the
+    reference's canonical lists for all 6040 users and its Recall/NDCG."""
+    nu, ni = c1split["n_users"], c1split["n_items"]
+    tu, ti = c1split["train"]
+    csr = g.NormAdjCSR.from_pairs(tu, ti, nu, ni, device=DEV, dis_lut=c1gold["dis_lut"])
+    rng = np.random.default_rng(42)
+    uw = (rng.standard_normal((nu, 64)) * 0.1).astype(np.float32)
+    iw = (rng.standard_normal((ni, 64)) * 0.1).astype(np.float32)
+    m = g.LightGCN(nu, ni, 64, 3, 0.1)
+    m.load_state_dict({"user_embedding.weight": torch.from_numpy(uw), "item_embedding.weight": torch.from_numpy(iw)})
+    m.to(DEV)
+    with torch.no_grad():
+        ue, ie = m(csr)
+    gt = ground_truth_dict(c1split["test"])
+    eu = sorted(gt)
+    ip, it = seen_csr(eu, nu, c1split["train"], c1split["valid"])
+    ids = g.full_rank_topk(ue, ie, eu, ip, it, 20).cpu()
+    assert np.array_equal(ids.numpy(), c1gold["topk20_canonical"].astype(np.int64))
+    met = g.compute_metrics_from_topk(ids, eu, gt, ni, [10, 20])
+    for k in ("recall@20", "ndcg@20", "recall@10", "ndcg@10"):
+        assert abs(met[k] - float(c1gold[f"metrics/{k}"])) <= 1e-12, k
+
+
+# ----------------------------------------------------------------------------- Trainer / Evaluator
+CFG = {"learning_rate": 1e-3, "weight_decay": 1e-4, "batch_size": 512, "epochs": 1, "eval_every": 1,
+       "use_scheduler": False, "warmup_epochs": 0, "max_grad_norm": 1.0, "negative_samples": 1,
+       "validation_metrics": ["recall@10", "recall@20", "recall@50", "ndcg@10", "ndcg@20", "ndcg@50"]}
+
+
+def test_trainer_epoch_validate_evaluate_vs_reference(tiny, tmp_path):
+    ds = dataset_from(tiny)
+    torch.manual_seed(42)
+    m = g.LightGCN(int(tiny["n_users"]), int(tiny["n_items"]), embedding_dim=64, n_layers=3, init_scale=0.1)
+    # same-seed construction reproduces the reference's initial parameters
+    assert np.array_equal(m.user_embedding.weight.detach().numpy(), tiny["lightgcn/user_embedding.weight"])
+    tr = g.Trainer(m, ds, dict(CFG, checkpoint_dir=str(tmp_path / "ckpt")), device=torch.device(DEV))
+    torch.manual_seed(123)
+    us, ps, ns = tr._sample_batch()
+    assert np.array_equal(us.cpu().numpy(), tiny["batch0/users"]) and np.array_equal(ns.cpu().numpy(), tiny["batch0/neg"])
+    torch.manual_seed(123)
+    loss = tr.train_epoch()                                     # 11 steps of sample/fwd/BPR/bwd/clip/Adam
+    assert abs(loss - float(tiny["epoch/loss"])) <= 1e-5 * abs(float(tiny["epoch/loss"]))
+    np.testing.assert_allclose(m.user_embedding.weight.detach().cpu().numpy(), tiny["epoch/user_w"], rtol=1e-4, atol=2e-6)
+    np.testing.assert_allclose(m.item_embedding.weight.detach().cpu().numpy(), tiny["epoch/item_w"], rtol=1e-4, atol=2e-6)
+    # validate / evaluate on the REFERENCE's post-epoch weights so the metric comparison is exact
+    m.load_state_dict({"user_embedding.weight": torch.from_numpy(tiny["epoch/user_w"]),
+                       "item_embedding.weight": torch.from_numpy(tiny["epoch/item_w"])})
+    vm = tr.validate()
+    for k, v in vm.items():
+        assert abs(v - float(tiny[f"validate/{k}"])) <= 1e-12, k
+    em = g.Evaluator(k_values=[10, 20], device=torch.device(DEV)).evaluate(m, ds, ds.test_data)
+    for k, v in em.items():
+        assert abs(v - float(tiny[f"evaluate/{k}"])) <= 1e-12, k
+    tr.save_checkpoint(1, vm)
+    tr.load_checkpoint(tmp_path / "ckpt" / "checkpoint_epoch_1.pt")
+    assert tr.current_epoch == 1

@@ -1,0 +1,117 @@
+"""CPU-only tests of the host-side logic around the kernels: sampler (host C function), metrics,
+seen-set construction, row partition, dataset boundary."""
+import numpy as np
+import pytest
+import torch
+
+import gnn_recommendations_b200 as g
+from gnn_recommendations_b200.dist import RowPartition
+from gnn_recommendations_b200.evaluator import ground_truth_dict, seen_csr
+from oracle import pyoracle as po
+
+
+def test_sampler_bit_exact_vs_reference_trainer(tiny):
+    s = g.BprSampler(tiny["train_u"], tiny["train_i"], int(tiny["n_users"]), int(tiny["n_items"]))
+    torch.manual_seed(123)
+    for b in range(3):
+        u, p, n = s.sample(512)
+        assert np.array_equal(u, tiny[f"batch{b}/users"])
+        assert np.array_equal(p, tiny[f"batch{b}/pos"])
+        assert np.array_equal(n, tiny[f"batch{b}/neg"].reshape(-1))
+    # the global generator is left exactly where the reference's python loop leaves it
+    nxt = torch.randint(0, 1 << 30, (4,))
+    torch.manual_seed(123)
+    gen = po.TorchCpuMt19937(123)
+    ps = po.positive_sets(tiny["train_u"], tiny["train_i"])
+    for _ in range(3):
+        po.sample_batch(gen, tiny["train_u"], tiny["train_i"], int(tiny["n_items"]), 512, ps)
+    assert np.array_equal(nxt.numpy(), gen.randint(1 << 30, 4))
+
+
+def test_sampler_c1_shape(c1gold, c1split):
+    tu, ti = c1split["train"]
+    s = g.BprSampler(tu, ti, c1split["n_users"], c1split["n_items"])
+    torch.manual_seed(2024)
+    for b in range(2):
+        u, p, n = s.sample(512)
+        assert np.array_equal(u, c1gold[f"batch{b}/users"])
+        assert np.array_equal(p, c1gold[f"batch{b}/pos"])
+        assert np.array_equal(n, c1gold[f"batch{b}/neg"].reshape(-1))
+
+
+def test_sampler_many_batches_cross_twist_boundary(tiny):
+    # > 624 draws per batch: the mt19937 block regeneration must agree with torch across many batches
+    s = g.BprSampler(tiny["train_u"], tiny["train_i"], int(tiny["n_users"]), int(tiny["n_items"]))
+    ps = po.positive_sets(tiny["train_u"], tiny["train_i"])
+    torch.manual_seed(7)
+    gen = po.TorchCpuMt19937(7)
+    for _ in range(12):
+        u, p, n = s.sample(300)
+        ou, op, on = po.sample_batch(gen, tiny["train_u"], tiny["train_i"], int(tiny["n_items"]), 300, ps)
+        assert np.array_equal(u, ou) and np.array_equal(p, op) and np.array_equal(n, on.reshape(-1))
+
+
+def test_sampler_dense_user_hits_the_ten_redraw_cap():
+    # user 0 has every item but one as a positive: most draws are rejected, the 10th redraw is kept unchecked
+    n_items = 12
+    tu = np.zeros(n_items - 1, dtype=np.int64)
+    ti = np.arange(n_items - 1, dtype=np.int64)
+    s = g.BprSampler(tu, ti, 1, n_items)
+    ps = po.positive_sets(tu, ti)
+    torch.manual_seed(3)
+    gen = po.TorchCpuMt19937(3)
+    u, p, n = s.sample(64)
+    ou, op, on = po.sample_batch(gen, tu, ti, n_items, 64, ps)
+    assert np.array_equal(n, on.reshape(-1)) and np.array_equal(p, op)
+    assert (n != n_items - 1).any()          # some accepted negatives are actually positives (reference quirk)
+
+
+def test_sampler_large_ranges_use_64_bit_draws():
+    # torch.randint switches to two 32-bit outputs per element for ranges >= 2^28
+    n_items = (1 << 28) + 5
+    tu = np.zeros(4, dtype=np.int64)
+    ti = np.array([1, 2, 3, 4], dtype=np.int64)
+    s = g.BprSampler(tu, ti, 1, n_items)
+    torch.manual_seed(9)
+    u, p, n = s.sample(4)
+    torch.manual_seed(9)
+    idx = torch.randint(0, 4, (4,)).numpy()
+    want = [int(torch.randint(0, n_items, (1,)).item()) for _ in range(4)]
+    assert np.array_equal(p, ti[idx]) and n.tolist() == want
+
+
+def test_metrics_match_reference_values(tiny):
+    gt = ground_truth_dict((tiny["test_u"], tiny["test_i"]))
+    m = g.compute_metrics_from_topk(torch.from_numpy(tiny["eval/topk20_canonical"]), tiny["eval/users"].tolist(), gt,
+                                    int(tiny["n_items"]), [10, 20])
+    for k in ("recall", "ndcg", "precision", "coverage", "gini"):
+        for kk in (10, 20):
+            assert abs(m[f"{k}@{kk}"] - float(tiny[f"evaluate/{k}@{kk}"])) <= 1e-12, (k, kk)
+    assert g.compute_metrics_from_topk(torch.zeros((0, 20), dtype=torch.int64), [], {}, 10) == {}
+
+
+def test_seen_csr_union_sorted_unique():
+    ip, it = seen_csr([2, 5], 8, (np.array([5, 2, 5, 7]), np.array([9, 3, 1, 4])), (np.array([5, 2]), np.array([9, 0])))
+    assert ip.tolist() == [0, 2, 4] and it.tolist() == [0, 3, 1, 9]
+
+
+def test_row_partition_covers_and_balances():
+    rng = np.random.default_rng(0)
+    lens = np.concatenate([rng.integers(0, 5, 1000), [5000], rng.integers(0, 50, 500)])
+    indptr = torch.from_numpy(np.concatenate([[0], np.cumsum(lens)]).astype(np.int32))
+    for g_ in (1, 2, 3, 8):
+        part = RowPartition(indptr, g_)
+        assert part.bounds[0] == 0 and part.bounds[-1] == len(lens) and (np.diff(part.bounds) >= 0).all()
+        ids = torch.arange(len(lens))
+        padded = part.to_padded(ids)
+        assert padded.unique().numel() == len(lens) and int(padded.max()) < part.padded_rows
+        for r in range(g_):
+            r0, r1 = part.rows_of(r)
+            assert torch.equal(padded[r0:r1], torch.arange(r1 - r0) + r * part.block_rows)
+
+
+def test_dataset_boundary_attributes(tiny):
+    ds = g.InteractionDataset((tiny["train_u"], tiny["train_i"]), (tiny["valid_u"], tiny["valid_i"]),
+                              (tiny["test_u"], tiny["test_i"]), int(tiny["n_users"]), int(tiny["n_items"]))
+    assert list(ds.train_data.columns) == ["userId", "itemId"] and len(ds.train_data) == len(tiny["train_u"])
+    assert ds.n_users == 300 and ds.n_items == 200

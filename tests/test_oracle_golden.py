@@ -172,6 +172,11 @@ def test_mt19937_matches_torch_randint():
     assert [g.randint1(3706) for _ in range(50)] == ref1
     c = coracle.Mt19937(42)
     assert [c.next() % 988129 for _ in range(1000)] == ref.tolist()
+    # ranges >= 2^28 consume two 32-bit outputs per element
+    for rng_ in ((1 << 28) - 1, 1 << 28, 500_000_000, (1 << 40) + 7):
+        torch.manual_seed(5)
+        want = torch.randint(0, rng_, (9,)).numpy()
+        assert np.array_equal(po.TorchCpuMt19937(5).randint(rng_, 9), want), rng_
 
 
 def test_sampler_bit_exact(tiny):
