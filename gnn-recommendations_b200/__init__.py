@@ -10,11 +10,18 @@ from .base import BaseRecommender  # noqa: F401
 from .graph_builder import (NormAdjCSR, as_csr, build_bipartite_graph, convert_to_torch_sparse,  # noqa: F401
                             normalize_adjacency_matrix)
 from .lightgcn import LightGCN, lightgcn_propagate  # noqa: F401
+from .ngcf import NGCF, NGCFLayer  # noqa: F401
+from .gat import GAT, GATLayer  # noqa: F401
+from .orthogonal_bundle import BundleConnectionLayer, GroupShuffleLayer, OrthogonalBundleGNN  # noqa: F401
 from .dataset import InteractionDataset  # noqa: F401
 from .evaluator import Evaluator, full_rank_topk  # noqa: F401
 from .losses import BPRLoss, bpr_fused  # noqa: F401
 from .metrics import compute_metrics_from_topk  # noqa: F401
 from .sampler import BprSampler  # noqa: F401
 from .trainer import Trainer  # noqa: F401
+
+# name -> class, as scripts/run_all_experiments.py:38-45 registers them (the plug-in point of the
+# reference's driver: create_model() looks the class up here and filters YAML kwargs by signature)
+MODEL_REGISTRY = {"lightgcn": LightGCN, "ngcf": NGCF, "gat": GAT, "orthogonal_bundle": OrthogonalBundleGNN}
 
 __version__ = "0.1.0"

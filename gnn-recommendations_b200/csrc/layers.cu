@@ -1,0 +1,364 @@
+// Per-row dense epilogues of the NGCF / GAT / Group-and-Shuffle layers, and the GAT edge-softmax
+// aggregation over the CSR pattern.
+//
+//   gr_rowmap_f32       out = alpha * act( X1 Wa + ba  +  (X2 * X3) Wb + bb ) + beta * R
+//                       NGCF layer    : X1 = n = A x, X2 = x, X3 = n, Wa = W1^T, Wb = W2^T, LeakyReLU(0.2)
+//                                       (src/models/baselines/ngcf.py:77-84)
+//                       Group&Shuffle : X1 = A x, Wa = W_conn W_orth[:,perm], alpha = 1-a, beta = a, R = x0
+//                                       (src/models/orthogonal_bundle/model.py:176-195)
+//                       GAT           : X1 = x, Wa = [W_0^T | ... | W_{H-1}^T]  (gat.py:99)
+//   gr_gat_node_scores  s[i,h] = <H_h[i], a_self_h>, t[i,h] = <H_h[i], a_neigh_h>   (gat.py:106-109)
+//   gr_gat_aggregate    out_i = sum_j softmax_j(LeakyReLU(s_i + t_j)) H[j]  over the row's neighbours,
+//                       heads concatenated or averaged, optional ELU               (gat.py:112-147, 283)
+//
+// The dense maps are at most 128 x 256 and are applied to N rows: HBM-bound streaming (read the
+// row, write the row), weights resident in shared memory, FFMA in fp32 (parity is 1e-5 in fp32,
+// which single-pass TF32 tensor-core MMA cannot hold).
+#include <math_constants.h>
+
+#include "gr_common.cuh"
+
+namespace gr {
+
+// =============================================================================================
+// rowmap
+// =============================================================================================
+struct RowMapArgs {
+    const float *x1, *x2, *x3, *wa, *wb, *ba, *bb, *resid;
+    long long ld1, ld2, ld3, ldr, ldo;
+    float *out;
+    int n_rows, d_in, d_out;
+    float alpha, beta, slope;
+    int act;  // 0 none, 1 LeakyReLU(slope), 2 ELU
+};
+
+constexpr int RM_ROWS = 64;
+
+__device__ __forceinline__ float act_apply(float z, int act, float slope) {
+    if (act == 1) return z > 0.f ? z : z * slope;
+    if (act == 2) return z > 0.f ? z : expm1f(z);
+    return z;
+}
+
+__global__ void __launch_bounds__(256) rowmap_kernel(const RowMapArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int d_in = a.d_in, d_out = a.d_out;
+    const bool has_b = a.wb != nullptr;
+    float *Wa = reinterpret_cast<float *>(smem_raw);              // [d_in][d_out]
+    float *Wb = Wa + (size_t)d_in * d_out;                        // [d_in][d_out] (if has_b)
+    float *Xs = Wb + (has_b ? (size_t)d_in * d_out : 0);          // [d_in][RM_ROWS]
+    float *Ys = Xs + (size_t)d_in * RM_ROWS;                      // [d_in][RM_ROWS] (if has_b)
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int row0 = blockIdx.x * RM_ROWS;
+
+    for (int i = tid; i < d_in * d_out / 4; i += 256) {
+        reinterpret_cast<float4 *>(Wa)[i] = __ldg(reinterpret_cast<const float4 *>(a.wa) + i);
+        if (has_b) reinterpret_cast<float4 *>(Wb)[i] = __ldg(reinterpret_cast<const float4 *>(a.wb) + i);
+    }
+    const int f4 = d_in / 4;
+    for (int i = tid; i < RM_ROWS * f4; i += 256) {
+        const int r = i / f4, f = i % f4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f), y = v;
+        if (row0 + r < a.n_rows) {
+            v = __ldg(reinterpret_cast<const float4 *>(a.x1 + (long long)(row0 + r) * a.ld1) + f);
+            if (has_b) {
+                const float4 p = __ldg(reinterpret_cast<const float4 *>(a.x2 + (long long)(row0 + r) * a.ld2) + f);
+                const float4 q = __ldg(reinterpret_cast<const float4 *>(a.x3 + (long long)(row0 + r) * a.ld3) + f);
+                y = make_float4(p.x * q.x, p.y * q.y, p.z * q.z, p.w * q.w);
+            }
+        }
+        Xs[(4 * f + 0) * RM_ROWS + r] = v.x;
+        Xs[(4 * f + 1) * RM_ROWS + r] = v.y;
+        Xs[(4 * f + 2) * RM_ROWS + r] = v.z;
+        Xs[(4 * f + 3) * RM_ROWS + r] = v.w;
+        if (has_b) {
+            Ys[(4 * f + 0) * RM_ROWS + r] = y.x;
+            Ys[(4 * f + 1) * RM_ROWS + r] = y.y;
+            Ys[(4 * f + 2) * RM_ROWS + r] = y.z;
+            Ys[(4 * f + 3) * RM_ROWS + r] = y.w;
+        }
+    }
+    __syncthreads();
+
+    const int nc4 = d_out / 4;  // float4 column groups; thread tx owns groups tx, tx+16, tx+32, tx+48
+    float accA[4][4][4], accB[4][4][4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m)
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) accA[m][g][c] = accB[m][g][c] = 0.f;
+
+    for (int k = 0; k < d_in; ++k) {
+        const float4 xv = *reinterpret_cast<const float4 *>(Xs + (size_t)k * RM_ROWS + ty * 4);
+        const float xm[4] = {xv.x, xv.y, xv.z, xv.w};
+        float ym[4] = {0.f, 0.f, 0.f, 0.f};
+        if (has_b) {
+            const float4 yv = *reinterpret_cast<const float4 *>(Ys + (size_t)k * RM_ROWS + ty * 4);
+            ym[0] = yv.x; ym[1] = yv.y; ym[2] = yv.z; ym[3] = yv.w;
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const int cg = tx + 16 * g;
+            if (cg < nc4) {
+                const float4 w = *reinterpret_cast<const float4 *>(Wa + (size_t)k * d_out + cg * 4);
+                const float wc[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                for (int m = 0; m < 4; ++m)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) accA[m][g][c] = __fmaf_rn(xm[m], wc[c], accA[m][g][c]);
+                if (has_b) {
+                    const float4 w2 = *reinterpret_cast<const float4 *>(Wb + (size_t)k * d_out + cg * 4);
+                    const float w2c[4] = {w2.x, w2.y, w2.z, w2.w};
+#pragma unroll
+                    for (int m = 0; m < 4; ++m)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) accB[m][g][c] = __fmaf_rn(ym[m], w2c[c], accB[m][g][c]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        const int cg = tx + 16 * g;
+        if (cg >= nc4) continue;
+        float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bb = ba;
+        if (a.ba) ba = __ldg(reinterpret_cast<const float4 *>(a.ba) + cg);
+        if (a.bb) bb = __ldg(reinterpret_cast<const float4 *>(a.bb) + cg);
+        const float bac[4] = {ba.x, ba.y, ba.z, ba.w}, bbc[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            const int r = row0 + ty * 4 + m;
+            if (r >= a.n_rows) continue;
+            float o[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                float z = accA[m][g][c] + bac[c];
+                if (has_b) z = z + (accB[m][g][c] + bbc[c]);
+                o[c] = a.alpha * act_apply(z, a.act, a.slope);
+            }
+            if (a.resid) {
+                const float4 rv = __ldg(reinterpret_cast<const float4 *>(a.resid + (long long)r * a.ldr) + cg);
+                o[0] += a.beta * rv.x; o[1] += a.beta * rv.y; o[2] += a.beta * rv.z; o[3] += a.beta * rv.w;
+            }
+            *reinterpret_cast<float4 *>(a.out + (long long)r * a.ldo + cg * 4) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+    }
+}
+
+// =============================================================================================
+// GAT
+// =============================================================================================
+// s[i,h] = <H[i, h*dh : (h+1)*dh], a_self[h]>,  t likewise with a_neigh.  One warp per node.
+__global__ void __launch_bounds__(256) gat_node_scores_kernel(const float *h, long long ldh, const float *a_self,
+                                                              const float *a_neigh, int n, int heads, int dh,
+                                                              float *s, float *t) {
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (i >= n) return;
+    for (int hd = 0; hd < heads; ++hd) {
+        float ps = 0.f, pt = 0.f;
+        for (int f = lane; f < dh; f += 32) {
+            const float v = __ldg(h + (long long)i * ldh + hd * dh + f);
+            ps = __fmaf_rn(v, __ldg(a_self + hd * dh + f), ps);
+            pt = __fmaf_rn(v, __ldg(a_neigh + hd * dh + f), pt);
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            ps += __shfl_xor_sync(0xffffffffu, ps, o);
+            pt += __shfl_xor_sync(0xffffffffu, pt, o);
+        }
+        if (lane == 0) {
+            s[(long long)i * heads + hd] = ps;
+            t[(long long)i * heads + hd] = pt;
+        }
+    }
+}
+
+struct GatArgs {
+    const int *indptr, *indices;
+    const float *h;
+    long long ldh;
+    const float *s, *t;
+    int n_rows, heads, dh;
+    float slope;
+    int mean_heads;  // 0: concat heads -> width heads*dh; 1: average heads -> width dh
+    int elu;
+    float *out;
+    long long ldo;
+    float *m_out, *z_out;  // [n_rows, heads] softmax statistics for the backward pass (may be NULL)
+};
+
+// One warp per row, online softmax (running max / running sum, rescaled accumulator), one pass over
+// the neighbours; lane owns float4 slots lane, lane+32 of the heads*dh wide row.  SLOTS = 1 or 2.
+template <int SLOTS>
+__global__ void __launch_bounds__(256) gat_aggregate_kernel(const GatArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (i >= a.n_rows) return;
+    const int width4 = a.heads * a.dh / 4;
+    const int dh4 = a.dh / 4;
+    int head[SLOTS];
+    bool on[SLOTS];
+    float si[SLOTS], m[SLOTS], z[SLOTS];
+    float4 acc[SLOTS];
+#pragma unroll
+    for (int q = 0; q < SLOTS; ++q) {
+        const int slot = lane + 32 * q;
+        on[q] = slot < width4;
+        head[q] = on[q] ? slot / dh4 : 0;
+        si[q] = __ldg(a.s + (long long)i * a.heads + head[q]);
+        m[q] = -CUDART_INF_F;
+        z[q] = 0.f;
+        acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const int start = a.indptr[i], end = a.indptr[i + 1];
+    for (int base = start; base < end; base += 32) {
+        const int mycol = (base + lane < end) ? __ldg(a.indices + base + lane) : 0;
+        const int cnt = min(32, end - base);
+        for (int k = 0; k < cnt; k += 4) {
+            float4 hv[4][SLOTS];
+            float tv[4][SLOTS];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int j = __shfl_sync(0xffffffffu, mycol, (k + u) & 31);
+                if (k + u < cnt) {
+#pragma unroll
+                    for (int q = 0; q < SLOTS; ++q)
+                        if (on[q]) {
+                            hv[u][q] = __ldg(reinterpret_cast<const float4 *>(a.h + (long long)j * a.ldh) + lane + 32 * q);
+                            tv[u][q] = __ldg(a.t + (long long)j * a.heads + head[q]);
+                        }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (k + u < cnt) {
+#pragma unroll
+                    for (int q = 0; q < SLOTS; ++q)
+                        if (on[q]) {
+                            float e = si[q] + tv[u][q];
+                            e = e > 0.f ? e : e * a.slope;
+                            const float mn = fmaxf(m[q], e);
+                            const float sc = expf(m[q] - mn);   // exp(-inf) = 0 on the first neighbour
+                            const float w = expf(e - mn);
+                            z[q] = z[q] * sc + w;
+                            acc[q].x = acc[q].x * sc + w * hv[u][q].x;
+                            acc[q].y = acc[q].y * sc + w * hv[u][q].y;
+                            acc[q].z = acc[q].z * sc + w * hv[u][q].z;
+                            acc[q].w = acc[q].w * sc + w * hv[u][q].w;
+                            m[q] = mn;
+                        }
+                }
+            }
+        }
+    }
+    // out = acc / z   (a row without neighbours gives 0/0 = NaN, like the reference's softmax of -inf)
+#pragma unroll
+    for (int q = 0; q < SLOTS; ++q)
+        if (on[q]) {
+            acc[q].x /= z[q]; acc[q].y /= z[q]; acc[q].z /= z[q]; acc[q].w /= z[q];
+            const int slot = lane + 32 * q;
+            if (a.m_out && (slot % dh4) == 0) {
+                a.m_out[(long long)i * a.heads + head[q]] = m[q];
+                a.z_out[(long long)i * a.heads + head[q]] = z[q];
+            }
+        }
+    if (!a.mean_heads) {
+#pragma unroll
+        for (int q = 0; q < SLOTS; ++q)
+            if (on[q]) {
+                float4 o = acc[q];
+                if (a.elu) { o.x = act_apply(o.x, 2, 0.f); o.y = act_apply(o.y, 2, 0.f); o.z = act_apply(o.z, 2, 0.f); o.w = act_apply(o.w, 2, 0.f); }
+                *reinterpret_cast<float4 *>(a.out + (long long)i * a.ldo + (lane + 32 * q) * 4) = o;
+            }
+    } else {
+        // average over heads (torch.stack(heads).mean(0): left-to-right sum / heads): slot (head, f4)
+        // -> output slot f4.  Heads of one f4 live in lanes f4 + dh4*head (mod 32) across the SLOTS.
+        __shared__ float4 stage[8][64];
+        float4 *st = stage[threadIdx.x >> 5];
+#pragma unroll
+        for (int q = 0; q < SLOTS; ++q)
+            if (on[q]) st[lane + 32 * q] = acc[q];
+        __syncwarp();
+        for (int f = lane; f < dh4; f += 32) {
+            float4 sum = st[f];
+            for (int hd = 1; hd < a.heads; ++hd) {
+                const float4 v = st[hd * dh4 + f];
+                sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+            }
+            const float hh = (float)a.heads;
+            float4 o = make_float4(sum.x / hh, sum.y / hh, sum.z / hh, sum.w / hh);
+            if (a.elu) { o.x = act_apply(o.x, 2, 0.f); o.y = act_apply(o.y, 2, 0.f); o.z = act_apply(o.z, 2, 0.f); o.w = act_apply(o.w, 2, 0.f); }
+            *reinterpret_cast<float4 *>(a.out + (long long)i * a.ldo + f * 4) = o;
+        }
+    }
+}
+
+}  // namespace gr
+
+using namespace gr;
+
+extern "C" int gr_rowmap_f32(const float *x1, int64_t ld1, const float *wa, const float *bias_a, const float *x2,
+                             int64_t ld2, const float *x3, int64_t ld3, const float *wb, const float *bias_b,
+                             const float *resid, int64_t ldr, float alpha, float beta, int32_t act, float slope,
+                             int64_t n_rows, int32_t d_in, int32_t d_out, float *out, int64_t ldo, void *stream) {
+    if (!x1 || !wa || !out || n_rows < 0) return GR_ERR_INVALID;
+    if (wb && (!x2 || !x3)) return GR_ERR_INVALID;
+    if (n_rows == 0) return GR_OK;
+    if (d_in <= 0 || d_out <= 0 || (d_in & 3) || (d_out & 3) || d_in > 256 || d_out > 256) return GR_ERR_UNSUPPORTED;
+    if ((ld1 & 3) || (ldo & 3) || ld1 < d_in || ldo < d_out || (resid && ((ldr & 3) || ldr < d_out))) return GR_ERR_INVALID;
+    if (wb && ((ld2 & 3) || (ld3 & 3) || ld2 < d_in || ld3 < d_in)) return GR_ERR_INVALID;
+    if (act < 0 || act > 2) return GR_ERR_INVALID;
+    if (n_rows > 0x7fffffffLL) return GR_ERR_OVERFLOW;
+    if (!aligned16(x1) || !aligned16(wa) || !aligned16(out) || !aligned16(x2) || !aligned16(x3) || !aligned16(wb) ||
+        !aligned16(bias_a) || !aligned16(bias_b) || !aligned16(resid))
+        return GR_ERR_INVALID;
+    RowMapArgs a;
+    a.x1 = x1; a.x2 = x2; a.x3 = x3; a.wa = wa; a.wb = wb; a.ba = bias_a; a.bb = bias_b; a.resid = resid;
+    a.ld1 = ld1; a.ld2 = ld2; a.ld3 = ld3; a.ldr = ldr; a.ldo = ldo;
+    a.out = out; a.n_rows = (int)n_rows; a.d_in = d_in; a.d_out = d_out;
+    a.alpha = alpha; a.beta = beta; a.slope = slope; a.act = act;
+    const size_t smem = ((size_t)d_in * d_out + (size_t)d_in * RM_ROWS) * 4 * (wb ? 2 : 1);
+    if (smem > 227 * 1024) return GR_ERR_UNSUPPORTED;
+    GR_CUDA_CHECK(cudaFuncSetAttribute(rowmap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    rowmap_kernel<<<(unsigned)((n_rows + RM_ROWS - 1) / RM_ROWS), 256, smem, static_cast<cudaStream_t>(stream)>>>(a);
+    GR_LAUNCH_CHECK();
+    return GR_OK;
+}
+
+extern "C" int gr_gat_node_scores(const float *h, int64_t ldh, const float *a_self, const float *a_neigh,
+                                  int64_t n_rows, int32_t heads, int32_t dh, float *s, float *t, void *stream) {
+    if (!h || !a_self || !a_neigh || !s || !t || n_rows < 0 || heads <= 0 || dh <= 0 || ldh < (int64_t)heads * dh)
+        return GR_ERR_INVALID;
+    if (n_rows == 0) return GR_OK;
+    if (n_rows > 0x7fffffffLL) return GR_ERR_OVERFLOW;
+    gat_node_scores_kernel<<<(unsigned)((n_rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        h, ldh, a_self, a_neigh, (int)n_rows, heads, dh, s, t);
+    GR_LAUNCH_CHECK();
+    return GR_OK;
+}
+
+extern "C" int gr_gat_aggregate(const int32_t *indptr, const int32_t *indices, int64_t n_rows, const float *h,
+                                int64_t ldh, const float *s, const float *t, int32_t heads, int32_t dh,
+                                float slope, int32_t mean_heads, int32_t elu, float *out, int64_t ldo, float *m_out,
+                                float *z_out, void *stream) {
+    if (!indptr || !indices || !h || !s || !t || !out || n_rows < 0 || heads <= 0 || dh <= 0) return GR_ERR_INVALID;
+    if ((m_out == nullptr) != (z_out == nullptr)) return GR_ERR_INVALID;
+    if (n_rows == 0) return GR_OK;
+    const int width = heads * dh;
+    if ((dh & 3) || width > 256 || (ldh & 3) || (ldo & 3) || ldh < width) return GR_ERR_UNSUPPORTED;
+    if (ldo < (mean_heads ? dh : width)) return GR_ERR_INVALID;
+    if (!aligned16(h) || !aligned16(out)) return GR_ERR_INVALID;
+    if (n_rows > 0x7fffffffLL) return GR_ERR_OVERFLOW;
+    GatArgs a;
+    a.indptr = indptr; a.indices = indices; a.h = h; a.ldh = ldh; a.s = s; a.t = t;
+    a.n_rows = (int)n_rows; a.heads = heads; a.dh = dh; a.slope = slope; a.mean_heads = mean_heads; a.elu = elu;
+    a.out = out; a.ldo = ldo; a.m_out = m_out; a.z_out = z_out;
+    const unsigned grid = (unsigned)((n_rows + 7) / 8);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (width / 4 <= 32) gat_aggregate_kernel<1><<<grid, 256, 0, st>>>(a);
+    else gat_aggregate_kernel<2><<<grid, 256, 0, st>>>(a);
+    GR_LAUNCH_CHECK();
+    return GR_OK;
+}

@@ -1,0 +1,176 @@
+"""OrthogonalBundleGNN (Group-and-Shuffle orthogonal GCN) — drop-in for
+src/models/orthogonal_bundle/{model.py:29, group_shuffle_layer.py:12, bundle_layer.py:9}.
+
+Per layer the reference computes  c = Â x ; t = c @ W_conn ; g = (t @ W_orth)[:, perm] ;
+x = (1-a) g + a x0.  The two 64x64 maps and the column permutation compose into one matrix
+M = W_conn (W_orth[:, perm]) built with stock torch ops (48 tiny matrix_exp calls, autograd kept),
+so a layer is one SpMM kernel plus one rowmap kernel (dense map + residual fused); the layer
+outputs are combined with softmax(layer_weights).  State-dict keys, constructor signature and
+RNG order match the reference.  The edge-list mode (use_edge_index=True, off by default,
+model.py:64) is not part of the hot path and raises NotImplementedError."""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .base import BaseRecommender
+from .graph_builder import as_csr
+from .layer_ops import rowmap, spmm
+
+
+def _block_orthogonal(skew_params) -> torch.Tensor:
+    return torch.block_diag(*[torch.matrix_exp(p - p.transpose(-2, -1)) for p in skew_params])
+
+
+def _orth_metrics(w: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    eye = torch.eye(w.shape[0], device=w.device, dtype=w.dtype)
+    diff = w.T @ w - eye
+    return torch.norm(diff, p="fro"), diff.abs().max()
+
+
+class GroupShuffleLayer(nn.Module):
+    """group_shuffle_layer.py:12-190: block-diagonal exp(skew) ("group") + fixed permutation ("shuffle")."""
+
+    def __init__(self, dim: int, block_size: int, init_scale: float = 0.01):
+        super().__init__()
+        if dim % block_size != 0:
+            raise ValueError(f"dim ({dim}) must be divisible by block_size ({block_size})")
+        self.dim, self.block_size, self.n_blocks = dim, block_size, dim // block_size
+        self.skew_params = nn.ParameterList([nn.Parameter(torch.randn(block_size, block_size) * init_scale)
+                                             for _ in range(self.n_blocks)])
+        self.register_buffer("perm", torch.randperm(dim))
+
+    def _build_orthogonal_matrix(self) -> torch.Tensor:
+        return _block_orthogonal(self.skew_params)
+
+    def matrix(self) -> torch.Tensor:
+        """The map the layer applies: x -> (x @ W_orth)[:, perm] == x @ W_orth[:, perm]."""
+        return self._build_orthogonal_matrix()[:, self.perm]
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return rowmap(x, self.matrix())
+
+    def get_orthogonality_error(self) -> torch.Tensor:
+        return _orth_metrics(self._build_orthogonal_matrix())[0]
+
+    def get_orthogonality_metrics(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        return _orth_metrics(self._build_orthogonal_matrix())
+
+    def reset_parameters(self):
+        for p in self.skew_params:
+            nn.init.normal_(p, mean=0.0, std=0.01)
+
+
+class BundleConnectionLayer(nn.Module):
+    """bundle_layer.py:9-88: the shared connection matrix W = blockdiag(exp(skew))[:, shuffle_perm]."""
+
+    def __init__(self, embedding_dim, block_size, n_blocks=None):
+        super().__init__()
+        self.embedding_dim, self.block_size = embedding_dim, block_size
+        self.n_blocks = n_blocks or (embedding_dim // block_size)
+        self.skew_params = nn.ParameterList([nn.Parameter(torch.randn(block_size, block_size) * 0.01)
+                                             for _ in range(self.n_blocks)])
+        self.register_buffer("shuffle_perm", torch.randperm(embedding_dim))
+
+    def forward(self, edge_index=None) -> torch.Tensor:
+        return _block_orthogonal(self.skew_params)[:, self.shuffle_perm]
+
+    def get_connection_matrix_for_edge(self, src_node, dst_node):
+        return self.forward()
+
+    def get_orthogonality_metrics(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        return _orth_metrics(self.forward())
+
+
+class OrthogonalBundleGNN(BaseRecommender):
+    def __init__(self, n_users: int, n_items: int, embedding_dim: int = 64, n_layers: int = 3, block_size: int = 8,
+                 residual_alpha: float = 0.1, dropout: float = 0.0, init_scale: float = 0.01,
+                 use_parallel_transport: bool = True, use_edge_index: bool = False):
+        super().__init__(n_users, n_items, embedding_dim)
+        if embedding_dim % block_size != 0:
+            raise ValueError(f"embedding_dim ({embedding_dim}) must be divisible by block_size ({block_size})")
+        self.n_layers, self.block_size, self.residual_alpha = n_layers, block_size, residual_alpha
+        self.dropout, self.use_parallel_transport, self.use_edge_index = dropout, use_parallel_transport, use_edge_index
+        # RNG order of model.py:96-112
+        self.user_embedding = nn.Embedding(n_users, embedding_dim)
+        self.item_embedding = nn.Embedding(n_items, embedding_dim)
+        nn.init.normal_(self.user_embedding.weight, std=0.01)
+        nn.init.normal_(self.item_embedding.weight, std=0.01)
+        if use_parallel_transport:
+            self.connection_layers = nn.ModuleList([BundleConnectionLayer(embedding_dim, block_size)
+                                                    for _ in range(n_layers)])
+        self.local_transform_layers = nn.ModuleList([GroupShuffleLayer(embedding_dim, block_size, init_scale)
+                                                     for _ in range(n_layers)])
+        self.dropout_layer = nn.Dropout(dropout) if dropout > 0 else None
+        self.layer_weights = nn.Parameter(torch.ones(n_layers + 1))
+
+    def _layer_matrix(self, l: int) -> torch.Tensor:
+        m = self.local_transform_layers[l].matrix()
+        if self.use_parallel_transport:
+            m = self.connection_layers[l]() @ m
+        return m
+
+    def _layers(self, adj_matrix, residual: bool) -> List[torch.Tensor]:
+        if self.use_edge_index:
+            raise NotImplementedError("edge_index mode (model.py:218-222) is outside the B200 hot path; "
+                                      "use the adjacency-matrix mode (the reference default)")
+        if adj_matrix is None:
+            raise ValueError("adj_matrix must be provided when use_edge_index=False")
+        csr = as_csr(adj_matrix)
+        x0 = torch.cat([self.user_embedding.weight, self.item_embedding.weight], dim=0)
+        x, outs = x0, [x0]
+        a = self.residual_alpha
+        for l in range(self.n_layers):
+            c = spmm(csr, x)
+            if residual:
+                x = rowmap(c, self._layer_matrix(l), resid=x0, alpha=1.0 - a, beta=a)
+                if self.dropout_layer is not None:
+                    x = self.dropout_layer(x)
+            else:
+                x = rowmap(c, self._layer_matrix(l))
+            outs.append(x)
+        return outs
+
+    def propagate(self, adj_matrix=None, edge_index=None) -> torch.Tensor:
+        outs = self._layers(adj_matrix, residual=True)
+        w = F.softmax(self.layer_weights, dim=0)
+        return sum([wi * e for wi, e in zip(w, outs)])
+
+    def forward(self, adj_matrix=None, edge_index=None) -> Tuple[torch.Tensor, torch.Tensor]:
+        x = self.propagate(adj_matrix, edge_index)
+        return x[:self.n_users], x[self.n_users:]
+
+    def predict(self, users, items, adj_matrix=None, edge_index=None) -> torch.Tensor:
+        ue, ie = self.get_all_embeddings(adj_matrix, edge_index)
+        return self._predict_pairs(users, items, ue, ie)
+
+    def get_all_embeddings(self, adj_matrix=None, edge_index=None) -> Tuple[torch.Tensor, torch.Tensor]:
+        return self.forward(adj_matrix, edge_index)
+
+    def get_layer_embeddings(self, adj_matrix=None, edge_index=None) -> List[torch.Tensor]:
+        """model.py:306-356: per-layer outputs WITHOUT the residual (analysis helper)."""
+        with torch.no_grad():
+            return [o.clone() for o in self._layers(adj_matrix, residual=False)]
+
+    def get_orthogonality_errors(self) -> torch.Tensor:
+        return torch.stack([l.get_orthogonality_error() for l in self.local_transform_layers])
+
+    def get_orthogonality_metrics(self) -> Dict[str, torch.Tensor]:
+        m: Dict[str, torch.Tensor] = {}
+        lf, lm = zip(*[l.get_orthogonality_metrics() for l in self.local_transform_layers])
+        m["local_fro_mean"], m["local_fro_max"] = torch.stack(lf).mean(), torch.stack(lf).max()
+        m["local_max_dev"] = torch.stack(lm).max()
+        if self.use_parallel_transport:
+            cf, cm = zip(*[l.get_orthogonality_metrics() for l in self.connection_layers])
+            m["conn_fro_mean"], m["conn_fro_max"] = torch.stack(cf).mean(), torch.stack(cf).max()
+            m["conn_max_dev"] = torch.stack(cm).max()
+        return m
+
+    def reset_parameters(self):
+        nn.init.normal_(self.user_embedding.weight, mean=0.0, std=0.01)
+        nn.init.normal_(self.item_embedding.weight, mean=0.0, std=0.01)
+        for layer in self.local_transform_layers:
+            layer.reset_parameters()

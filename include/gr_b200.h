@@ -115,6 +115,35 @@ int gr_spmm_csr_f32(const int32_t *indptr, const int32_t *indices, const float *
                     int64_t ldx, float *y, int64_t ldy, const float *addend, int64_t lda, float *out,
                     int64_t ldo, float scale, int32_t scale_mode, void *stream);
 
+/* Per-row dense epilogue shared by the NGCF, Group-and-Shuffle and GAT layers:
+ *     out = alpha * act( X1 Wa + bias_a  +  (X2 * X3) Wb + bias_b ) + beta * R
+ * Wa, Wb: [d_in, d_out] row-major (i.e. nn.Linear.weight TRANSPOSED); the (X2*X3) term, the
+ * biases and R are optional (NULL).  act: 0 none, 1 LeakyReLU(slope), 2 ELU.
+ *   NGCF  (src/models/baselines/ngcf.py:77-84): X1 = X3 = A x, X2 = x, act = LeakyReLU(0.2)
+ *   G&S   (src/models/orthogonal_bundle/model.py:176-195, group_shuffle_layer.py:88-94):
+ *         X1 = A x, Wa = W_conn W_orth[:,perm], alpha = 1 - a, beta = a, R = x0
+ *   GAT   (src/models/baselines/gat.py:99): X1 = x, Wa = [W_0^T | ... | W_{H-1}^T]
+ * d_in, d_out multiples of 4, <= 256. */
+int gr_rowmap_f32(const float *x1, int64_t ld1, const float *wa, const float *bias_a, const float *x2, int64_t ld2,
+                  const float *x3, int64_t ld3, const float *wb, const float *bias_b, const float *resid,
+                  int64_t ldr, float alpha, float beta, int32_t act, float slope, int64_t n_rows, int32_t d_in,
+                  int32_t d_out, float *out, int64_t ldo, void *stream);
+
+/* GAT (src/models/baselines/gat.py:76-151) over the CSR PATTERN of the adjacency (its values are
+ * ignored, gat.py:120-127) instead of the reference's dense N x N temporaries.
+ *   gr_gat_node_scores: s[i,h] = <H_h[i], a_self_h>, t[i,h] = <H_h[i], a_neigh_h>      (gat.py:106-109)
+ *   gr_gat_aggregate:   out_i = sum_j softmax_j(LeakyReLU_slope(s[i,h] + t[j,h])) H_h[j] over the
+ *       row's neighbours (online softmax, one pass); heads concatenated (mean_heads = 0, width
+ *       heads*dh) or averaged (mean_heads = 1, width dh) (gat.py:144-147); elu = 1 applies the ELU of
+ *       GAT.forward (gat.py:283).  A row without neighbours yields NaN like the reference.
+ *       m_out / z_out (optional, [n_rows, heads]): softmax max / normaliser for the backward pass.
+ * H: [N, heads*dh], heads*dh <= 256, dh % 4 == 0. */
+int gr_gat_node_scores(const float *h, int64_t ldh, const float *a_self, const float *a_neigh, int64_t n_rows,
+                       int32_t heads, int32_t dh, float *s, float *t, void *stream);
+int gr_gat_aggregate(const int32_t *indptr, const int32_t *indices, int64_t n_rows, const float *h, int64_t ldh,
+                     const float *s, const float *t, int32_t heads, int32_t dh, float slope, int32_t mean_heads,
+                     int32_t elu, float *out, int64_t ldo, float *m_out, float *z_out, void *stream);
+
 /* ------------------------------------------------------------------------------------------
  * BPR step
  * ------------------------------------------------------------------------------------------ */

@@ -75,3 +75,22 @@ def test_constructor_signatures_and_same_seed_parameters():
     b = g.LightGCN(50, 40, 64, 3, 0.1)
     for (ka, va), (kb, vb) in zip(a.state_dict().items(), b.state_dict().items()):
         assert ka == kb and torch.equal(va, vb)
+
+
+@pytest.mark.reference
+def test_all_models_same_seed_same_parameters_as_reference():
+    sys.path.insert(0, REFERENCE)
+    from src.models import GAT as RGAT, NGCF as RNGCF, OrthogonalBundleGNN as ROB
+
+    for ref_cls, cls, kw in ((RNGCF, g.NGCF, dict(embedding_dim=64, layer_sizes=[64, 64, 64], dropout=0.1, init_scale=0.05)),
+                             (RGAT, g.GAT, dict(embedding_dim=64, n_layers=3, n_heads=4, dropout=0.1, alpha=0.2, init_scale=0.05)),
+                             (ROB, g.OrthogonalBundleGNN, dict(embedding_dim=64, n_layers=3, block_size=8))):
+        assert sig(ref_cls) == sig(cls), cls.__name__
+        torch.manual_seed(11)
+        a = ref_cls(40, 30, **kw)
+        torch.manual_seed(11)
+        b = cls(40, 30, **kw)
+        sa, sb = a.state_dict(), b.state_dict()
+        assert list(sa) == list(sb), cls.__name__
+        for k in sa:
+            assert torch.equal(sa[k], sb[k]), (cls.__name__, k)
