@@ -101,3 +101,80 @@ def lightgcn_propagate_sharded(local: NormAdjCSR, part: RowPartition, rank: int,
             spmm(bufs[cur], bufs[nxt][off:off + n_local], addend, acc, 1.0, _lib.GR_SCALE_NONE)
             cur = nxt
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# item-sharded full-ranking evaluation
+# ------------------------------------------------------------------------------------------------
+def item_shard(n_items: int, world_size: int, rank: int):
+    """Contiguous id range [lo, hi) of the rank's items (multiple-of-128 boundaries)."""
+    per = -(-n_items // world_size)
+    per = -(-per // 128) * 128
+    lo = min(n_items, rank * per)
+    return lo, min(n_items, lo + per)
+
+
+def gather_rows(part: RowPartition, rank: int, x_local: torch.Tensor, group=None) -> torch.Tensor:
+    """All ranks' row blocks -> the full [N, d] matrix in natural row order (replicated)."""
+    import torch.distributed as dist
+
+    d = x_local.shape[1]
+    buf = torch.zeros((part.padded_rows, d), dtype=x_local.dtype, device=x_local.device)
+    r0, r1 = part.rows_of(rank)
+    buf[rank * part.block_rows: rank * part.block_rows + (r1 - r0)].copy_(x_local)
+    _all_gather_rows(buf, rank, part.block_rows, group)
+    pieces = []
+    for g in range(part.world_size):
+        a, b = part.rows_of(g)
+        pieces.append(buf[g * part.block_rows: g * part.block_rows + (b - a)])
+    return torch.cat(pieces, dim=0)
+
+
+def full_rank_topk_sharded(user_emb: torch.Tensor, item_emb_local: torch.Tensor, item_lo: int, item_hi: int,
+                           eval_users, seen_indptr, seen_items, k: int, world_size: int, group=None,
+                           n_splits: int = 1, partial_fn: Optional[Callable] = None,
+                           merge_fn: Optional[Callable] = None) -> torch.Tensor:
+    """Each rank ranks its own item id range [item_lo, item_hi) for ALL eval users
+    (gr_score_topk_partial), the per-rank top-k (score, id) lists are all-gathered
+    (k * 8 bytes per user per rank) and merged under (score desc, id asc) (gr_topk_merge).
+    Scores are per-(user,item) independent, so the result is bit-identical to the 1-GPU list.
+    ``partial_fn`` / ``merge_fn`` are injectable for the CPU (gloo) tests of the exchange logic."""
+    import torch.distributed as dist
+
+    dev = user_emb.device
+    eval_users = torch.as_tensor(eval_users, dtype=torch.int64).to(dev).contiguous()
+    n_eval = int(eval_users.numel())
+    if partial_fn is None:
+        from ._lib import check, lib, ptr, stream_ptr
+
+        def partial_fn(ue, ie, lo, hi, eu, sip, sit, kk, ns):
+            ps = torch.empty((ns, n_eval, kk), dtype=torch.float32, device=dev)
+            pi = torch.empty((ns, n_eval, kk), dtype=torch.int32, device=dev)
+            with torch.cuda.device(dev):
+                check(lib().gr_score_topk_partial(ptr(ue), ue.stride(0), ptr(ie), ie.stride(0), int(ue.shape[1]),
+                                                  ptr(eu), n_eval, lo, hi, ptr(sip), ptr(sit), kk, ns, ptr(ps),
+                                                  ptr(pi), stream_ptr()), "gr_score_topk_partial")
+            return ps, pi
+
+        def merge_fn(ps, pi, kk):
+            ids = torch.empty((n_eval, kk), dtype=torch.int64, device=dev)
+            sc = torch.empty((n_eval, kk), dtype=torch.float32, device=dev)
+            with torch.cuda.device(dev):
+                check(lib().gr_topk_merge(ptr(ps), ptr(pi), int(ps.shape[0]), n_eval, kk, ptr(ids), ptr(sc),
+                                          stream_ptr()), "gr_topk_merge")
+            return ids
+
+    if seen_indptr is not None:
+        seen_indptr = torch.as_tensor(seen_indptr, dtype=torch.int64).to(dev).contiguous()
+        seen_items = torch.as_tensor(seen_items, dtype=torch.int32).to(dev).contiguous()
+        if seen_items.numel() == 0:
+            seen_items = torch.zeros(1, dtype=torch.int32, device=dev)
+    ps, pi = partial_fn(user_emb.contiguous(), item_emb_local.contiguous(), int(item_lo), int(item_hi), eval_users,
+                        seen_indptr, seen_items, k, n_splits)
+    if world_size > 1 and dist.is_initialized():
+        all_ps = torch.empty((world_size * ps.shape[0], n_eval, k), dtype=ps.dtype, device=dev)
+        all_pi = torch.empty((world_size * pi.shape[0], n_eval, k), dtype=pi.dtype, device=dev)
+        dist.all_gather_into_tensor(all_ps, ps.contiguous(), group=group)
+        dist.all_gather_into_tensor(all_pi, pi.contiguous(), group=group)
+        ps, pi = all_ps, all_pi
+    return merge_fn(ps, pi, k)
