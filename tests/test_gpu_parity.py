@@ -232,3 +232,19 @@ def test_c1_graph_and_forward_vs_reference_hashes(c1gold, c1split):
         a = g.lightgcn_propagate(csr, x0, 3)
         b = g.lightgcn_propagate(csr, x0 * 2.0, 3)
     assert torch.equal(a * 2.0, b)
+
+
+def test_multi_gpu_bit_identical_when_two_gpus_present():
+    """Spawns tests/multigpu_check.py under torchrun when the box has >= 2 GPUs."""
+    import os
+    import subprocess
+    import sys
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    here = os.path.dirname(os.path.abspath(__file__))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29517", os.path.join(here, "multigpu_check.py"), "C1"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "propagation_bit_identical=True topk_bit_identical=True" in r.stdout
