@@ -265,6 +265,24 @@ __global__ void schedule_emit_kernel(const uint64_t *keys, long long n_rows, int
     }
 }
 
+// group_ptr[g] = first row whose entries start at or after g * group_nnz (row groups of about
+// group_nnz entries for the streaming SpMM kernel); group_ptr[n_groups] = n_rows.
+__global__ void row_groups_kernel(const int *indptr, int n_rows, int group_nnz, int n_groups, int *group_ptr) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g > n_groups) return;
+    if (g == n_groups) {
+        group_ptr[g] = n_rows;
+        return;
+    }
+    const long long target = g * (long long)group_nnz;
+    int lo = 0, hi = n_rows;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if ((long long)indptr[mid] < target) lo = mid + 1; else hi = mid;
+    }
+    group_ptr[g] = lo;
+}
+
 // =============================================================================================
 // (user,item) pairs -> CSR pattern with multiplicities and degrees
 // =============================================================================================
@@ -420,6 +438,16 @@ extern "C" int gr_row_schedule(const int32_t *indptr, int64_t n_rows, int32_t lo
                             workspace_bytes - 2 * align256((size_t)n_rows * 8), &in_a, s);
     if (rc != GR_OK) return rc;
     schedule_emit_kernel<<<g, 256, 0, s>>>(in_a ? ka : kb, n_rows, row_bits, long_threshold, row_order, n_long_out);
+    GR_LAUNCH_CHECK();
+    return GR_OK;
+}
+
+extern "C" int gr_row_groups(const int32_t *indptr, int64_t n_rows, int32_t group_nnz, int32_t n_groups,
+                             int32_t *group_ptr, void *stream) {
+    if (!indptr || !group_ptr || n_rows < 0 || group_nnz < 1 || n_groups < 1) return GR_ERR_INVALID;
+    if (n_rows >= 0x7fffffffLL) return GR_ERR_OVERFLOW;
+    row_groups_kernel<<<(unsigned)((n_groups + 1 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        indptr, (int)n_rows, group_nnz, n_groups, group_ptr);
     GR_LAUNCH_CHECK();
     return GR_OK;
 }

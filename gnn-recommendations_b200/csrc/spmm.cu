@@ -38,6 +38,9 @@ struct SpmmArgs {
     long long ldo4;
     float scale;
     int scale_mode;
+    const int *group_ptr;  // streaming kernel: rows [group_ptr[g], group_ptr[g+1]) per sub-warp
+    int n_groups;
+    int long_thr;          // rows with >= long_thr entries are left to the long-row kernel
 };
 
 template <int D>
@@ -146,6 +149,163 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) spmm_warp_rows(const SpmmAr
                 st_stream_f4(a.out + (long long)r * a.ldo4 + off, scale4(o, a.scale, a.scale_mode));
             }
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// short rows, streaming: one GROUP of consecutive rows (about group_nnz entries) per sub-warp
+//
+// The sub-warp walks the group's entries as ONE contiguous stream: (col,val) chunks are loaded
+// coalesced and prefetched one chunk ahead, gathers are issued UNROLL at a time without regard to
+// row boundaries (no partial batches, no per-row pipeline restart, no per-row dependent
+// row_order -> indptr -> indices load chain).  Row boundaries only matter to the fmaf chain: when
+// the stream crosses indptr[r+1] the finished row is written (epilogue fused) and the accumulator
+// restarts from zero — each (row, feature) is still the exact storage-order chain.  indptr[r+2]
+// and the addend row are prefetched at the previous boundary.  Rows with >= long_thr entries
+// belong to the long-row kernel: the stream jumps over them.
+// ---------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(kWarpsPerCta * 32) spmm_stream_rows(const SpmmArgs a) {
+    using C = RowCfg<D>;
+    constexpr int LPR = C::LPR, VPL = C::VPL, SPW = C::RPW, UNROLL = C::UNROLL;
+    constexpr unsigned kFull = 0xffffffffu;
+
+    const uint64_t pol_s = policy_evict_first(), pol_g = policy_evict_last();
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int gl = lane % LPR;
+    const long long g = ((long long)blockIdx.x * kWarpsPerCta + warp) * SPW + lane / LPR;
+    const int n_rows = a.order_end;
+
+    int r = 0, r_end = 0, row_stop = 0, stop_next = 0, stream_end = 0, kc = 0, dead_until = 0;
+    float4 acc[VPL], add_cur[VPL];
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) acc[j] = add_cur[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    auto load_addend = [&](int row) {
+        if (a.addend) {
+#pragma unroll
+            for (int j = 0; j < VPL; ++j) add_cur[j] = __ldg(a.addend + (long long)row * a.lda4 + gl + j * LPR);
+        }
+    };
+    auto flush = [&](int row) {
+#pragma unroll
+        for (int j = 0; j < VPL; ++j) {
+            const int off = gl + j * LPR;
+            if (a.y) st_stream_f4(a.y + (long long)row * a.ldy4 + off, acc[j]);
+            if (a.out) {
+                float4 o = acc[j];
+                if (a.addend) o = add4(add_cur[j], o);
+                st_stream_f4(a.out + (long long)row * a.ldo4 + off, scale4(o, a.scale, a.scale_mode));
+            }
+            acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    // move to row r+1 (its end offset comes from the prefetched stop_next); jump over long rows
+    auto next_row = [&]() {
+        int rs = row_stop;
+        ++r;
+        row_stop = stop_next;
+        stop_next = (r + 2 <= n_rows) ? __ldg(a.indptr + r + 2) : row_stop;
+        while (r < r_end && row_stop - rs >= a.long_thr) {
+            dead_until = row_stop;
+            rs = row_stop;
+            ++r;
+            row_stop = stop_next;
+            stop_next = (r + 2 <= n_rows) ? __ldg(a.indptr + r + 2) : row_stop;
+        }
+        if (r < r_end) load_addend(r);
+    };
+
+    if (g < a.n_groups) {
+        r = a.group_ptr[g];
+        r_end = a.group_ptr[g + 1];
+    }
+    if (r < r_end) {
+        stream_end = a.indptr[r_end];
+        int rs = a.indptr[r];
+        row_stop = a.indptr[r + 1];
+        stop_next = (r + 2 <= n_rows) ? a.indptr[r + 2] : row_stop;
+        while (r < r_end && row_stop - rs >= a.long_thr) {
+            rs = row_stop;
+            ++r;
+            row_stop = stop_next;
+            stop_next = (r + 2 <= n_rows) ? a.indptr[r + 2] : row_stop;
+        }
+        kc = rs;
+        dead_until = rs;
+        if (r < r_end) load_addend(r);
+    }
+    if (r >= r_end) {
+        stream_end = 0;
+        kc = 0;
+    }
+
+    int c_cur = 0;
+    float v_cur = 0.f;
+    if (kc + gl < stream_end) {
+        c_cur = ld_stream_i32(a.indices + kc + gl, pol_s);
+        v_cur = ld_stream_f32(a.vals + kc + gl, pol_s);
+    }
+    while (__any_sync(kFull, kc < stream_end)) {
+        int c_nxt = 0;
+        float v_nxt = 0.f;
+        {
+            const int idx = kc + LPR + gl;
+            if (idx < stream_end) {
+                c_nxt = ld_stream_i32(a.indices + idx, pol_s);
+                v_nxt = ld_stream_f32(a.vals + idx, pol_s);
+            }
+        }
+#pragma unroll
+        for (int kk = 0; kk < LPR; kk += UNROLL) {
+            if (!__any_sync(kFull, kc + kk < stream_end)) break;
+            float4 xv[UNROLL][VPL];
+            float vv[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const int cc = __shfl_sync(kFull, c_cur, kk + u, LPR);
+                vv[u] = __shfl_sync(kFull, v_cur, kk + u, LPR);
+                const int e = kc + kk + u;
+                if (e < stream_end && e >= dead_until) {
+                    const float4 *src = a.x + (long long)cc * a.ldx4 + gl;
+#pragma unroll
+                    for (int j = 0; j < VPL; ++j) xv[u][j] = ld_gather_f4(src + j * LPR, pol_g);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const int e = kc + kk + u;
+                if (e < stream_end && e >= dead_until) {
+                    while (e >= row_stop) {  // row r is complete (or empty): write it, start the next
+                        flush(r);
+                        next_row();
+                    }
+                    if (e >= dead_until) {
+#pragma unroll
+                        for (int j = 0; j < VPL; ++j) fma4(acc[j], vv[u], xv[u][j]);
+                    }
+                }
+            }
+        }
+        if (dead_until > kc + LPR && kc < stream_end) {  // jump over a long row: reload the chunk registers
+            kc = dead_until;
+            c_cur = 0;
+            v_cur = 0.f;
+            if (kc + gl < stream_end) {
+                c_cur = ld_stream_i32(a.indices + kc + gl, pol_s);
+                v_cur = ld_stream_f32(a.vals + kc + gl, pol_s);
+            }
+        } else {
+            kc += LPR;
+            c_cur = c_nxt;
+            v_cur = v_nxt;
+        }
+    }
+    // the last row with entries and any trailing empty rows of the group
+    while (r < r_end) {
+        flush(r);
+        next_row();
     }
 }
 
@@ -339,7 +499,18 @@ static int launch(const SpmmArgs &base, int n_long, long long n_rows, int slot, 
         GR_CUDA_CHECK(cudaEventRecord(side->join, side->stream));
     }
     const long long rest = n_rows - (use_long ? n_long : 0);
-    if (rest > 0) {
+    if (base.group_ptr != nullptr) {
+        SpmmArgs wa = base;
+        wa.order_begin = 0;
+        wa.order_end = (int)n_rows;
+        if (!use_long) wa.long_thr = 0x7fffffff;
+        const long long per_cta = (long long)kWarpsPerCta * C::RPW;
+        const long long ctas = (base.n_groups + per_cta - 1) / per_cta;
+        if (ctas > 0) {
+            spmm_stream_rows<D><<<(unsigned)ctas, kWarpsPerCta * 32, 0, stream>>>(wa);
+            GR_LAUNCH_CHECK();
+        }
+    } else if (rest > 0) {
         SpmmArgs wa = base;
         wa.order_begin = use_long ? n_long : 0;
         wa.order_end = (int)n_rows;
@@ -355,13 +526,15 @@ static int launch(const SpmmArgs &base, int n_long, long long n_rows, int slot, 
 }  // namespace gr
 
 extern "C" int gr_spmm_csr_f32(const int32_t *indptr, const int32_t *indices, const float *vals,
-                               const int32_t *row_order, int32_t n_long, int64_t n_rows, int32_t d, const float *x,
+                               const int32_t *row_order, int32_t n_long, const int32_t *group_ptr,
+                               int32_t n_groups, int32_t long_threshold, int64_t n_rows, int32_t d, const float *x,
                                int64_t ldx, float *y, int64_t ldy, const float *addend, int64_t lda, float *out,
                                int64_t ldo, float scale, int32_t scale_mode, void *stream) {
     using namespace gr;
     if (n_rows == 0) return GR_OK;
     if (!indptr || !indices || !vals || !x || n_rows < 0 || n_long < 0 || n_long > n_rows) return GR_ERR_INVALID;
     if (!y && !out) return GR_ERR_INVALID;
+    if (group_ptr && (n_groups < 0 || long_threshold < 1)) return GR_ERR_INVALID;
     if (n_rows > 0x7fffffffLL) return GR_ERR_OVERFLOW;
     if (scale_mode < GR_SCALE_NONE || scale_mode > GR_SCALE_DIV) return GR_ERR_INVALID;
     if ((ldx & 3) || (y && (ldy & 3)) || (addend && (lda & 3)) || (out && (ldo & 3))) return GR_ERR_INVALID;
@@ -384,6 +557,9 @@ extern "C" int gr_spmm_csr_f32(const int32_t *indptr, const int32_t *indices, co
     a.ldo4 = ldo / 4;
     a.scale = scale;
     a.scale_mode = scale_mode;
+    a.group_ptr = group_ptr;
+    a.n_groups = group_ptr ? n_groups : 0;
+    a.long_thr = long_threshold;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     switch (d) {
         case 32: return launch<32>(a, n_long, n_rows, 0, s);

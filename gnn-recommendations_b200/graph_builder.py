@@ -21,6 +21,7 @@ from . import _lib
 from ._lib import check, lib, ptr, stream_ptr
 
 LONG_ROW_THRESHOLD = int(os.environ.get("GR_LONG_ROW_THRESHOLD", "1024"))
+GROUP_NNZ = int(os.environ.get("GR_GROUP_NNZ", "0"))      # 0 = choose by graph size
 _NORM_MODES = {"symmetric": 0, "row": 1, "none": 2}
 
 
@@ -48,6 +49,7 @@ class NormAdjCSR:
         self._transpose: Optional["NormAdjCSR"] = None
         self.row_order = None
         self.n_long = 0
+        self.group_ptr, self.n_groups, self.group_nnz = None, 0, 0
         self.timings = None      # set to a list to collect (start, end) CUDA events per SpMM launch
         self.launches = 0        # kernels launched by spmm() so far
         self.long_threshold = LONG_ROW_THRESHOLD if long_threshold is None else int(long_threshold)
@@ -85,6 +87,14 @@ class NormAdjCSR:
             check(l.gr_row_schedule(ptr(self.indptr), n, self.long_threshold, ptr(self.row_order), ptr(n_long),
                                     ptr(ws), ws_bytes, stream_ptr()), "gr_row_schedule")
         self.n_long = int(n_long.item())
+        # row groups for the streaming short-row kernel
+        if os.environ.get("GR_SPMM_STREAM", "1") != "0":
+            self.group_nnz = GROUP_NNZ if GROUP_NNZ > 0 else (256 if self.nnz < (1 << 26) else 512)
+            self.n_groups = self.nnz // self.group_nnz + 1
+            self.group_ptr = torch.empty(self.n_groups + 1, dtype=torch.int32, device=self.device)
+            with torch.cuda.device(self.device):
+                check(l.gr_row_groups(ptr(self.indptr), n, self.group_nnz, self.n_groups, ptr(self.group_ptr),
+                                      stream_ptr()), "gr_row_groups")
 
     @classmethod
     def from_torch_coo(cls, adj: torch.Tensor) -> "NormAdjCSR":
@@ -233,7 +243,8 @@ class NormAdjCSR:
                 ev[0].record()
             self.launches += 1 + (1 if (self.n_long > 0 and self.row_order is not None) else 0)
             check(lib().gr_spmm_csr_f32(
-                ptr(self.indptr), ptr(self.indices), ptr(self.vals), ptr(self.row_order), self.n_long, self.n_rows,
+                ptr(self.indptr), ptr(self.indices), ptr(self.vals), ptr(self.row_order), self.n_long,
+                ptr(self.group_ptr), self.n_groups, self.long_threshold, self.n_rows,
                 d, ptr(x), x.stride(0),
                 ptr(y), y.stride(0) if y is not None else 0,
                 ptr(addend), addend.stride(0) if addend is not None else 0,

@@ -94,6 +94,12 @@ size_t gr_row_schedule_workspace_bytes(int64_t n_rows);
 int gr_row_schedule(const int32_t *indptr, int64_t n_rows, int32_t long_threshold, int32_t *row_order,
                     int32_t *n_long_out, void *workspace, size_t workspace_bytes, void *stream);
 
+/* Row groups for the streaming short-row kernel: group g = rows whose first entry lies in
+ * [g*group_nnz, (g+1)*group_nnz); group_ptr has n_groups + 1 entries, n_groups must be
+ * nnz / group_nnz + 1. */
+int gr_row_groups(const int32_t *indptr, int64_t n_rows, int32_t group_nnz, int32_t n_groups, int32_t *group_ptr,
+                  void *stream);
+
 /* ------------------------------------------------------------------------------------------
  * Propagation
  * ------------------------------------------------------------------------------------------ */
@@ -106,12 +112,15 @@ int gr_row_schedule(const int32_t *indptr, int64_t n_rows, int32_t long_threshol
  *   y[r,:]   = t[r,:]                                   if y   != NULL
  *   out[r,:] = scale_op(addend ? addend[r,:] + t : t)   if out != NULL
  *
- * `row_order` may be NULL (natural order, n_long ignored).  Rows row_order[0..n_long) are
- * processed one CTA per row with the gathered x rows staged through shared memory by
- * cp.async; the rest one row per (sub-)warp with 128-bit gathers.  d in {32,64,128,256}.
- * n_rows may be a row block of a larger matrix (column ids index x, not y). */
+ * `row_order` may be NULL (natural order, n_long ignored).  Rows row_order[0..n_long) (those
+ * with >= long_threshold entries) are processed one CTA per row with the gathered x rows staged
+ * through shared memory by cp.async.  The remaining rows: with `group_ptr` (gr_row_groups) one
+ * group of consecutive rows per (sub-)warp as a continuous gather stream; without it one row per
+ * (sub-)warp in row_order.  d in {32,64,128,256}.  n_rows may be a row block of a larger matrix
+ * (column ids index x, not y). */
 int gr_spmm_csr_f32(const int32_t *indptr, const int32_t *indices, const float *vals,
-                    const int32_t *row_order, int32_t n_long, int64_t n_rows, int32_t d, const float *x,
+                    const int32_t *row_order, int32_t n_long, const int32_t *group_ptr, int32_t n_groups,
+                    int32_t long_threshold, int64_t n_rows, int32_t d, const float *x,
                     int64_t ldx, float *y, int64_t ldy, const float *addend, int64_t lda, float *out,
                     int64_t ldo, float scale, int32_t scale_mode, void *stream);
 
