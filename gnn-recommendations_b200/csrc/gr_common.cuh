@@ -88,6 +88,16 @@ __device__ __forceinline__ void cp_async4(void *smem_dst, const void *gmem_src, 
     asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 4, %2;" ::"r"(s), "l"(gmem_src), "l"(pol)
                  : "memory");
 }
+// hint-free variants (the persistent long-row kernel: ptxas keeps the policy descriptor in uniform
+// registers, and the looped kernel faulted with "illegal instruction" on LDGSTS with a hint)
+__device__ __forceinline__ void cp_async16_plain(void *smem_dst, const void *gmem_src) {
+    unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async4_plain(void *smem_dst, const void *gmem_src) {
+    unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gmem_src) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {

@@ -334,6 +334,10 @@ struct LongCfg {
     static_assert(STAGES - 1 <= IDX_AHEAD && STAGES + IDX_AHEAD + 1 <= IDX_RING, "index ring too small");
 };
 
+// ticket counter of the persistent long-row kernel; zeroed on the side stream before each launch
+// (one gr_spmm_csr_f32 in flight per device at a time)
+__device__ unsigned int g_long_ticket = 0;
+
 template <int D>
 __global__ void __launch_bounds__(LongCfg<D>::THREADS, 1) spmm_long_rows(const SpmmArgs a) {
     using L = LongCfg<D>;
@@ -353,7 +357,16 @@ __global__ void __launch_bounds__(LongCfg<D>::THREADS, 1) spmm_long_rows(const S
     const int warp = threadIdx.x >> 5;
     const bool is_cons = warp < CONS;
     const int p = warp - CONS;  // producer index, < 0 for consumers
-    const int r = a.row_order[a.order_begin + blockIdx.x];
+
+    // persistent CTAs: rows are handed out in row_order (longest first) through a ticket counter,
+    // so the hottest row starts first and no CTA queues work behind it.
+    int &s_ticket = *reinterpret_cast<int *>(smem_raw + L::SMEM);  // one int after the rings
+    for (;;) {
+    if (threadIdx.x == 0) s_ticket = (int)atomicAdd(&g_long_ticket, 1u);
+    __syncthreads();
+    const int ticket = s_ticket;
+    if (ticket >= a.order_end - a.order_begin) break;
+    const int r = a.row_order[a.order_begin + ticket];
     const int start = a.indptr[r];
     const int len = a.indptr[r + 1] - start;
     const int nchunks = (len + CH - 1) / CH;
@@ -368,8 +381,8 @@ __global__ void __launch_bounds__(LongCfg<D>::THREADS, 1) spmm_long_rows(const S
                 const int e = lane + 32 * t;
                 const int idx = chunk * CH + e;
                 if (idx < len) {
-                    cp_async4(cs + slot * CH + e, ci + idx, pol_s);
-                    cp_async4(vs + slot * CH + e, cv + idx, pol_s);
+                    cp_async4_plain(cs + slot * CH + e, ci + idx);
+                    cp_async4_plain(vs + slot * CH + e, cv + idx);
                 }
             }
         }
@@ -386,7 +399,7 @@ __global__ void __launch_bounds__(LongCfg<D>::THREADS, 1) spmm_long_rows(const S
                 const int f = item % F4;
                 if (e < nvalid) {
                     const int cc = cs[slot * CH + e];
-                    cp_async16(xs + ((size_t)stage * CH + e) * F4 + f, a.x + (long long)cc * a.ldx4 + f, pol_g);
+                    cp_async16_plain(xs + ((size_t)stage * CH + e) * F4 + f, a.x + (long long)cc * a.ldx4 + f);
                 }
             }
         }
@@ -444,6 +457,8 @@ __global__ void __launch_bounds__(LongCfg<D>::THREADS, 1) spmm_long_rows(const S
             reinterpret_cast<float *>(a.out + (long long)r * a.ldo4)[f] = apply_scale(o, a.scale, a.scale_mode);
         }
     }
+    __syncthreads();  // the rings are reused by the next row
+    }  // ticket loop
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -486,7 +501,7 @@ static int launch(const SpmmArgs &base, int n_long, long long n_rows, int slot, 
         if (rc != GR_OK) return rc;
         if (!side->smem_attr_set[slot]) {
             GR_CUDA_CHECK(cudaFuncSetAttribute(spmm_long_rows<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               (int)L::SMEM));
+                                               (int)L::SMEM + 16));
             side->smem_attr_set[slot] = true;
         }
         GR_CUDA_CHECK(cudaEventRecord(side->fork, stream));
@@ -494,7 +509,13 @@ static int launch(const SpmmArgs &base, int n_long, long long n_rows, int slot, 
         SpmmArgs la = base;
         la.order_begin = 0;
         la.order_end = n_long;
-        spmm_long_rows<D><<<n_long, L::THREADS, L::SMEM, side->stream>>>(la);
+        void *ticket_addr = nullptr;
+        GR_CUDA_CHECK(cudaGetSymbolAddress(&ticket_addr, g_long_ticket));
+        GR_CUDA_CHECK(cudaMemsetAsync(ticket_addr, 0, sizeof(unsigned int), side->stream));
+        int long_ctas = sm_count();
+        if (long_ctas > n_long) long_ctas = n_long;
+        if (long_ctas < 1) long_ctas = 1;
+        spmm_long_rows<D><<<long_ctas, L::THREADS, L::SMEM + 16, side->stream>>>(la);
         GR_LAUNCH_CHECK();
         GR_CUDA_CHECK(cudaEventRecord(side->join, side->stream));
     }
