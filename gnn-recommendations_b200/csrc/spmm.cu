@@ -41,6 +41,14 @@ struct SpmmArgs {
     const int *group_ptr;  // streaming kernel: rows [group_ptr[g], group_ptr[g+1]) per sub-warp
     int n_groups;
     int long_thr;          // rows with >= long_thr entries are left to the long-row kernel
+    // long-row work items (optional): [4][n_items] = row, offset into the row, length, partial slot
+    // (-1: the item is a whole row).  Rows above the split threshold are cut into segments whose
+    // partial chains land in part_buf and are added in segment order by spmm_combine_parts.
+    const int *items;
+    int n_items;
+    const int *split_rows;  // [3][n_split] = row, first partial slot, number of partials
+    int n_split;
+    float *part_buf;        // [n_partials][D]
 };
 
 template <int D>
@@ -365,10 +373,19 @@ __global__ void __launch_bounds__(LongCfg<D>::THREADS, 1) spmm_long_rows(const S
     if (threadIdx.x == 0) s_ticket = (int)atomicAdd(&g_long_ticket, 1u);
     __syncthreads();
     const int ticket = s_ticket;
-    if (ticket >= a.order_end - a.order_begin) break;
-    const int r = a.row_order[a.order_begin + ticket];
-    const int start = a.indptr[r];
-    const int len = a.indptr[r + 1] - start;
+    int r, start, len, part = -1;
+    if (a.items) {
+        if (ticket >= a.n_items) break;
+        r = a.items[ticket];
+        start = a.indptr[r] + a.items[a.n_items + ticket];
+        len = a.items[2 * a.n_items + ticket];
+        part = a.items[3 * a.n_items + ticket];
+    } else {
+        if (ticket >= a.order_end - a.order_begin) break;
+        r = a.row_order[a.order_begin + ticket];
+        start = a.indptr[r];
+        len = a.indptr[r + 1] - start;
+    }
     const int nchunks = (len + CH - 1) / CH;
     const int *ci = a.indices + start;
     const float *cv = a.vals + start;
@@ -448,7 +465,9 @@ __global__ void __launch_bounds__(LongCfg<D>::THREADS, 1) spmm_long_rows(const S
     }
     cp_async_wait<0>();
 
-    if (is_cons) {
+    if (is_cons && part >= 0) {
+        a.part_buf[(long long)part * D + warp * 32 + lane] = acc;
+    } else if (is_cons) {
         const int f = warp * 32 + lane;
         if (a.y) reinterpret_cast<float *>(a.y + (long long)r * a.ldy4)[f] = acc;
         if (a.out) {
@@ -459,6 +478,24 @@ __global__ void __launch_bounds__(LongCfg<D>::THREADS, 1) spmm_long_rows(const S
     }
     __syncthreads();  // the rings are reused by the next row
     }  // ticket loop
+}
+
+// Split rows: total = ((p0 + p1) + p2) + ... in segment order, then the usual epilogue.
+__global__ void spmm_combine_parts(const SpmmArgs a, int d) {
+    const int sidx = blockIdx.x;
+    const int r = a.split_rows[sidx];
+    const int first = a.split_rows[a.n_split + sidx];
+    const int n = a.split_rows[2 * a.n_split + sidx];
+    for (int f = threadIdx.x; f < d; f += blockDim.x) {
+        float t = a.part_buf[(long long)first * d + f];
+        for (int k = 1; k < n; ++k) t = __fadd_rn(t, a.part_buf[(long long)(first + k) * d + f]);
+        if (a.y) reinterpret_cast<float *>(a.y + (long long)r * a.ldy4)[f] = t;
+        if (a.out) {
+            float o = t;
+            if (a.addend) o = __fadd_rn(reinterpret_cast<const float *>(a.addend + (long long)r * a.lda4)[f], o);
+            reinterpret_cast<float *>(a.out + (long long)r * a.ldo4)[f] = apply_scale(o, a.scale, a.scale_mode);
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -512,11 +549,16 @@ static int launch(const SpmmArgs &base, int n_long, long long n_rows, int slot, 
         void *ticket_addr = nullptr;
         GR_CUDA_CHECK(cudaGetSymbolAddress(&ticket_addr, g_long_ticket));
         GR_CUDA_CHECK(cudaMemsetAsync(ticket_addr, 0, sizeof(unsigned int), side->stream));
+        const int n_work = la.items ? la.n_items : n_long;
         int long_ctas = sm_count();
-        if (long_ctas > n_long) long_ctas = n_long;
+        if (long_ctas > n_work) long_ctas = n_work;
         if (long_ctas < 1) long_ctas = 1;
         spmm_long_rows<D><<<long_ctas, L::THREADS, L::SMEM + 16, side->stream>>>(la);
         GR_LAUNCH_CHECK();
+        if (la.items && la.n_split > 0) {
+            spmm_combine_parts<<<la.n_split, 128, 0, side->stream>>>(la, D);
+            GR_LAUNCH_CHECK();
+        }
         GR_CUDA_CHECK(cudaEventRecord(side->join, side->stream));
     }
     const long long rest = n_rows - (use_long ? n_long : 0);
@@ -547,7 +589,9 @@ static int launch(const SpmmArgs &base, int n_long, long long n_rows, int slot, 
 }  // namespace gr
 
 extern "C" int gr_spmm_csr_f32(const int32_t *indptr, const int32_t *indices, const float *vals,
-                               const int32_t *row_order, int32_t n_long, const int32_t *group_ptr,
+                               const int32_t *row_order, int32_t n_long, const int32_t *long_items,
+                               int32_t n_long_items, const int32_t *split_rows, int32_t n_split, float *part_buf,
+                               const int32_t *group_ptr,
                                int32_t n_groups, int32_t long_threshold, int64_t n_rows, int32_t d, const float *x,
                                int64_t ldx, float *y, int64_t ldy, const float *addend, int64_t lda, float *out,
                                int64_t ldo, float scale, int32_t scale_mode, void *stream) {
@@ -556,6 +600,8 @@ extern "C" int gr_spmm_csr_f32(const int32_t *indptr, const int32_t *indices, co
     if (!indptr || !indices || !vals || !x || n_rows < 0 || n_long < 0 || n_long > n_rows) return GR_ERR_INVALID;
     if (!y && !out) return GR_ERR_INVALID;
     if (group_ptr && (n_groups < 0 || long_threshold < 1)) return GR_ERR_INVALID;
+    if (long_items && (!row_order || n_long_items < n_long || n_split < 0 || (n_split > 0 && (!split_rows || !part_buf))))
+        return GR_ERR_INVALID;
     if (n_rows > 0x7fffffffLL) return GR_ERR_OVERFLOW;
     if (scale_mode < GR_SCALE_NONE || scale_mode > GR_SCALE_DIV) return GR_ERR_INVALID;
     if ((ldx & 3) || (y && (ldy & 3)) || (addend && (lda & 3)) || (out && (ldo & 3))) return GR_ERR_INVALID;
@@ -581,6 +627,11 @@ extern "C" int gr_spmm_csr_f32(const int32_t *indptr, const int32_t *indices, co
     a.group_ptr = group_ptr;
     a.n_groups = group_ptr ? n_groups : 0;
     a.long_thr = long_threshold;
+    a.items = long_items;
+    a.n_items = long_items ? n_long_items : 0;
+    a.split_rows = split_rows;
+    a.n_split = long_items ? n_split : 0;
+    a.part_buf = part_buf;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     switch (d) {
         case 32: return launch<32>(a, n_long, n_rows, 0, s);

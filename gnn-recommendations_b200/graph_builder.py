@@ -22,6 +22,11 @@ from ._lib import check, lib, ptr, stream_ptr
 
 LONG_ROW_THRESHOLD = int(os.environ.get("GR_LONG_ROW_THRESHOLD", "1024"))
 GROUP_NNZ = int(os.environ.get("GR_GROUP_NNZ", "0"))      # 0 = choose by graph size
+# Rows above SPLIT_ROW_THRESHOLD entries are cut into SPLIT_ROW_SEGMENT-entry segments processed by
+# different CTAs (partials added in segment order).  No dataset shape of the reference has such a
+# row (max degree <= 91 599 at the Amazon-Book shape), so C1-C4 stay on the exact single chain.
+SPLIT_ROW_THRESHOLD = int(os.environ.get("GR_SPLIT_ROW_THRESHOLD", "131072"))
+SPLIT_ROW_SEGMENT = int(os.environ.get("GR_SPLIT_ROW_SEGMENT", "65536"))
 _NORM_MODES = {"symmetric": 0, "row": 1, "none": 2}
 
 
@@ -50,6 +55,8 @@ class NormAdjCSR:
         self.row_order = None
         self.n_long = 0
         self.group_ptr, self.n_groups, self.group_nnz = None, 0, 0
+        self.long_items, self.n_long_items, self.split_rows, self.n_split, self.n_parts = None, 0, None, 0, 0
+        self._part_buf = {}
         self.timings = None      # set to a list to collect (start, end) CUDA events per SpMM launch
         self.launches = 0        # kernels launched by spmm() so far
         self.long_threshold = LONG_ROW_THRESHOLD if long_threshold is None else int(long_threshold)
@@ -87,6 +94,7 @@ class NormAdjCSR:
             check(l.gr_row_schedule(ptr(self.indptr), n, self.long_threshold, ptr(self.row_order), ptr(n_long),
                                     ptr(ws), ws_bytes, stream_ptr()), "gr_row_schedule")
         self.n_long = int(n_long.item())
+        self._build_long_items()
         # row groups for the streaming short-row kernel
         if os.environ.get("GR_SPMM_STREAM", "1") != "0":
             self.group_nnz = GROUP_NNZ if GROUP_NNZ > 0 else (256 if self.nnz < (1 << 26) else 512)
@@ -95,6 +103,53 @@ class NormAdjCSR:
             with torch.cuda.device(self.device):
                 check(l.gr_row_groups(ptr(self.indptr), n, self.group_nnz, self.n_groups, ptr(self.group_ptr),
                                       stream_ptr()), "gr_row_groups")
+
+    def _build_long_items(self) -> None:
+        """Work items of the long-row kernel when some row exceeds the split threshold: whole rows
+        and SPLIT_ROW_SEGMENT-entry segments of the extreme rows, longest first."""
+        self.long_items, self.n_long_items, self.split_rows, self.n_split, self.n_parts = None, 0, None, 0, 0
+        self._part_buf = {}
+        thr = getattr(self, "split_threshold", SPLIT_ROW_THRESHOLD)
+        seg = getattr(self, "split_segment", SPLIT_ROW_SEGMENT)
+        if self.n_long == 0:
+            return
+        rows = self.row_order[: self.n_long].long()
+        lens = (self.indptr[rows + 1] - self.indptr[rows]).cpu().numpy().astype(np.int64)
+        if lens.max() <= thr:
+            return
+        rows = rows.cpu().numpy()
+        it_row, it_off, it_len, it_part, sp = [], [], [], [], []
+        n_parts = 0
+        for r, ln in zip(rows.tolist(), lens.tolist()):
+            if ln > thr:
+                k = -(-ln // seg)
+                sp.append((r, n_parts, k))
+                for j in range(k):
+                    it_row.append(r)
+                    it_off.append(j * seg)
+                    it_len.append(min(seg, ln - j * seg))
+                    it_part.append(n_parts + j)
+                n_parts += k
+            else:
+                it_row.append(r)
+                it_off.append(0)
+                it_len.append(ln)
+                it_part.append(-1)
+        order = np.argsort(-np.asarray(it_len), kind="stable")
+        items = np.stack([np.asarray(a, dtype=np.int32)[order] for a in (it_row, it_off, it_len, it_part)])
+        self.long_items = torch.from_numpy(np.ascontiguousarray(items)).to(self.device)
+        self.n_long_items = int(items.shape[1])
+        self.split_rows = torch.from_numpy(np.ascontiguousarray(np.asarray(sp, dtype=np.int32).T)).to(self.device)
+        self.n_split, self.n_parts = len(sp), n_parts
+
+    def _parts(self, d: int):
+        if self.n_parts == 0:
+            return None
+        buf = self._part_buf.get(d)
+        if buf is None:
+            buf = torch.empty((self.n_parts, d), dtype=torch.float32, device=self.device)
+            self._part_buf[d] = buf
+        return buf
 
     @classmethod
     def from_torch_coo(cls, adj: torch.Tensor) -> "NormAdjCSR":
@@ -241,9 +296,11 @@ class NormAdjCSR:
             if self.timings is not None:
                 ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
                 ev[0].record()
-            self.launches += 1 + (1 if (self.n_long > 0 and self.row_order is not None) else 0)
+            self.launches += 1 + (1 if (self.n_long > 0 and self.row_order is not None) else 0) + \
+                (1 if self.n_split > 0 else 0)
             check(lib().gr_spmm_csr_f32(
                 ptr(self.indptr), ptr(self.indices), ptr(self.vals), ptr(self.row_order), self.n_long,
+                ptr(self.long_items), self.n_long_items, ptr(self.split_rows), self.n_split, ptr(self._parts(d)),
                 ptr(self.group_ptr), self.n_groups, self.long_threshold, self.n_rows,
                 d, ptr(x), x.stride(0),
                 ptr(y), y.stride(0) if y is not None else 0,

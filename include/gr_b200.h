@@ -117,9 +117,19 @@ int gr_row_groups(const int32_t *indptr, int64_t n_rows, int32_t group_nnz, int3
  * through shared memory by cp.async.  The remaining rows: with `group_ptr` (gr_row_groups) one
  * group of consecutive rows per (sub-)warp as a continuous gather stream; without it one row per
  * (sub-)warp in row_order.  d in {32,64,128,256}.  n_rows may be a row block of a larger matrix
- * (column ids index x, not y). */
+ * (column ids index x, not y).
+ *
+ * Optional split of extreme rows (`long_items` != NULL): the long-row kernel then works through
+ * `long_items` = int32[4][n_long_items] (row, offset into the row, length, partial slot or -1)
+ * instead of whole rows; a row cut into segments has each segment's chain stored in
+ * part_buf[slot][d] and the partials added in segment order by a combine pass driven by
+ * `split_rows` = int32[3][n_split] (row, first slot, number of slots).  A split row is no longer the
+ * single storage-order chain (deterministic, ~1e-7 relative); the host layer only splits rows
+ * above 131 072 entries, which none of the reference's dataset shapes has. */
 int gr_spmm_csr_f32(const int32_t *indptr, const int32_t *indices, const float *vals,
-                    const int32_t *row_order, int32_t n_long, const int32_t *group_ptr, int32_t n_groups,
+                    const int32_t *row_order, int32_t n_long, const int32_t *long_items,
+                    int32_t n_long_items, const int32_t *split_rows, int32_t n_split, float *part_buf,
+                    const int32_t *group_ptr, int32_t n_groups,
                     int32_t long_threshold, int64_t n_rows, int32_t d, const float *x,
                     int64_t ldx, float *y, int64_t ldy, const float *addend, int64_t lda, float *out,
                     int64_t ldo, float scale, int32_t scale_mode, void *stream);

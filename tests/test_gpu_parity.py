@@ -248,3 +248,44 @@ def test_multi_gpu_bit_identical_when_two_gpus_present():
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "propagation_bit_identical=True topk_bit_identical=True" in r.stdout
+
+
+def test_spmm_split_rows_deterministic_segment_sums():
+    """Rows above the split threshold are cut into segments; the result must equal, bit for bit, the sum
+    (in segment order) of the exact per-segment chains, and stay within 1e-6 of the single chain."""
+    rng = np.random.default_rng(9)
+    nu, ni = 6000, 50
+    u = np.concatenate([np.arange(nu), rng.integers(0, nu, 20000)])
+    i = np.concatenate([np.zeros(nu, dtype=np.int64), rng.integers(1, ni, 20000)])
+    ref = po.build_norm_adj(u, i, nu, ni)
+    csr = g.NormAdjCSR.from_pairs(u, i, nu, ni, device=DEV)
+    csr.split_threshold, csr.split_segment = 2048, 1000
+    csr._schedule()
+    assert csr.n_split >= 1 and csr.n_parts >= 6
+    hot = nu                                            # item 0: adjacent to every user
+    lens = np.diff(ref["indptr"])
+    assert lens[hot] == nu
+    for d in (64, 128):
+        x = torch.randn(ref["n"], d, generator=torch.Generator().manual_seed(d))
+        exact = coracle.spmm_fmaf(ref["indptr"], ref["indices"], ref["vals"], x.numpy())
+        y1, _ = csr.spmm(x.to(DEV))
+        y2, _ = csr.spmm(x.to(DEV))
+        assert torch.equal(y1, y2)                       # deterministic
+        got = y1.cpu().numpy()
+        split = set(csr.split_rows[0].cpu().tolist())
+        keep = np.array([r not in split for r in range(ref["n"])])
+        assert np.array_equal(bits(got[keep]), bits(exact[keep]))          # unsplit rows: exact chain
+        for r in split:
+            s, e = ref["indptr"][r], ref["indptr"][r + 1]
+            cuts = list(range(s, e, 1000)) + [e]
+            ip = np.asarray(cuts, dtype=np.int64)
+            parts = coracle.spmm_fmaf(ip - ip[0], ref["indices"][s:e], ref["vals"][s:e], x.numpy())
+            tot = parts[0].copy()
+            for p in parts[1:]:
+                tot = tot + p
+            assert np.array_equal(bits(got[r]), bits(tot))
+            np.testing.assert_allclose(got[r], exact[r], rtol=1e-5, atol=1e-6)
+        # epilogue on a split row
+        add = torch.randn(ref["n"], d, generator=torch.Generator().manual_seed(1))
+        _, out = csr.spmm(x.to(DEV), addend=add.to(DEV), scale=4.0, scale_mode=_lib.GR_SCALE_DIV, want_y=False)
+        assert np.array_equal(bits(out.cpu().numpy()), bits((add.numpy() + got) / np.float32(4.0)))
