@@ -352,6 +352,13 @@ def run_b200(args):
                          f"3 full forwards after 1 warm-up, torch CPU torch.sparse.mm (oracle port of "
                          f"lightgcn.py:62-104)"}
 
+    # ---- the rest of the path, small configs (not the headline; N=1 only) -------------------------
+    extras = None
+    if rank == 0 and world == 1 and not args.no_extras:
+        model = csr = full = None
+        torch.cuda.empty_cache()
+        extras = run_extras(g, dev)
+
     if rank == 0:
         line = {
             "metric": "lightgcn_propagation_edges_per_s", "value": value, "unit": "edges/s", "n_gpus": world,
@@ -360,11 +367,69 @@ def run_b200(args):
             "config": workload_config(args.workload, world),
             "clocks": sampler.summary() if sampler else None,
             "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-            "setup_s": t_setup, "nnz": nnz, "long_rows": n_long,
+            "setup_s": t_setup, "nnz": nnz, "long_rows": n_long, "extras": extras,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_extras(g, dev):
+    """Secondary measurements of the other path stages at the small dataset shapes: full-ranking
+    top-20 evaluation (C4, Amazon-Book shape) and one full training epoch with the reference's
+    semantics — a complete propagation forward + backward per 512-triple step — (C1, ML-1M shape)."""
+    from gnn_recommendations_b200.evaluator import full_rank_topk, seen_csr
+    from gnn_recommendations_b200.synthetic import synth_pairs_device
+
+    out = {}
+    # --- eval users/s at C4: scores + seen-mask + top-20 for every user, catalogue 91 599 items
+    nu, ni, e, d, L = WORKLOADS["C4"]
+    u, i = synth_pairs_device(nu, ni, e, 42, dev)
+    csr = g.NormAdjCSR.from_pairs(u, i, nu, ni, device=dev)
+    with torch.device(dev):
+        model = g.LightGCN(nu, ni, embedding_dim=d, n_layers=L, init_scale=0.1)
+    with torch.no_grad():
+        ue, ie = model.get_all_embeddings(csr)
+    eval_users = np.arange(nu)
+    ip, it = seen_csr(eval_users, nu, (u.cpu().numpy(), i.cpu().numpy()))
+    ip_d, it_d = torch.from_numpy(ip).to(dev), torch.from_numpy(it).to(dev)
+    eu_d = torch.from_numpy(eval_users).to(dev)
+    for _ in range(2):
+        full_rank_topk(ue, ie, eu_d, ip_d, it_d, 20)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        full_rank_topk(ue, ie, eu_d, ip_d, it_d, 20)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 3
+    out["eval_c4"] = {"users_per_s": nu / (ms * 1e-3), "ms": ms, "users": nu, "items": ni, "k": 20, "d": d,
+                      "gflop_per_s": 2.0 * nu * ni * d / (ms * 1e-3) / 1e9,
+                      "what": "gr_score_topk: exact fp32 scores + seen mask + top-20, all users"}
+    del csr, model, ue, ie
+    # --- epoch time at C1: 1 954 steps of sample + propagate + fused BPR + backward + clip + Adam
+    nu, ni, e, d, L = WORKLOADS["C1"]
+    u, i = synth_pairs_device(nu, ni, e, 42, dev)
+    empty = (np.zeros(0, np.int64), np.zeros(0, np.int64))
+    ds = g.InteractionDataset((u.cpu().numpy(), i.cpu().numpy()), empty, empty, nu, ni, device=dev, name="C1")
+    torch.manual_seed(42)
+    model = g.LightGCN(nu, ni, embedding_dim=d, n_layers=L, init_scale=0.1)
+    cfg = {"batch_size": 512, "learning_rate": 1e-3, "weight_decay": 1e-4, "use_scheduler": False,
+           "checkpoint_dir": "/tmp/gr_bench_ckpt"}
+    tr = g.Trainer(model, ds, cfg, device=dev)
+    steps = len(u) // 512 + 1
+    tr.batch_size = 512
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    loss = tr.train_epoch()
+    torch.cuda.synchronize()
+    sec = time.perf_counter() - t0
+    out["epoch_c1"] = {"epoch_s": sec, "steps": steps, "ms_per_step": sec / steps * 1e3, "loss": loss,
+                       "edge_traversals_per_s": steps * 2 * L * 2 * e / sec,
+                       "what": "Trainer.train_epoch at the ML-1M shape (B=512, full propagation fwd+bwd per step, "
+                               "host sampler included); reference CPU: 1410.6 s (BASELINE.md)"}
+    return out
 
 
 class _Null:
@@ -384,6 +449,7 @@ def main():
     ap.add_argument("--workload", default=os.environ.get("GR_BENCH_WORKLOAD", "C5"), choices=sorted(WORKLOADS))
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
