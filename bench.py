@@ -166,8 +166,9 @@ def workload_config(name, n_gpus):
     nu, ni, e, d, L = WORKLOADS[name]
     return {"workload": f"{name}: LightGCN {L}-layer d={d} fp32 propagation, synthetic power-law graph "
                         f"{nu} users x {ni} items, {e} edges (nnz(A_hat)={2 * e})",
-            "partition": "single GPU" if n_gpus == 1 else f"rows split in {n_gpus} nnz-balanced blocks, "
-                                                           "all-gather of layer rows per layer (NCCL)",
+            "partition": "single GPU" if n_gpus == 1 else f"rows split in {n_gpus} nnz-balanced blocks; layer rows "
+                                                           "exchanged by P2P stores from the SpMM epilogue (fused "
+                                                           "all-gather) or NCCL all-gather (--nccl-allgather)",
             "l2": f"inputs larger than L2 (table {(nu + ni) * d * 4 / 1e9:.2f} GB, CSR {2 * e * 8 / 1e9:.2f} GB)"
             if (nu + ni) * d * 4 + 2 * e * 8 > 2 * 126e6 else "L2 flushed between iterations (256 MB write)"}
 
@@ -224,8 +225,24 @@ def run_b200(args):
         del full
         torch.cuda.empty_cache()
         x0_local = torch.randn(r1 - r0, d, device=dev, generator=gen) * 0.1
+        exchange = None
+        if not args.nccl_allgather:
+            try:
+                from gnn_recommendations_b200.dist import PeerExchange, lightgcn_propagate_fused
+
+                exchange = PeerExchange(part, d, dev)
+            except Exception as err:  # symmetric memory unavailable: NCCL all-gather path
+                if rank == 0:
+                    print(f"[bench] peer exchange unavailable ({type(err).__name__}: {err}); using NCCL all-gather",
+                          file=sys.stderr)
+        ok = torch.tensor([1 if exchange is not None else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            exchange = None
 
         def step():
+            if exchange is not None:
+                return lightgcn_propagate_fused(csr, exchange, x0_local, L)
             return lightgcn_propagate_sharded(csr, part, rank, x0_local, L)
         n_rows_local = r1 - r0
 
@@ -325,7 +342,8 @@ def run_b200(args):
                 out_host[:nu].copy_(ue, non_blocking=True)
                 out_host[nu:].copy_(ie, non_blocking=True)
             else:
-                out = lightgcn_propagate_sharded(loc, part, rank, x0_local, L)
+                out = (lightgcn_propagate_fused(loc, exchange, x0_local, L) if exchange is not None
+                       else lightgcn_propagate_sharded(loc, part, rank, x0_local, L))
                 out_host.copy_(out, non_blocking=True)
             torch.cuda.current_stream().synchronize()
             return float(out_host[0, 0])
@@ -368,6 +386,7 @@ def run_b200(args):
             "clocks": sampler.summary() if sampler else None,
             "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
             "setup_s": t_setup, "nnz": nnz, "long_rows": n_long, "extras": extras,
+            "exchange": None if world == 1 else ("fused_peer_stores" if exchange is not None else "nccl_all_gather"),
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -450,6 +469,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--nccl-allgather", action="store_true", help="N>1: NCCL all-gather per layer instead of the "
+                    "fused peer-store exchange")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

@@ -21,6 +21,8 @@
 
 namespace gr {
 
+constexpr int kMaxPeers = 8;
+
 struct SpmmArgs {
     const int *indptr;
     const int *indices;
@@ -49,6 +51,11 @@ struct SpmmArgs {
     const int *split_rows;  // [3][n_split] = row, first partial slot, number of partials
     int n_split;
     float *part_buf;        // [n_partials][D]
+    // fused all-gather: t[r,:] is also stored to row (peer_row_off + r) of every peer's gathered
+    // buffer (NVLink P2P stores from the epilogue; ld = ldy4).  n_peers = 0 disables it.
+    float4 *peer_y[kMaxPeers];
+    int n_peers;
+    long long peer_row_off;
 };
 
 template <int D>
@@ -201,6 +208,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) spmm_stream_rows(const Spmm
         for (int j = 0; j < VPL; ++j) {
             const int off = gl + j * LPR;
             if (a.y) st_stream_f4(a.y + (long long)row * a.ldy4 + off, acc[j]);
+            for (int p = 0; p < a.n_peers; ++p)
+                a.peer_y[p][(a.peer_row_off + row) * a.ldy4 + off] = acc[j];
             if (a.out) {
                 float4 o = acc[j];
                 if (a.addend) o = add4(add_cur[j], o);
@@ -470,6 +479,8 @@ __global__ void __launch_bounds__(LongCfg<D>::THREADS, 1) spmm_long_rows(const S
     } else if (is_cons) {
         const int f = warp * 32 + lane;
         if (a.y) reinterpret_cast<float *>(a.y + (long long)r * a.ldy4)[f] = acc;
+        for (int p = 0; p < a.n_peers; ++p)
+            reinterpret_cast<float *>(a.peer_y[p] + (a.peer_row_off + r) * a.ldy4)[f] = acc;
         if (a.out) {
             float o = acc;
             if (a.addend) o = __fadd_rn(reinterpret_cast<const float *>(a.addend + (long long)r * a.lda4)[f], o);
@@ -490,6 +501,8 @@ __global__ void spmm_combine_parts(const SpmmArgs a, int d) {
         float t = a.part_buf[(long long)first * d + f];
         for (int k = 1; k < n; ++k) t = __fadd_rn(t, a.part_buf[(long long)(first + k) * d + f]);
         if (a.y) reinterpret_cast<float *>(a.y + (long long)r * a.ldy4)[f] = t;
+        for (int p = 0; p < a.n_peers; ++p)
+            reinterpret_cast<float *>(a.peer_y[p] + (a.peer_row_off + r) * a.ldy4)[f] = t;
         if (a.out) {
             float o = t;
             if (a.addend) o = __fadd_rn(reinterpret_cast<const float *>(a.addend + (long long)r * a.lda4)[f], o);
@@ -586,7 +599,45 @@ static int launch(const SpmmArgs &base, int n_long, long long n_rows, int slot, 
     return GR_OK;
 }
 
+// rows [0, n_rows) of src -> rows [row_off, row_off + n_rows) of every peer buffer (layer-0 exchange)
+__global__ void peer_scatter_rows_kernel(const float4 *src, long long lds4, long long n_rows, int f4,
+                                         SpmmArgs a) {
+    const long long total = n_rows * f4;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const long long r = i / f4;
+        const int f = (int)(i % f4);
+        const float4 v = __ldg(src + r * lds4 + f);
+        for (int p = 0; p < a.n_peers; ++p) a.peer_y[p][(a.peer_row_off + r) * a.ldy4 + f] = v;
+    }
+}
+
 }  // namespace gr
+
+extern "C" int gr_peer_scatter_rows(const float *src, int64_t lds, int64_t n_rows, int32_t d,
+                                    float *const *peer_dst_host, int32_t n_peers, int64_t ldd,
+                                    int64_t peer_row_offset, void *stream) {
+    using namespace gr;
+    if (!src || !peer_dst_host || n_rows < 0 || n_peers < 1 || n_peers > kMaxPeers) return GR_ERR_INVALID;
+    if ((d & 3) || (lds & 3) || (ldd & 3) || lds < d || ldd < d || !aligned16(src)) return GR_ERR_INVALID;
+    if (n_rows == 0) return GR_OK;
+    SpmmArgs a = {};
+    a.n_peers = n_peers;
+    a.peer_row_off = peer_row_offset;
+    a.ldy4 = ldd / 4;
+    for (int p = 0; p < n_peers; ++p) {
+        if (!peer_dst_host[p] || !aligned16(peer_dst_host[p])) return GR_ERR_INVALID;
+        a.peer_y[p] = reinterpret_cast<float4 *>(peer_dst_host[p]);
+    }
+    const long long total = n_rows * (d / 4);
+    long long blocks = (total + 255) / 256;
+    const long long cap = (long long)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    peer_scatter_rows_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const float4 *>(src), lds / 4, n_rows, d / 4, a);
+    GR_LAUNCH_CHECK();
+    return GR_OK;
+}
 
 extern "C" int gr_spmm_csr_f32(const int32_t *indptr, const int32_t *indices, const float *vals,
                                const int32_t *row_order, int32_t n_long, const int32_t *long_items,
@@ -594,11 +645,13 @@ extern "C" int gr_spmm_csr_f32(const int32_t *indptr, const int32_t *indices, co
                                const int32_t *group_ptr,
                                int32_t n_groups, int32_t long_threshold, int64_t n_rows, int32_t d, const float *x,
                                int64_t ldx, float *y, int64_t ldy, const float *addend, int64_t lda, float *out,
-                               int64_t ldo, float scale, int32_t scale_mode, void *stream) {
+                               int64_t ldo, float scale, int32_t scale_mode, float *const *peer_y_host,
+                               int32_t n_peers, int64_t peer_row_offset, void *stream) {
     using namespace gr;
     if (n_rows == 0) return GR_OK;
+    if (n_peers < 0 || n_peers > kMaxPeers || (n_peers > 0 && !peer_y_host)) return GR_ERR_INVALID;
     if (!indptr || !indices || !vals || !x || n_rows < 0 || n_long < 0 || n_long > n_rows) return GR_ERR_INVALID;
-    if (!y && !out) return GR_ERR_INVALID;
+    if (!y && !out && n_peers == 0) return GR_ERR_INVALID;
     if (group_ptr && (n_groups < 0 || long_threshold < 1)) return GR_ERR_INVALID;
     if (long_items && (!row_order || n_long_items < n_long || n_split < 0 || (n_split > 0 && (!split_rows || !part_buf))))
         return GR_ERR_INVALID;
@@ -617,7 +670,7 @@ extern "C" int gr_spmm_csr_f32(const int32_t *indptr, const int32_t *indices, co
     a.x = reinterpret_cast<const float4 *>(x);
     a.ldx4 = ldx / 4;
     a.y = reinterpret_cast<float4 *>(y);
-    a.ldy4 = ldy / 4;
+    a.ldy4 = ldy / 4;  // also the leading dimension of the peers' gathered buffers
     a.addend = reinterpret_cast<const float4 *>(addend);
     a.lda4 = lda / 4;
     a.out = reinterpret_cast<float4 *>(out);
@@ -632,6 +685,13 @@ extern "C" int gr_spmm_csr_f32(const int32_t *indptr, const int32_t *indices, co
     a.split_rows = split_rows;
     a.n_split = long_items ? n_split : 0;
     a.part_buf = part_buf;
+    a.n_peers = n_peers;
+    a.peer_row_off = peer_row_offset;
+    for (int p = 0; p < kMaxPeers; ++p) {
+        a.peer_y[p] = p < n_peers ? reinterpret_cast<float4 *>(peer_y_host[p]) : nullptr;
+        if (p < n_peers && (!peer_y_host[p] || !aligned16(peer_y_host[p]))) return GR_ERR_INVALID;
+    }
+    if (n_peers > 0 && ((ldy & 3) || ldy < d)) return GR_ERR_INVALID;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     switch (d) {
         case 32: return launch<32>(a, n_long, n_rows, 0, s);

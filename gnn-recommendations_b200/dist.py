@@ -62,6 +62,78 @@ class RowPartition:
         return x_full[r0:r1]
 
 
+class PeerExchange:
+    """Symmetric (peer-mapped) gathered-layer buffers for the fused SpMM + all-gather.
+
+    Every rank allocates the same two [G*H, d] buffers with torch's symmetric-memory allocator and
+    exchanges their device pointers (plumbing); the SpMM epilogue then stores each finished row
+    straight into all G buffers over NVLink (gr_spmm_csr_f32 `peer_y`), so a layer's exchange is
+    hidden behind its own computation and the only collective left is the barrier between layers."""
+
+    def __init__(self, part: RowPartition, d: int, device, group=None):
+        import ctypes
+
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        self.part, self.d = part, d
+        self.bufs, self.handles, self.ptr_arrays = [], [], []
+        for _ in range(2):
+            t = symm_mem.empty((part.padded_rows, d), dtype=torch.float32, device=device)
+            h = symm_mem.rendezvous(t, self.group)
+            t.zero_()
+            arr = (ctypes.c_void_p * self.world)(*[int(p) for p in h.buffer_ptrs])
+            self.bufs.append(t)
+            self.handles.append(h)
+            self.ptr_arrays.append(arr)
+        self.row_off = self.rank * part.block_rows
+        torch.cuda.synchronize(device)
+        dist.barrier(self.group)
+
+    def peers(self, which: int):
+        return (self.ptr_arrays[which], self.world, self.row_off, self.d)
+
+    def barrier(self, which: int):
+        """All ranks' stores into buffer `which` have landed (stream-ordered, device-side)."""
+        self.handles[which].barrier()
+
+    def scatter(self, which: int, x_local: torch.Tensor):
+        from ._lib import check, lib, ptr, stream_ptr
+
+        with torch.cuda.device(x_local.device):
+            check(lib().gr_peer_scatter_rows(ptr(x_local), x_local.stride(0), x_local.shape[0], self.d,
+                                             self.ptr_arrays[which], self.world, self.d, self.row_off,
+                                             stream_ptr()), "gr_peer_scatter_rows")
+
+
+def lightgcn_propagate_fused(local: NormAdjCSR, ex: PeerExchange, x0_local: torch.Tensor,
+                             n_layers: int) -> torch.Tensor:
+    """Row-partitioned LightGCN propagation with the exchange fused into the SpMM epilogue."""
+    if n_layers == 0:
+        return x0_local.clone()
+    acc = torch.empty_like(x0_local)
+    out = torch.empty_like(x0_local)
+    cur = 0
+    ex.barrier(cur)                       # nobody is still reading buffer `cur` from the previous call
+    ex.scatter(cur, x0_local)             # layer-0 rows -> every rank's buffer
+    ex.barrier(cur)
+    for l in range(n_layers):
+        last = l == n_layers - 1
+        addend = x0_local if l == 0 else acc
+        if last:
+            local.spmm(ex.bufs[cur], addend=addend, out=out, scale=float(n_layers + 1),
+                       scale_mode=_lib.GR_SCALE_DIV, want_y=False)
+        else:
+            nxt = cur ^ 1
+            local.spmm(ex.bufs[cur], addend=addend, out=acc, want_y=False, peers=ex.peers(nxt))
+            ex.barrier(nxt)
+            cur = nxt
+    return out
+
+
 def _all_gather_rows(buf: torch.Tensor, rank: int, block_rows: int, group=None) -> None:
     import torch.distributed as dist
 

@@ -278,8 +278,10 @@ class NormAdjCSR:
     # ---- the kernel -----------------------------------------------------------------------------
     def spmm(self, x: torch.Tensor, y: Optional[torch.Tensor] = None, addend: Optional[torch.Tensor] = None,
              out: Optional[torch.Tensor] = None, scale: float = 1.0, scale_mode: int = _lib.GR_SCALE_NONE,
-             want_y: bool = True) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
-        """t = Â x;  y = t (if want_y);  out = scale_op(addend + t) (if out/addend given)."""
+             want_y: bool = True, peers=None) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
+        """t = Â x;  y = t (if want_y);  out = scale_op(addend + t) (if out/addend given).
+        ``peers`` = (ctypes array of device pointers, n_peers, row offset, leading dim): t is also
+        stored into every peer's gathered buffer (fused all-gather, dist.PeerExchange)."""
         if x.dtype != torch.float32 or x.dim() != 2 or x.stride(1) != 1:
             raise ValueError("x must be a row-major float32 matrix")
         if x.shape[0] != self.n_cols:
@@ -303,10 +305,12 @@ class NormAdjCSR:
                 ptr(self.long_items), self.n_long_items, ptr(self.split_rows), self.n_split, ptr(self._parts(d)),
                 ptr(self.group_ptr), self.n_groups, self.long_threshold, self.n_rows,
                 d, ptr(x), x.stride(0),
-                ptr(y), y.stride(0) if y is not None else 0,
+                ptr(y), y.stride(0) if y is not None else (peers[3] if peers else 0),
                 ptr(addend), addend.stride(0) if addend is not None else 0,
                 ptr(out), out.stride(0) if out is not None else 0,
-                float(scale), int(scale_mode), stream_ptr()), "gr_spmm_csr_f32")
+                float(scale), int(scale_mode),
+                peers[0] if peers else None, peers[1] if peers else 0, peers[2] if peers else 0,
+                stream_ptr()), "gr_spmm_csr_f32")
             if ev is not None:
                 ev[1].record()
                 self.timings.append(ev)

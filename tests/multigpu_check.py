@@ -13,8 +13,8 @@ import torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 import gnn_recommendations_b200 as g  # noqa: E402
-from gnn_recommendations_b200.dist import (RowPartition, full_rank_topk_sharded, gather_rows, item_shard,  # noqa: E402
-                                           lightgcn_propagate_sharded)
+from gnn_recommendations_b200.dist import (PeerExchange, RowPartition, full_rank_topk_sharded, gather_rows,  # noqa: E402
+                                           item_shard, lightgcn_propagate_fused, lightgcn_propagate_sharded)
 from gnn_recommendations_b200.evaluator import ground_truth_dict, seen_csr  # noqa: E402
 from gnn_recommendations_b200.synthetic import SHAPES, synth_split  # noqa: E402
 
@@ -38,6 +38,12 @@ def main():
     mine = lightgcn_propagate_sharded(local_csr, part, rank, x0[r0:r1].contiguous(), L)
     gathered = gather_rows(part, rank, mine)
     ok_prop = bool(torch.equal(gathered, single))
+    # fused SpMM + all-gather over peer memory (NVLink P2P stores from the epilogue)
+    ex = PeerExchange(part, d, dev)
+    ok_fused = True
+    for _ in range(3):                                   # repeated calls reuse the two buffers
+        mine_f = lightgcn_propagate_fused(local_csr, ex, x0[r0:r1].contiguous(), L)
+        ok_fused = ok_fused and bool(torch.equal(mine_f, mine))
 
     gt = ground_truth_dict(sp["test"])
     eu = sorted(gt)
@@ -46,11 +52,12 @@ def main():
     lo, hi = item_shard(ni, world, rank)
     got = full_rank_topk_sharded(gathered[:nu], gathered[nu + lo: nu + hi], lo, hi, eu, ip, it, 20, world, n_splits=2)
     ok_topk = bool(torch.equal(got, want))
-    flags = torch.tensor([int(ok_prop), int(ok_topk)], device=dev)
+    flags = torch.tensor([int(ok_prop), int(ok_topk), int(ok_fused)], device=dev)
     dist.all_reduce(flags, op=dist.ReduceOp.MIN)
     if rank == 0:
         print(f"multigpu_check shape={shape} world={world} rows/rank={[part.rows_of(r) for r in range(world)]} "
-              f"propagation_bit_identical={bool(flags[0])} topk_bit_identical={bool(flags[1])}", flush=True)
+              f"propagation_bit_identical={bool(flags[0])} topk_bit_identical={bool(flags[1])} "
+              f"fused_peer_exchange_bit_identical={bool(flags[2])}", flush=True)
     dist.destroy_process_group()
     sys.exit(0 if bool(flags.min()) else 1)
 
