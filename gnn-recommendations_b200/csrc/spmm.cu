@@ -15,6 +15,7 @@
 // Rows arrive sorted by descending length (gr_row_schedule) so the hardware CTA scheduler
 // performs longest-processing-time-first list scheduling; the hot rows start first on a
 // high-priority side stream and overlap the short-row kernel.
+#include <cstdlib>
 #include <mutex>
 
 #include "gr_common.cuh"
@@ -179,7 +180,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) spmm_warp_rows(const SpmmAr
 // and the addend row are prefetched at the previous boundary.  Rows with >= long_thr entries
 // belong to the long-row kernel: the stream jumps over them.
 // ---------------------------------------------------------------------------------------------
-template <int D>
+template <int D, bool PEERS>
 __global__ void __launch_bounds__(kWarpsPerCta * 32) spmm_stream_rows(const SpmmArgs a) {
     using C = RowCfg<D>;
     constexpr int LPR = C::LPR, VPL = C::VPL, SPW = C::RPW, UNROLL = C::UNROLL;
@@ -208,8 +209,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) spmm_stream_rows(const Spmm
         for (int j = 0; j < VPL; ++j) {
             const int off = gl + j * LPR;
             if (a.y) st_stream_f4(a.y + (long long)row * a.ldy4 + off, acc[j]);
-            for (int p = 0; p < a.n_peers; ++p)
-                a.peer_y[p][(a.peer_row_off + row) * a.ldy4 + off] = acc[j];
+            if constexpr (PEERS) {
+#pragma unroll 1
+                for (int p = 0; p < a.n_peers; ++p) a.peer_y[p][(a.peer_row_off + row) * a.ldy4 + off] = acc[j];
+            }
             if (a.out) {
                 float4 o = acc[j];
                 if (a.addend) o = add4(add_cur[j], o);
@@ -355,7 +358,7 @@ struct LongCfg {
 // (one gr_spmm_csr_f32 in flight per device at a time)
 __device__ unsigned int g_long_ticket = 0;
 
-template <int D>
+template <int D, bool PEERS>
 __global__ void __launch_bounds__(LongCfg<D>::THREADS, 1) spmm_long_rows(const SpmmArgs a) {
     using L = LongCfg<D>;
     constexpr int STAGES = L::STAGES, CH = L::CHUNK, F4 = D / 4, CONS = L::CONS, PROD = L::PROD;
@@ -479,8 +482,11 @@ __global__ void __launch_bounds__(LongCfg<D>::THREADS, 1) spmm_long_rows(const S
     } else if (is_cons) {
         const int f = warp * 32 + lane;
         if (a.y) reinterpret_cast<float *>(a.y + (long long)r * a.ldy4)[f] = acc;
-        for (int p = 0; p < a.n_peers; ++p)
-            reinterpret_cast<float *>(a.peer_y[p] + (a.peer_row_off + r) * a.ldy4)[f] = acc;
+        if constexpr (PEERS) {
+#pragma unroll 1
+            for (int p = 0; p < a.n_peers; ++p)
+                reinterpret_cast<float *>(a.peer_y[p] + (a.peer_row_off + r) * a.ldy4)[f] = acc;
+        }
         if (a.out) {
             float o = acc;
             if (a.addend) o = __fadd_rn(reinterpret_cast<const float *>(a.addend + (long long)r * a.lda4)[f], o);
@@ -550,7 +556,9 @@ static int launch(const SpmmArgs &base, int n_long, long long n_rows, int slot, 
         int rc = get_side(&side);
         if (rc != GR_OK) return rc;
         if (!side->smem_attr_set[slot]) {
-            GR_CUDA_CHECK(cudaFuncSetAttribute(spmm_long_rows<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            GR_CUDA_CHECK(cudaFuncSetAttribute(spmm_long_rows<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (int)L::SMEM + 16));
+            GR_CUDA_CHECK(cudaFuncSetAttribute(spmm_long_rows<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                (int)L::SMEM + 16));
             side->smem_attr_set[slot] = true;
         }
@@ -566,7 +574,8 @@ static int launch(const SpmmArgs &base, int n_long, long long n_rows, int slot, 
         int long_ctas = sm_count();
         if (long_ctas > n_work) long_ctas = n_work;
         if (long_ctas < 1) long_ctas = 1;
-        spmm_long_rows<D><<<long_ctas, L::THREADS, L::SMEM + 16, side->stream>>>(la);
+        if (la.n_peers > 0) spmm_long_rows<D, true><<<long_ctas, L::THREADS, L::SMEM + 16, side->stream>>>(la);
+        else spmm_long_rows<D, false><<<long_ctas, L::THREADS, L::SMEM + 16, side->stream>>>(la);
         GR_LAUNCH_CHECK();
         if (la.items && la.n_split > 0) {
             spmm_combine_parts<<<la.n_split, 128, 0, side->stream>>>(la, D);
@@ -583,7 +592,8 @@ static int launch(const SpmmArgs &base, int n_long, long long n_rows, int slot, 
         const long long per_cta = (long long)kWarpsPerCta * C::RPW;
         const long long ctas = (base.n_groups + per_cta - 1) / per_cta;
         if (ctas > 0) {
-            spmm_stream_rows<D><<<(unsigned)ctas, kWarpsPerCta * 32, 0, stream>>>(wa);
+            if (base.n_peers > 0) spmm_stream_rows<D, true><<<(unsigned)ctas, kWarpsPerCta * 32, 0, stream>>>(wa);
+            else spmm_stream_rows<D, false><<<(unsigned)ctas, kWarpsPerCta * 32, 0, stream>>>(wa);
             GR_LAUNCH_CHECK();
         }
     } else if (rest > 0) {
