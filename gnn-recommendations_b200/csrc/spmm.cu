@@ -277,35 +277,45 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) spmm_stream_rows(const Spmm
                 v_nxt = ld_stream_f32(a.vals + idx, pol_s);
             }
         }
-#pragma unroll
+        // The batch loop is kept rolled and the row-boundary work (flush / next_row) appears once:
+        // fully unrolled, this kernel overflowed the instruction cache (ncu: 2.2 no_instruction
+        // stalls per issue at C4).
+#pragma unroll 1
         for (int kk = 0; kk < LPR; kk += UNROLL) {
             if (!__any_sync(kFull, kc + kk < stream_end)) break;
+            const int e0 = kc + kk;
             float4 xv[UNROLL][VPL];
             float vv[UNROLL];
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {
                 const int cc = __shfl_sync(kFull, c_cur, kk + u, LPR);
                 vv[u] = __shfl_sync(kFull, v_cur, kk + u, LPR);
-                const int e = kc + kk + u;
+                const int e = e0 + u;
                 if (e < stream_end && e >= dead_until) {
                     const float4 *src = a.x + (long long)cc * a.ldx4 + gl;
 #pragma unroll
                     for (int j = 0; j < VPL; ++j) xv[u][j] = ld_gather_f4(src + j * LPR, pol_g);
                 }
             }
+            // consume entries [u0, nvalid) of the batch, one row segment at a time
+            const int nvalid = min(UNROLL, stream_end - e0);
+            int u0 = max(0, dead_until - e0);
+            while (u0 < nvalid) {
+                if (e0 + u0 >= row_stop) {  // row r is complete (or empty): write it, start the next
+                    flush(r);
+                    next_row();
+                    u0 = max(u0, dead_until - e0);  // next_row may have begun a jump over a long row
+                    continue;
+                }
+                const int lim = min(nvalid, row_stop - e0);  // entries [u0, lim) continue row r
 #pragma unroll
-            for (int u = 0; u < UNROLL; ++u) {
-                const int e = kc + kk + u;
-                if (e < stream_end && e >= dead_until) {
-                    while (e >= row_stop) {  // row r is complete (or empty): write it, start the next
-                        flush(r);
-                        next_row();
-                    }
-                    if (e >= dead_until) {
+                for (int u = 0; u < UNROLL; ++u) {
+                    if (u >= u0 && u < lim) {
 #pragma unroll
                         for (int j = 0; j < VPL; ++j) fma4(acc[j], vv[u], xv[u][j]);
                     }
                 }
+                u0 = lim;
             }
         }
         if (dead_until > kc + LPR && kc < stream_end) {  // jump over a long row: reload the chunk registers
