@@ -364,9 +364,9 @@ struct LongCfg {
     static_assert(STAGES - 1 <= IDX_AHEAD && STAGES + IDX_AHEAD + 1 <= IDX_RING, "index ring too small");
 };
 
-// ticket counter of the persistent long-row kernel; zeroed on the side stream before each launch
+// ticket / exit counters of the persistent long-row kernel, re-armed by the last CTA of each launch
 // (one gr_spmm_csr_f32 in flight per device at a time)
-__device__ unsigned int g_long_ticket = 0;
+__device__ unsigned int g_long_ticket = 0, g_long_done = 0;
 
 template <int D, bool PEERS>
 __global__ void __launch_bounds__(LongCfg<D>::THREADS, 1) spmm_long_rows(const SpmmArgs a) {
@@ -505,6 +505,16 @@ __global__ void __launch_bounds__(LongCfg<D>::THREADS, 1) spmm_long_rows(const S
     }
     __syncthreads();  // the rings are reused by the next row
     }  // ticket loop
+    // the last CTA to leave re-arms the counters, so every launch (and every profiler replay)
+    // starts from ticket 0 without host involvement
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&g_long_done, 1u) == gridDim.x - 1) {
+            g_long_ticket = 0;
+            g_long_done = 0;
+            __threadfence();
+        }
+    }
 }
 
 // Split rows: total = ((p0 + p1) + p2) + ... in segment order, then the usual epilogue.
@@ -577,9 +587,6 @@ static int launch(const SpmmArgs &base, int n_long, long long n_rows, int slot, 
         SpmmArgs la = base;
         la.order_begin = 0;
         la.order_end = n_long;
-        void *ticket_addr = nullptr;
-        GR_CUDA_CHECK(cudaGetSymbolAddress(&ticket_addr, g_long_ticket));
-        GR_CUDA_CHECK(cudaMemsetAsync(ticket_addr, 0, sizeof(unsigned int), side->stream));
         const int n_work = la.items ? la.n_items : n_long;
         int long_ctas = sm_count();
         if (long_ctas > n_work) long_ctas = n_work;

@@ -25,9 +25,10 @@ class RowPartition:
         ip = indptr.detach().to("cpu", torch.int64).numpy()
         n = len(ip) - 1
         nnz = int(ip[-1])
-        # cut after the row where the running nnz (+1 per row so empty rows spread too) crosses k/G
-        weight = ip[1:] + np.arange(1, n + 1)
-        total = nnz + n
+        # cut where the running cost crosses k/G; cost = bytes moved: one gathered row per entry, about
+        # three row-sized accesses per output row (y store, running-sum load and store)
+        weight = ip[1:] + 3 * np.arange(1, n + 1)
+        total = nnz + 3 * n
         cuts = [0]
         for k in range(1, world_size):
             cuts.append(int(np.searchsorted(weight, total * k / world_size, side="left")) + 1)
