@@ -166,7 +166,7 @@ def workload_config(name, n_gpus):
     nu, ni, e, d, L = WORKLOADS[name]
     return {"workload": f"{name}: LightGCN {L}-layer d={d} fp32 propagation, synthetic power-law graph "
                         f"{nu} users x {ni} items, {e} edges (nnz(A_hat)={2 * e})",
-            "partition": "single GPU" if n_gpus == 1 else f"rows split in {n_gpus} nnz-balanced blocks; layer rows "
+            "partition": "single GPU" if n_gpus == 1 else f"rows distributed cyclically over {n_gpus} ranks; layer rows "
                                                            "exchanged by P2P stores from the SpMM epilogue (fused "
                                                            "all-gather) or NCCL all-gather (--nccl-allgather)",
             "l2": f"inputs larger than L2 (table {(nu + ni) * d * 4 / 1e9:.2f} GB, CSR {2 * e * 8 / 1e9:.2f} GB)"
@@ -221,10 +221,10 @@ def run_b200(args):
     else:
         part = RowPartition(full.indptr, world)
         csr = part.local_csr(full, rank)
-        r0, r1 = part.rows_of(rank)
+        n_loc = part.n_local(rank)
         del full
         torch.cuda.empty_cache()
-        x0_local = torch.randn(r1 - r0, d, device=dev, generator=gen) * 0.1
+        x0_local = torch.randn(n_loc, d, device=dev, generator=gen) * 0.1
         exchange = None
         if not args.nccl_allgather:
             try:
@@ -244,7 +244,7 @@ def run_b200(args):
             if exchange is not None:
                 return lightgcn_propagate_fused(csr, exchange, x0_local, L)
             return lightgcn_propagate_sharded(csr, part, rank, x0_local, L)
-        n_rows_local = r1 - r0
+        n_rows_local = n_loc
 
     def barrier():
         if world > 1:

@@ -1,11 +1,11 @@
 """Row-partitioned propagation across the GPUs of one box (no reference
 counterpart — the reference is single-process).
 
-Rows of Â are split into G contiguous blocks balanced by nnz.  Rank g owns the embedding rows
-of its block; every layer is one exchange (all-gather of the layer's rows over NVLink) followed
-by a local SpMM on the rank's row block.  Blocks are padded to a common height H so the gathered
-matrix is a dense [G*H, d] buffer and the all-gather is in place with equal chunks; column ids
-are remapped once to that padded numbering.  Per (row, feature) the arithmetic is the same fmaf
+Rows of Â are distributed cyclically over the G ranks (rank g owns rows g, g+G, ...; see
+RowPartition).  Rank g owns the embedding rows of its share; every layer is one exchange of the
+layer's rows (fused into the SpMM epilogue as NVLink P2P stores, or an NCCL all-gather) followed by
+a local SpMM.  Shares are padded to a common height H so the gathered matrix is a dense [G*H, d]
+buffer with equal chunks; column ids are remapped once to that owner-major numbering.  Per (row, feature) the arithmetic is the same fmaf
 chain as on one GPU, so the G-GPU result is bit-identical to the 1-GPU result.
 """
 from __future__ import annotations
@@ -20,47 +20,50 @@ from .graph_builder import NormAdjCSR
 
 
 class RowPartition:
-    def __init__(self, indptr: torch.Tensor, world_size: int):
-        """``indptr``: the full matrix's row pointer (any device)."""
-        ip = indptr.detach().to("cpu", torch.int64).numpy()
-        n = len(ip) - 1
-        nnz = int(ip[-1])
-        # cut where the running cost crosses k/G; cost = bytes moved: one gathered row per entry, about
-        # three row-sized accesses per output row (y store, running-sum load and store)
-        weight = ip[1:] + 3 * np.arange(1, n + 1)
-        total = nnz + 3 * n
-        cuts = [0]
-        for k in range(1, world_size):
-            cuts.append(int(np.searchsorted(weight, total * k / world_size, side="left")) + 1)
-        cuts.append(n)
-        cuts = np.maximum.accumulate(np.minimum(np.asarray(cuts, dtype=np.int64), n))
-        self.bounds = cuts                                   # G+1 row boundaries
-        self.world_size = world_size
-        self.n = n
-        self.block_rows = int(max(1, np.diff(cuts).max()))
-        self.block_rows = (self.block_rows + 3) // 4 * 4
-        self.padded_rows = self.block_rows * world_size
+    """Cyclic row distribution: rank g owns global rows g, g+G, g+2G, ...
 
-    def rows_of(self, rank: int):
-        return int(self.bounds[rank]), int(self.bounds[rank + 1])
+    Both the work (entries) and the exchange volume (rows) of a rank must be 1/G of the total: the
+    all-gather of a layer moves every owned ROW to every peer, the SpMM cost follows the ENTRIES.
+    Node ids of the synthetic / real graphs are popularity-ordered, so contiguous blocks cannot
+    balance both (measured on 4 GPUs: the nnz-balanced block of low-activity users held 58 % of all
+    rows and its NVLink egress set the step time); a cyclic distribution balances rows exactly and
+    entries statistically, and also spreads the hottest item rows over all ranks."""
+
+    def __init__(self, indptr: torch.Tensor, world_size: int):
+        """``indptr``: the full matrix's row pointer (only its length is used)."""
+        self.n = int(indptr.numel()) - 1
+        self.world_size = int(world_size)
+        rows = -(-self.n // self.world_size)
+        self.block_rows = max(4, (rows + 3) // 4 * 4)        # common padded block height H
+        self.padded_rows = self.block_rows * self.world_size
+
+    def n_local(self, rank: int) -> int:
+        return len(range(rank, self.n, self.world_size))
+
+    def local_ids(self, rank: int, device=None) -> torch.Tensor:
+        return torch.arange(rank, self.n, self.world_size, device=device)
+
+    def take_rows(self, x_full: torch.Tensor, rank: int) -> torch.Tensor:
+        return x_full[rank::self.world_size].contiguous()
 
     def to_padded(self, ids: torch.Tensor) -> torch.Tensor:
-        """global node id -> position in the padded [G*H] numbering."""
-        b = torch.as_tensor(self.bounds, device=ids.device)
-        owner = torch.searchsorted(b[1:].contiguous(), ids.long(), right=True)
-        return owner * self.block_rows + (ids.long() - b[owner])
+        """global node id -> position in the padded [G*H] numbering (owner-major)."""
+        ids = ids.long()
+        return (ids % self.world_size) * self.block_rows + ids // self.world_size
 
     def local_csr(self, full: NormAdjCSR, rank: int) -> NormAdjCSR:
-        r0, r1 = self.rows_of(rank)
-        lo, hi = int(full.indptr[r0].item()), int(full.indptr[r1].item())
-        indptr = (full.indptr[r0:r1 + 1] - lo).to(torch.int32).contiguous()
-        indices = self.to_padded(full.indices[lo:hi]).to(torch.int32).contiguous()
-        vals = full.vals[lo:hi].contiguous()
-        return NormAdjCSR(indptr, indices, vals, r1 - r0, self.padded_rows, long_threshold=full.long_threshold)
-
-    def scatter_rows(self, x_full: torch.Tensor, rank: int) -> torch.Tensor:
-        r0, r1 = self.rows_of(rank)
-        return x_full[r0:r1]
+        rows = self.local_ids(rank, full.indptr.device)
+        starts = full.indptr[rows].long()
+        counts = (full.indptr[rows + 1] - full.indptr[rows]).long()
+        indptr = torch.zeros(rows.numel() + 1, dtype=torch.int64, device=rows.device)
+        torch.cumsum(counts, 0, out=indptr[1:])
+        total = int(indptr[-1].item())
+        # entry k of local row j  ->  full entry starts[j] + (k - indptr[j])
+        src = torch.repeat_interleave(starts - indptr[:-1], counts) + torch.arange(total, device=rows.device)
+        indices = self.to_padded(full.indices[src]).to(torch.int32).contiguous()
+        vals = full.vals[src].contiguous()
+        return NormAdjCSR(indptr.to(torch.int32), indices, vals, int(rows.numel()), self.padded_rows,
+                          long_threshold=full.long_threshold)
 
 
 class PeerExchange:
@@ -146,7 +149,7 @@ def _all_gather_rows(buf: torch.Tensor, rank: int, block_rows: int, group=None) 
 def lightgcn_propagate_sharded(local: NormAdjCSR, part: RowPartition, rank: int, x0_local: torch.Tensor,
                                n_layers: int, group=None,
                                spmm: Optional[Callable] = None) -> torch.Tensor:
-    """mean_{l<=L} Â^l x0 for this rank's rows.  ``x0_local``: [rows_of(rank), d].  ``spmm`` is
+    """mean_{l<=L} Â^l x0 for this rank's rows.  ``x0_local``: [n_local(rank), d].  ``spmm`` is
     injectable for the CPU (gloo) tests of the partition / exchange logic; the product path is
     the CUDA kernel."""
     n_local, d = x0_local.shape
@@ -188,19 +191,15 @@ def item_shard(n_items: int, world_size: int, rank: int):
 
 
 def gather_rows(part: RowPartition, rank: int, x_local: torch.Tensor, group=None) -> torch.Tensor:
-    """All ranks' row blocks -> the full [N, d] matrix in natural row order (replicated)."""
-    import torch.distributed as dist
-
+    """All ranks' rows -> the full [N, d] matrix in natural row order (replicated)."""
     d = x_local.shape[1]
     buf = torch.zeros((part.padded_rows, d), dtype=x_local.dtype, device=x_local.device)
-    r0, r1 = part.rows_of(rank)
-    buf[rank * part.block_rows: rank * part.block_rows + (r1 - r0)].copy_(x_local)
+    buf[rank * part.block_rows: rank * part.block_rows + x_local.shape[0]].copy_(x_local)
     _all_gather_rows(buf, rank, part.block_rows, group)
-    pieces = []
+    out = torch.empty((part.n, d), dtype=x_local.dtype, device=x_local.device)
     for g in range(part.world_size):
-        a, b = part.rows_of(g)
-        pieces.append(buf[g * part.block_rows: g * part.block_rows + (b - a)])
-    return torch.cat(pieces, dim=0)
+        out[g::part.world_size] = buf[g * part.block_rows: g * part.block_rows + part.n_local(g)]
+    return out
 
 
 def full_rank_topk_sharded(user_emb: torch.Tensor, item_emb_local: torch.Tensor, item_lo: int, item_hi: int,

@@ -34,15 +34,15 @@ def main():
 
     part = RowPartition(full.indptr, world)
     local_csr = part.local_csr(full, rank)
-    r0, r1 = part.rows_of(rank)
-    mine = lightgcn_propagate_sharded(local_csr, part, rank, x0[r0:r1].contiguous(), L)
+    x0_mine = part.take_rows(x0, rank)
+    mine = lightgcn_propagate_sharded(local_csr, part, rank, x0_mine, L)
     gathered = gather_rows(part, rank, mine)
     ok_prop = bool(torch.equal(gathered, single))
     # fused SpMM + all-gather over peer memory (NVLink P2P stores from the epilogue)
     ex = PeerExchange(part, d, dev)
     ok_fused = True
     for _ in range(3):                                   # repeated calls reuse the two buffers
-        mine_f = lightgcn_propagate_fused(local_csr, ex, x0[r0:r1].contiguous(), L)
+        mine_f = lightgcn_propagate_fused(local_csr, ex, x0_mine, L)
         ok_fused = ok_fused and bool(torch.equal(mine_f, mine))
 
     gt = ground_truth_dict(sp["test"])
@@ -55,7 +55,7 @@ def main():
     flags = torch.tensor([int(ok_prop), int(ok_topk), int(ok_fused)], device=dev)
     dist.all_reduce(flags, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print(f"multigpu_check shape={shape} world={world} rows/rank={[part.rows_of(r) for r in range(world)]} "
+        print(f"multigpu_check shape={shape} world={world} rows/rank={[part.n_local(r) for r in range(world)]} "
               f"propagation_bit_identical={bool(flags[0])} topk_bit_identical={bool(flags[1])} "
               f"fused_peer_exchange_bit_identical={bool(flags[2])}", flush=True)
     dist.destroy_process_group()

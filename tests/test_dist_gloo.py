@@ -35,11 +35,13 @@ class CpuCsr:
 
 
 def _cpu_local_csr(part, adj, rank):
-    r0, r1 = part.rows_of(rank)
-    ip = torch.from_numpy(adj["indptr"])
-    lo, hi = int(ip[r0]), int(ip[r1])
-    indices = part.to_padded(torch.from_numpy(adj["indices"][lo:hi].astype(np.int64)))
-    return CpuCsr((ip[r0:r1 + 1] - lo), indices, torch.from_numpy(adj["vals"][lo:hi]), r1 - r0, part.padded_rows)
+    ip = adj["indptr"]
+    rows = np.arange(rank, part.n, part.world_size)
+    counts = ip[rows + 1] - ip[rows]
+    src = np.concatenate([np.arange(ip[r], ip[r + 1]) for r in rows]) if len(rows) else np.zeros(0, np.int64)
+    indptr = torch.from_numpy(np.concatenate([[0], np.cumsum(counts)]).astype(np.int64))
+    indices = part.to_padded(torch.from_numpy(adj["indices"][src].astype(np.int64)))
+    return CpuCsr(indptr, indices, torch.from_numpy(adj["vals"][src]), len(rows), part.padded_rows)
 
 
 def _worker(rank, world, port, out):
@@ -62,8 +64,7 @@ def _worker(rank, world, port, out):
                 r = t if addend is None else addend + t
                 o.copy_(r / scale if mode == _lib.GR_SCALE_DIV else r)
 
-        r0, r1 = part.rows_of(rank)
-        mine = lightgcn_propagate_sharded(local, part, rank, x0[r0:r1].clone(), 3, spmm=spmm)
+        mine = lightgcn_propagate_sharded(local, part, rank, part.take_rows(x0, rank), 3, spmm=spmm)
         full = gather_rows(part, rank, mine)
         ue, ie = po.lightgcn_forward(po.to_torch_coo(adj), x0[:nu], x0[nu:], 3)
         ok_prop = torch.equal(full, torch.cat([ue, ie]))          # bit-identical to the single-process result

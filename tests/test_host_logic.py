@@ -97,17 +97,21 @@ def test_seen_csr_union_sorted_unique():
 
 def test_row_partition_covers_and_balances():
     rng = np.random.default_rng(0)
-    lens = np.concatenate([rng.integers(0, 5, 1000), [5000], rng.integers(0, 50, 500)])
+    lens = np.concatenate([[5000], rng.integers(0, 50, 500), rng.integers(0, 5, 1003)])   # popularity-ordered
     indptr = torch.from_numpy(np.concatenate([[0], np.cumsum(lens)]).astype(np.int32))
+    n = len(lens)
     for g_ in (1, 2, 3, 8):
         part = RowPartition(indptr, g_)
-        assert part.bounds[0] == 0 and part.bounds[-1] == len(lens) and (np.diff(part.bounds) >= 0).all()
-        ids = torch.arange(len(lens))
+        ids = torch.arange(n)
         padded = part.to_padded(ids)
-        assert padded.unique().numel() == len(lens) and int(padded.max()) < part.padded_rows
+        assert padded.unique().numel() == n and int(padded.max()) < part.padded_rows
+        owned = [part.local_ids(r) for r in range(g_)]
+        assert torch.equal(torch.sort(torch.cat(owned)).values, ids)                # a partition of the rows
         for r in range(g_):
-            r0, r1 = part.rows_of(r)
-            assert torch.equal(padded[r0:r1], torch.arange(r1 - r0) + r * part.block_rows)
+            assert part.n_local(r) == owned[r].numel() and abs(part.n_local(r) - n / g_) < 1   # rows balanced
+            assert torch.equal(padded[owned[r]], torch.arange(part.n_local(r)) + r * part.block_rows)
+            x = torch.arange(n * 2, dtype=torch.float32).view(n, 2)
+            assert torch.equal(part.take_rows(x, r), x[owned[r]])
 
 
 def test_dataset_boundary_attributes(tiny):
