@@ -386,7 +386,8 @@ def run_b200(args):
             "clocks": sampler.summary() if sampler else None,
             "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
             "setup_s": t_setup, "nnz": nnz, "long_rows": n_long, "extras": extras,
-            "exchange": None if world == 1 else ("fused_peer_stores" if exchange is not None else "nccl_all_gather"),
+            "exchange": None if world == 1 else (("fused_multicast_stores" if exchange.multicast else "fused_peer_stores")
+                                                  if exchange is not None else "nccl_all_gather"),
         }
         print(json.dumps(line), flush=True)
     if world > 1:

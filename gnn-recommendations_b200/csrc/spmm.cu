@@ -56,8 +56,24 @@ struct SpmmArgs {
     // buffer (NVLink P2P stores from the epilogue; ld = ldy4).  n_peers = 0 disables it.
     float4 *peer_y[kMaxPeers];
     int n_peers;
+    int peer_multicast;     // peer_y[0] is a multicast address
     long long peer_row_off;
 };
+
+// kernel template parameter PEERS: how the finished row also leaves the GPU
+constexpr int kPeersNone = 0;       // not at all
+constexpr int kPeersP2P = 1;        // one store per rank to its mapped buffer
+constexpr int kPeersMulticast = 2;  // one multimem.st to an NVSwitch multicast address (peer_y[0]): the switch
+                                    // replicates it to every rank, NVLink egress is 1x instead of (G-1)x
+
+__device__ __forceinline__ void st_multimem_f4(float4 *p, const float4 &v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y),
+                 "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ void st_multimem_f1(float *p, float v) {
+    asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
 
 template <int D>
 struct RowCfg {
@@ -180,7 +196,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) spmm_warp_rows(const SpmmAr
 // and the addend row are prefetched at the previous boundary.  Rows with >= long_thr entries
 // belong to the long-row kernel: the stream jumps over them.
 // ---------------------------------------------------------------------------------------------
-template <int D, bool PEERS>
+template <int D, int PEERS>
 __global__ void __launch_bounds__(kWarpsPerCta * 32) spmm_stream_rows(const SpmmArgs a) {
     using C = RowCfg<D>;
     constexpr int LPR = C::LPR, VPL = C::VPL, SPW = C::RPW, UNROLL = C::UNROLL;
@@ -209,9 +225,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) spmm_stream_rows(const Spmm
         for (int j = 0; j < VPL; ++j) {
             const int off = gl + j * LPR;
             if (a.y) st_stream_f4(a.y + (long long)row * a.ldy4 + off, acc[j]);
-            if constexpr (PEERS) {
+            if constexpr (PEERS == kPeersP2P) {
 #pragma unroll 1
                 for (int p = 0; p < a.n_peers; ++p) a.peer_y[p][(a.peer_row_off + row) * a.ldy4 + off] = acc[j];
+            } else if constexpr (PEERS == kPeersMulticast) {
+                st_multimem_f4(a.peer_y[0] + (a.peer_row_off + row) * a.ldy4 + off, acc[j]);
             }
             if (a.out) {
                 float4 o = acc[j];
@@ -368,7 +386,7 @@ struct LongCfg {
 // (one gr_spmm_csr_f32 in flight per device at a time)
 __device__ unsigned int g_long_ticket = 0, g_long_done = 0;
 
-template <int D, bool PEERS>
+template <int D, int PEERS>
 __global__ void __launch_bounds__(LongCfg<D>::THREADS, 1) spmm_long_rows(const SpmmArgs a) {
     using L = LongCfg<D>;
     constexpr int STAGES = L::STAGES, CH = L::CHUNK, F4 = D / 4, CONS = L::CONS, PROD = L::PROD;
@@ -492,10 +510,12 @@ __global__ void __launch_bounds__(LongCfg<D>::THREADS, 1) spmm_long_rows(const S
     } else if (is_cons) {
         const int f = warp * 32 + lane;
         if (a.y) reinterpret_cast<float *>(a.y + (long long)r * a.ldy4)[f] = acc;
-        if constexpr (PEERS) {
+        if constexpr (PEERS == kPeersP2P) {
 #pragma unroll 1
             for (int p = 0; p < a.n_peers; ++p)
                 reinterpret_cast<float *>(a.peer_y[p] + (a.peer_row_off + r) * a.ldy4)[f] = acc;
+        } else if constexpr (PEERS == kPeersMulticast) {
+            st_multimem_f1(reinterpret_cast<float *>(a.peer_y[0] + (a.peer_row_off + r) * a.ldy4) + f, acc);
         }
         if (a.out) {
             float o = acc;
@@ -527,8 +547,12 @@ __global__ void spmm_combine_parts(const SpmmArgs a, int d) {
         float t = a.part_buf[(long long)first * d + f];
         for (int k = 1; k < n; ++k) t = __fadd_rn(t, a.part_buf[(long long)(first + k) * d + f]);
         if (a.y) reinterpret_cast<float *>(a.y + (long long)r * a.ldy4)[f] = t;
-        for (int p = 0; p < a.n_peers; ++p)
-            reinterpret_cast<float *>(a.peer_y[p] + (a.peer_row_off + r) * a.ldy4)[f] = t;
+        if (a.peer_multicast) {
+            st_multimem_f1(reinterpret_cast<float *>(a.peer_y[0] + (a.peer_row_off + r) * a.ldy4) + f, t);
+        } else {
+            for (int p = 0; p < a.n_peers; ++p)
+                reinterpret_cast<float *>(a.peer_y[p] + (a.peer_row_off + r) * a.ldy4)[f] = t;
+        }
         if (a.out) {
             float o = t;
             if (a.addend) o = __fadd_rn(reinterpret_cast<const float *>(a.addend + (long long)r * a.lda4)[f], o);
@@ -576,10 +600,12 @@ static int launch(const SpmmArgs &base, int n_long, long long n_rows, int slot, 
         int rc = get_side(&side);
         if (rc != GR_OK) return rc;
         if (!side->smem_attr_set[slot]) {
-            GR_CUDA_CHECK(cudaFuncSetAttribute(spmm_long_rows<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               (int)L::SMEM + 16));
-            GR_CUDA_CHECK(cudaFuncSetAttribute(spmm_long_rows<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               (int)L::SMEM + 16));
+            GR_CUDA_CHECK(cudaFuncSetAttribute(spmm_long_rows<D, kPeersNone>,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::SMEM + 16));
+            GR_CUDA_CHECK(cudaFuncSetAttribute(spmm_long_rows<D, kPeersP2P>,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::SMEM + 16));
+            GR_CUDA_CHECK(cudaFuncSetAttribute(spmm_long_rows<D, kPeersMulticast>,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::SMEM + 16));
             side->smem_attr_set[slot] = true;
         }
         GR_CUDA_CHECK(cudaEventRecord(side->fork, stream));
@@ -591,8 +617,12 @@ static int launch(const SpmmArgs &base, int n_long, long long n_rows, int slot, 
         int long_ctas = sm_count();
         if (long_ctas > n_work) long_ctas = n_work;
         if (long_ctas < 1) long_ctas = 1;
-        if (la.n_peers > 0) spmm_long_rows<D, true><<<long_ctas, L::THREADS, L::SMEM + 16, side->stream>>>(la);
-        else spmm_long_rows<D, false><<<long_ctas, L::THREADS, L::SMEM + 16, side->stream>>>(la);
+        if (la.n_peers > 0 && la.peer_multicast)
+            spmm_long_rows<D, kPeersMulticast><<<long_ctas, L::THREADS, L::SMEM + 16, side->stream>>>(la);
+        else if (la.n_peers > 0)
+            spmm_long_rows<D, kPeersP2P><<<long_ctas, L::THREADS, L::SMEM + 16, side->stream>>>(la);
+        else
+            spmm_long_rows<D, kPeersNone><<<long_ctas, L::THREADS, L::SMEM + 16, side->stream>>>(la);
         GR_LAUNCH_CHECK();
         if (la.items && la.n_split > 0) {
             spmm_combine_parts<<<la.n_split, 128, 0, side->stream>>>(la, D);
@@ -609,8 +639,12 @@ static int launch(const SpmmArgs &base, int n_long, long long n_rows, int slot, 
         const long long per_cta = (long long)kWarpsPerCta * C::RPW;
         const long long ctas = (base.n_groups + per_cta - 1) / per_cta;
         if (ctas > 0) {
-            if (base.n_peers > 0) spmm_stream_rows<D, true><<<(unsigned)ctas, kWarpsPerCta * 32, 0, stream>>>(wa);
-            else spmm_stream_rows<D, false><<<(unsigned)ctas, kWarpsPerCta * 32, 0, stream>>>(wa);
+            if (base.n_peers > 0 && base.peer_multicast)
+                spmm_stream_rows<D, kPeersMulticast><<<(unsigned)ctas, kWarpsPerCta * 32, 0, stream>>>(wa);
+            else if (base.n_peers > 0)
+                spmm_stream_rows<D, kPeersP2P><<<(unsigned)ctas, kWarpsPerCta * 32, 0, stream>>>(wa);
+            else
+                spmm_stream_rows<D, kPeersNone><<<(unsigned)ctas, kWarpsPerCta * 32, 0, stream>>>(wa);
             GR_LAUNCH_CHECK();
         }
     } else if (rest > 0) {
@@ -635,21 +669,27 @@ __global__ void peer_scatter_rows_kernel(const float4 *src, long long lds4, long
         const long long r = i / f4;
         const int f = (int)(i % f4);
         const float4 v = __ldg(src + r * lds4 + f);
-        for (int p = 0; p < a.n_peers; ++p) a.peer_y[p][(a.peer_row_off + r) * a.ldy4 + f] = v;
+        if (a.peer_multicast) {
+            st_multimem_f4(a.peer_y[0] + (a.peer_row_off + r) * a.ldy4 + f, v);
+        } else {
+            for (int p = 0; p < a.n_peers; ++p) a.peer_y[p][(a.peer_row_off + r) * a.ldy4 + f] = v;
+        }
     }
 }
 
 }  // namespace gr
 
 extern "C" int gr_peer_scatter_rows(const float *src, int64_t lds, int64_t n_rows, int32_t d,
-                                    float *const *peer_dst_host, int32_t n_peers, int64_t ldd,
-                                    int64_t peer_row_offset, void *stream) {
+                                    float *const *peer_dst_host, int32_t n_peers, int32_t peer_multicast,
+                                    int64_t ldd, int64_t peer_row_offset, void *stream) {
     using namespace gr;
     if (!src || !peer_dst_host || n_rows < 0 || n_peers < 1 || n_peers > kMaxPeers) return GR_ERR_INVALID;
     if ((d & 3) || (lds & 3) || (ldd & 3) || lds < d || ldd < d || !aligned16(src)) return GR_ERR_INVALID;
     if (n_rows == 0) return GR_OK;
     SpmmArgs a = {};
     a.n_peers = n_peers;
+    a.peer_multicast = peer_multicast ? 1 : 0;
+    if (a.peer_multicast && n_peers != 1) return GR_ERR_INVALID;
     a.peer_row_off = peer_row_offset;
     a.ldy4 = ldd / 4;
     for (int p = 0; p < n_peers; ++p) {
@@ -673,7 +713,7 @@ extern "C" int gr_spmm_csr_f32(const int32_t *indptr, const int32_t *indices, co
                                int32_t n_groups, int32_t long_threshold, int64_t n_rows, int32_t d, const float *x,
                                int64_t ldx, float *y, int64_t ldy, const float *addend, int64_t lda, float *out,
                                int64_t ldo, float scale, int32_t scale_mode, float *const *peer_y_host,
-                               int32_t n_peers, int64_t peer_row_offset, void *stream) {
+                               int32_t n_peers, int32_t peer_multicast, int64_t peer_row_offset, void *stream) {
     using namespace gr;
     if (n_rows == 0) return GR_OK;
     if (n_peers < 0 || n_peers > kMaxPeers || (n_peers > 0 && !peer_y_host)) return GR_ERR_INVALID;
@@ -713,6 +753,8 @@ extern "C" int gr_spmm_csr_f32(const int32_t *indptr, const int32_t *indices, co
     a.n_split = long_items ? n_split : 0;
     a.part_buf = part_buf;
     a.n_peers = n_peers;
+    a.peer_multicast = (n_peers > 0 && peer_multicast) ? 1 : 0;
+    if (a.peer_multicast && n_peers != 1) return GR_ERR_INVALID;
     a.peer_row_off = peer_row_offset;
     for (int p = 0; p < kMaxPeers; ++p) {
         a.peer_y[p] = p < n_peers ? reinterpret_cast<float4 *>(peer_y_host[p]) : nullptr;

@@ -10,6 +10,7 @@ chain as on one GPU, so the G-GPU result is bit-identical to the 1-GPU result.
 """
 from __future__ import annotations
 
+import os
 from typing import Callable, List, Optional
 
 import numpy as np
@@ -85,20 +86,32 @@ class PeerExchange:
         self.rank = dist.get_rank(self.group)
         self.part, self.d = part, d
         self.bufs, self.handles, self.ptr_arrays = [], [], []
+        want_mc = os.environ.get("GR_MULTICAST", "0") == "1" and self.world > 1
+        self.multicast = want_mc
         for _ in range(2):
             t = symm_mem.empty((part.padded_rows, d), dtype=torch.float32, device=device)
             h = symm_mem.rendezvous(t, self.group)
             t.zero_()
-            arr = (ctypes.c_void_p * self.world)(*[int(p) for p in h.buffer_ptrs])
             self.bufs.append(t)
             self.handles.append(h)
+            if not int(getattr(h, "multicast_ptr", 0) or 0):
+                self.multicast = False
+        flag = torch.tensor([1 if self.multicast else 0], device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)       # all ranks must agree
+        self.multicast = bool(flag.item())
+        for h in self.handles:
+            if self.multicast:      # NVSwitch multicast (NVLS): one store reaches every rank
+                arr = (ctypes.c_void_p * 1)(int(h.multicast_ptr))
+            else:                   # one mapped pointer per rank
+                arr = (ctypes.c_void_p * self.world)(*[int(p) for p in h.buffer_ptrs])
             self.ptr_arrays.append(arr)
+        self.n_targets = 1 if self.multicast else self.world
         self.row_off = self.rank * part.block_rows
         torch.cuda.synchronize(device)
         dist.barrier(self.group)
 
     def peers(self, which: int):
-        return (self.ptr_arrays[which], self.world, self.row_off, self.d)
+        return (self.ptr_arrays[which], self.n_targets, self.row_off, self.d, 1 if self.multicast else 0)
 
     def barrier(self, which: int):
         """All ranks' stores into buffer `which` have landed (stream-ordered, device-side)."""
@@ -109,8 +122,8 @@ class PeerExchange:
 
         with torch.cuda.device(x_local.device):
             check(lib().gr_peer_scatter_rows(ptr(x_local), x_local.stride(0), x_local.shape[0], self.d,
-                                             self.ptr_arrays[which], self.world, self.d, self.row_off,
-                                             stream_ptr()), "gr_peer_scatter_rows")
+                                             self.ptr_arrays[which], self.n_targets, 1 if self.multicast else 0,
+                                             self.d, self.row_off, stream_ptr()), "gr_peer_scatter_rows")
 
 
 def lightgcn_propagate_fused(local: NormAdjCSR, ex: PeerExchange, x0_local: torch.Tensor,

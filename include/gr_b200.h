@@ -133,7 +133,7 @@ int gr_spmm_csr_f32(const int32_t *indptr, const int32_t *indices, const float *
                     int32_t long_threshold, int64_t n_rows, int32_t d, const float *x,
                     int64_t ldx, float *y, int64_t ldy, const float *addend, int64_t lda, float *out,
                     int64_t ldo, float scale, int32_t scale_mode, float *const *peer_y_host, int32_t n_peers,
-                    int64_t peer_row_offset, void *stream);
+                    int32_t peer_multicast, int64_t peer_row_offset, void *stream);
 
 /* Fused compute + all-gather for the row-partitioned multi-GPU propagation (no reference
  * counterpart).  `peer_y_host` (HOST array of n_peers <= 8 DEVICE pointers, one per rank of the
@@ -141,9 +141,13 @@ int gr_spmm_csr_f32(const int32_t *indptr, const int32_t *indices, const float *
  * [G*H, ldy] layer buffer: the SpMM epilogue stores t[r,:] to row (peer_row_offset + r) of each of
  * them with plain P2P stores over NVLink, so the exchange of a layer overlaps its computation row
  * by row and no separate all-gather runs.  The caller orders layers with a cross-rank barrier.
+ * With peer_multicast = 1, peer_y_host[0] (n_peers = 1) is an NVSwitch MULTICAST address of the
+ * buffer (symmetric memory multicast_ptr): each row is written once with multimem.st and replicated
+ * to every rank inside the switch (NVLS), so a rank's NVLink egress is 1x the layer instead of (G-1)x.
  * gr_peer_scatter_rows does the same store fan-out for an existing matrix (the layer-0 exchange). */
 int gr_peer_scatter_rows(const float *src, int64_t lds, int64_t n_rows, int32_t d, float *const *peer_dst_host,
-                         int32_t n_peers, int64_t ldd, int64_t peer_row_offset, void *stream);
+                         int32_t n_peers, int32_t peer_multicast, int64_t ldd, int64_t peer_row_offset,
+                         void *stream);
 
 /* Per-row dense epilogue shared by the NGCF, Group-and-Shuffle and GAT layers:
  *     out = alpha * act( X1 Wa + bias_a  +  (X2 * X3) Wb + bias_b ) + beta * R
