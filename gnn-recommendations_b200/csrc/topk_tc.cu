@@ -1,0 +1,533 @@
+// Tensor-core candidate pass for the full-ranking evaluation (tcgen05 / TMEM, sm_100a).
+//
+// The exact ranking (topk.cu) evaluates every user x item score as a k-sequential fp32 fmaf chain on
+// the FFMA pipe: 2*U*I*d flops, ~21 TFLOP/s.  fp32 has no tensor-core MMA; TF32 (10 mantissa bits)
+// changes ~11 % of the top-20 lists when used directly.  This pass therefore only NOMINATES: it
+// computes all scores with tcgen05.mma.kind::tf32 (fp32 accumulators in TMEM), masks the seen
+// items, and keeps the K' > K best approximate scores per user.  gr_topk_rescore then re-scores
+// those K' candidates with the exact chain, ranks them canonically and PROVES the result: every
+// item outside the candidate list has approximate score <= a_min (the K'-th kept), and
+// |s_tf32 - s_exact| <= eps * |u| * max|i|, so if a_min + bound < (K-th exact score) no outside item
+// can enter or tie into the top-K.  Users for which the proof fails are flagged and re-ranked by the
+// exact kernel; results are therefore always bit-identical to the exact path.
+//
+// One CTA = 128 eval users (UMMA M = 128) against all items in tiles of 128 (UMMA N = 128):
+//   warps 0-3  producers : item tile fp32 rows -> shared memory in the K-major SWIZZLE_128B
+//                          canonical layout (32 tf32 per 128-byte row, 8-row atoms, 16-byte chunks
+//                          XOR-swizzled), fence.proxy.async, mbarrier arrive; 2-stage ring
+//   warp  8    MMA       : one elected lane issues d/8 tcgen05.mma (K = 8 per instruction) per tile
+//                          into one of two 128-column TMEM accumulators, tcgen05.commit to mbarriers
+//   warps 4-7  epilogue  : tcgen05.ld 32 columns at a time; thread = TMEM lane = one user: seen-item
+//                          cursor, threshold filter, insertion into its own sorted K' list (shared)
+#include <math_constants.h>
+
+#include <cstdlib>
+
+#include "gr_common.cuh"
+
+namespace gr {
+
+constexpr int TC_M = 128;       // users per CTA
+constexpr int TC_N = 128;       // items per tile
+constexpr int TC_KB = 32;       // tf32 elements per 128-byte swizzle row
+constexpr int TC_STAGES = 1;     // one item-tile stage: two CTAs fit per SM and cover each other's bubbles
+constexpr int TC_THREADS = 288; // 4 producer + 4 epilogue + 1 MMA warps
+constexpr int TC_KPRIME_MAX = 64;
+
+struct TcArgs {
+    const float *user_emb;
+    long long ldu;
+    const float *item_emb;  // row 0 = item id item_lo
+    long long ldi;
+    int d;
+    const int64_t *eval_users;
+    int n_eval;
+    long long item_lo, item_hi;
+    const int64_t *seen_indptr;
+    const int32_t *seen_items;
+    int kprime;
+    float *cand_scores;  // [n_eval][kprime] approximate scores (heap order, unsorted)
+    int *cand_ids;       // [n_eval][kprime]
+    int *cand_cnt;       // [n_eval]
+    int debug;           // GR_TC_DEBUG bits (timing experiments): 1 = epilogue skips selection, 2 = producers skip loads
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// waiting role that is NOT on the critical path (producers, MMA issuer): back off between polls so the
+// spin does not take issue slots from the epilogue warp sharing the scheduler
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(2000u)
+            : "memory");
+        if (done) break;
+        __nanosleep(200);
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address
+// and offsets in 16-byte units, stride between 8-row atoms = 1024 B, version 1, layout type 2.
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+    uint64_t desc = 0;
+    desc |= (uint64_t)((smem_addr & 0x3ffff) >> 4);  // start address, bits [0,14)
+    desc |= (uint64_t)0 << 16;                       // leading byte offset (unused for swizzled K-major)
+    desc |= (uint64_t)(1024 >> 4) << 32;             // stride byte offset, bits [32,46)
+    desc |= (uint64_t)1 << 46;                       // version
+    desc |= (uint64_t)2 << 61;                       // SWIZZLE_128B
+    return desc;
+}
+// byte offset of 16-byte chunk `c16` (0..7) of row `row` inside a [rows][128 B] SWIZZLE_128B tile
+__device__ __forceinline__ uint32_t sw128_offset(int row, int c16) {
+    return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((c16 ^ (row & 7)) << 4));
+}
+
+// instruction descriptor: D = F32, A = B = TF32, both K-major, N at bits [17,23) (N>>3), M at [24,29) (M>>4)
+constexpr uint32_t kIdescTf32 = (1u << 4) | (2u << 7) | (2u << 10) | ((TC_N >> 3) << 17) | ((TC_M >> 4) << 24);
+
+// Per-user candidate set = binary MIN-heap of the K' best (approximate score, id) pairs seen so far,
+// position-major in shared memory (entry p of user m at [p * 128 + m]).  "a worse than b" =
+// a.score < b.score, or equal scores and a.id > b.id (the canonical order prefers small ids).  The
+// root is the worst kept candidate, so the admission threshold is its score and a push is O(log K')
+// (a sorted list cost ~K'/2 shifts per push and, with warp divergence, dominated the kernel).
+struct HeapState {
+    int cnt;
+    float thr;
+};
+__device__ __forceinline__ bool tc_worse(float sa, int ia, float sb, int ib) { return sa < sb || (sa == sb && ia > ib); }
+
+__device__ __noinline__ HeapState tc_heap_push(float *hs, int *hi, int m, int K, int cnt, float thr, float s, int id) {
+    if (cnt < K) {                       // filling: append and sift up
+        int i = cnt++;
+        while (i > 0) {
+            const int par = (i - 1) >> 1;
+            const float ps = hs[par * TC_M + m];
+            const int pi = hi[par * TC_M + m];
+            if (!tc_worse(s, id, ps, pi)) break;     // parent must be the worse one
+            hs[i * TC_M + m] = ps;
+            hi[i * TC_M + m] = pi;
+            i = par;
+        }
+        hs[i * TC_M + m] = s;
+        hi[i * TC_M + m] = id;
+    } else {                             // full: the new entry replaces the root, sift down
+        int i = 0;
+        while (true) {
+            int c = 2 * i + 1;
+            if (c >= K) break;
+            float cs = hs[c * TC_M + m];
+            if (c + 1 < K) {
+                const float rs = hs[(c + 1) * TC_M + m];
+                // ids are only read on exact score ties
+                if (rs < cs || (rs == cs && hi[(c + 1) * TC_M + m] > hi[c * TC_M + m])) { ++c; cs = rs; }
+            }
+            // the new entry has the largest id so far: on a score tie it is the worse one and stays above
+            if (!(cs < s)) break;                    // both children are better than (or tie with) the new entry
+            hs[i * TC_M + m] = cs;
+            hi[i * TC_M + m] = hi[c * TC_M + m];
+            i = c;
+        }
+        hs[i * TC_M + m] = s;
+        hi[i * TC_M + m] = id;
+    }
+    HeapState st;
+    st.cnt = cnt;
+    st.thr = (cnt == K) ? hs[m] : -CUDART_INF_F;     // root score once the heap is full
+    return st;
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 2) topk_tc_candidates_kernel(const TcArgs a) {
+    extern __shared__ unsigned char smem_dyn[];
+    // SWIZZLE_128B operand tiles need 1024-byte alignment (the launch adds 1 KB of slack)
+    unsigned char *smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+    const int d = a.d;
+    const int nkb = d / TC_KB;                       // k-blocks of 32 tf32
+    const uint32_t tile_bytes = TC_M * 128;          // one k-block of a 128-row operand: 16 KB
+    unsigned char *sA = smem_raw;                    // [nkb][128 rows][128 B]
+    unsigned char *sB = sA + (size_t)nkb * tile_bytes;            // [stages][nkb][128 rows][128 B]
+    float *ls = reinterpret_cast<float *>(sB + (size_t)TC_STAGES * nkb * tile_bytes);   // [kprime][128]
+    int *li = reinterpret_cast<int *>(ls + (size_t)a.kprime * TC_M);                      // [kprime][128]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(li + (size_t)a.kprime * TC_M);
+    uint64_t *b_full = bars, *b_empty = bars + 2, *t_full = bars + 4, *t_empty = bars + 6, *a_full = bars + 8;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 9);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int row0 = blockIdx.x * TC_M;
+    const long long n_it = a.item_hi - a.item_lo;
+    const int n_tiles = (int)((n_it + TC_N - 1) / TC_N);
+
+    if (tid == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) {
+            mbar_init(&b_full[s], 128);   // 128 producer threads
+            mbar_init(&b_empty[s], 1);    // tcgen05.commit
+        }
+        for (int s = 0; s < 2; ++s) {     // the TMEM accumulator is always double-buffered
+            mbar_init(&t_full[s], 1);     // tcgen05.commit
+            mbar_init(&t_empty[s], 128);  // 128 epilogue threads
+        }
+        mbar_init(a_full, 128);
+        fence_barrier_init();
+    }
+    if (warp == 8) tmem_alloc(tmem_slot, 2 * TC_N);  // two 128-column fp32 accumulators
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 4) {
+        // ===== producers =====
+        const int f4_per_row = d / 4;
+        for (int idx = tid; idx < TC_M * f4_per_row; idx += 128) {   // user tile, once
+            const int r = idx / f4_per_row, f = idx % f4_per_row;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row0 + r < a.n_eval) v = __ldg(reinterpret_cast<const float4 *>(a.user_emb + a.eval_users[row0 + r] * a.ldu) + f);
+            *reinterpret_cast<float4 *>(sA + (size_t)(f >> 3) * tile_bytes + sw128_offset(r, f & 7)) = v;
+        }
+        fence_proxy_async();
+        mbar_arrive(a_full);
+        for (int t = 0; t < n_tiles; ++t) {
+            const int s = t % TC_STAGES;
+            if (t >= TC_STAGES) mbar_wait_relaxed(&b_empty[s], ((t / TC_STAGES) - 1) & 1);
+            unsigned char *dst = sB + (size_t)s * nkb * tile_bytes;
+            const long long i0 = a.item_lo + (long long)t * TC_N;
+            // 8 independent 16-byte loads in flight per thread, then their swizzled stores
+            for (int base = (a.debug & 2) && t >= TC_STAGES ? TC_N * f4_per_row : 0; base < TC_N * f4_per_row; base += 128 * 8) {
+                float4 v[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int idx = base + q * 128 + tid;
+                    const int r = idx / f4_per_row, f = idx % f4_per_row;
+                    v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (idx < TC_N * f4_per_row && i0 + r < a.item_hi)
+                        v[q] = __ldg(reinterpret_cast<const float4 *>(a.item_emb + (i0 + r - a.item_lo) * a.ldi) + f);
+                }
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int idx = base + q * 128 + tid;
+                    const int r = idx / f4_per_row, f = idx % f4_per_row;
+                    if (idx < TC_N * f4_per_row)
+                        *reinterpret_cast<float4 *>(dst + (size_t)(f >> 3) * tile_bytes + sw128_offset(r, f & 7)) = v[q];
+                }
+            }
+            fence_proxy_async();
+            mbar_arrive(&b_full[s]);
+        }
+    } else if (warp == 8) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            mbar_wait_relaxed(a_full, 0);
+            for (int t = 0; t < n_tiles; ++t) {
+                const int s = t % TC_STAGES, acc = t & 1;
+                mbar_wait_relaxed(&b_full[s], (t / TC_STAGES) & 1);
+                if (t >= 2) mbar_wait_relaxed(&t_empty[acc], ((t >> 1) - 1) & 1);
+                tc_fence_after();
+                const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB + (size_t)s * nkb * tile_bytes);
+                const uint32_t tmem_d = tmem_base + (uint32_t)acc * TC_N;
+                for (int kb = 0; kb < nkb; ++kb) {
+#pragma unroll
+                    for (int k = 0; k < TC_KB / 8; ++k) {   // UMMA K = 8 tf32 = 32 bytes
+                        const uint64_t da = make_sw128_desc(a_base + kb * tile_bytes + k * 32);
+                        const uint64_t db = make_sw128_desc(b_base + kb * tile_bytes + k * 32);
+                        umma_tf32(tmem_d, da, db, kIdescTf32, (kb | k) ? 1u : 0u);
+                    }
+                }
+                umma_commit(&b_empty[s]);   // shared-memory stage may be refilled once these MMAs retire
+                umma_commit(&t_full[acc]);  // accumulator ready for the epilogue
+            }
+        }
+    } else {
+        // ===== epilogue: thread = TMEM lane = one user row =====
+        const int m = (warp & 3) * 32 + lane;
+        const bool user_ok = row0 + m < a.n_eval;
+        const int K = a.kprime;
+        int cnt = 0;
+        float thr = -CUDART_INF_F;   // K'-th kept score once the list is full
+        int sc = 0, se = 0;
+        if (user_ok && a.seen_indptr) {
+            long long lo = a.seen_indptr[row0 + m], hi = a.seen_indptr[row0 + m + 1];
+            se = (int)hi;
+            while (lo < hi) {   // first seen id >= item_lo
+                const long long mid = (lo + hi) >> 1;
+                if (a.seen_items[mid] < a.item_lo) lo = mid + 1; else hi = mid;
+            }
+            sc = (int)lo;
+        }
+        long long next_seen = sc < se ? (long long)a.seen_items[sc] : (1LL << 62);
+        for (int t = 0; t < n_tiles; ++t) {
+            const int acc = t & 1;
+            mbar_wait(&t_full[acc], (t >> 1) & 1);
+            tc_fence_after();
+            const long long i0 = a.item_lo + (long long)t * TC_N;
+#pragma unroll 1
+            for (int c = 0; c < TC_N / 32; ++c) {
+                float v[32];
+                tmem_ld32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(acc * TC_N + c * 32), v);
+                if (!user_ok || (a.debug & 1)) continue;
+                const long long cbase = i0 + c * 32;
+                unsigned seen = 0;
+                while (next_seen < cbase + 32) {          // next_seen is prefetched: no load on the common path
+                    if (next_seen >= cbase) seen |= 1u << (int)(next_seen - cbase);
+                    ++sc;
+                    next_seen = sc < se ? (long long)a.seen_items[sc] : (1LL << 62);
+                }
+                unsigned pass = 0;
+                const long long room = a.item_hi - cbase;  // columns beyond the catalogue are padding
+#pragma unroll
+                for (int j = 0; j < 32; ++j) pass |= (unsigned)(v[j] > thr || cnt < K) << j;
+                pass &= ~seen;
+                if (room < 32) pass &= (room <= 0) ? 0u : ((1u << (int)room) - 1u);
+                if (pass) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (((pass >> j) & 1u) && (cnt < K || v[j] > thr)) {
+                            const HeapState st = tc_heap_push(ls, li, m, K, cnt, thr, v[j], (int)(cbase + j));
+                            cnt = st.cnt;
+                            thr = st.thr;
+                        }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&t_empty[acc]);
+        }
+        if (user_ok) {
+            a.cand_cnt[row0 + m] = cnt;
+            for (int p = 0; p < K; ++p) {
+                a.cand_scores[(size_t)(row0 + m) * K + p] = p < cnt ? ls[p * TC_M + m] : -CUDART_INF_F;
+                a.cand_ids[(size_t)(row0 + m) * K + p] = p < cnt ? li[p * TC_M + m] : -1;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) tmem_dealloc(tmem_base, 2 * TC_N);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// exact re-scoring of the candidates + proof of completeness
+// ---------------------------------------------------------------------------------------------------
+struct RescoreArgs {
+    const float *user_emb;
+    long long ldu;
+    const float *item_emb;
+    long long ldi;
+    int d;
+    const int64_t *eval_users;
+    int n_eval;
+    int n_items;
+    const float *cand_scores;
+    const int *cand_ids;
+    const int *cand_cnt;
+    int kprime, k;
+    float eps;
+    const float *max_item_norm;  // device scalar
+    int64_t *out_ids;
+    float *out_scores;
+    int *flags;       // [n_eval] 1 = not proven, re-rank exactly
+    int *n_flagged;   // device counter
+};
+
+__global__ void __launch_bounds__(256) topk_rescore_kernel(const RescoreArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= a.n_eval) return;
+    const float *u = a.user_emb + a.eval_users[row] * a.ldu;
+    const int cnt = a.cand_cnt[row];
+    const int K = a.k, KP = a.kprime;
+    int id[2];
+    float sc[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const int c = lane + 32 * q;
+        id[q] = (c < cnt) ? a.cand_ids[(size_t)row * KP + c] : -1;
+        sc[q] = -CUDART_INF_F;
+        if (id[q] >= 0) {
+            const float *it = a.item_emb + (long long)id[q] * a.ldi;
+            float s = 0.f;
+            for (int k = 0; k < a.d; ++k) s = __fmaf_rn(__ldg(u + k), __ldg(it + k), s);   // the exact chain
+            sc[q] = s;
+        }
+    }
+    float un = 0.f;
+    for (int k = lane; k < a.d; k += 32) un += __ldg(u + k) * __ldg(u + k);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) un += __shfl_xor_sync(0xffffffffu, un, o);
+    // canonical rank of each candidate among the candidates
+    float kth = -CUDART_INF_F;
+    int have_k = 0;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        int rank = 0;
+#pragma unroll
+        for (int q2 = 0; q2 < 2; ++q2) {
+            for (int o = 0; o < 32; ++o) {
+                const float os = __shfl_sync(0xffffffffu, sc[q2], o);
+                const int oid = __shfl_sync(0xffffffffu, id[q2], o);
+                if (oid >= 0 && id[q] >= 0 && (os > sc[q] || (os == sc[q] && oid < id[q]))) ++rank;
+            }
+        }
+        if (id[q] >= 0 && rank < K) {
+            a.out_ids[(size_t)row * K + rank] = id[q];
+            a.out_scores[(size_t)row * K + rank] = sc[q];
+        }
+        const bool is_kth = id[q] >= 0 && rank == K - 1;
+        const unsigned bal = __ballot_sync(0xffffffffu, is_kth);
+        if (bal) {
+            kth = __shfl_sync(0xffffffffu, sc[q], __ffs(bal) - 1);
+            have_k = 1;
+        }
+    }
+    // proof: outside items have approx score <= a_min (the worst kept candidate), exact <= a_min + bound
+    float a_min = CUDART_INF_F;
+    for (int c = lane; c < cnt; c += 32) a_min = fminf(a_min, a.cand_scores[(size_t)row * KP + c]);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) a_min = fminf(a_min, __shfl_xor_sync(0xffffffffu, a_min, o));
+    const float bound = a.eps * sqrtf(un) * __ldg(a.max_item_norm) * 1.0001f;
+    bool proven;
+    if (cnt < KP) proven = have_k && cnt >= K;          // every unmasked item was a candidate
+    else proven = have_k && (a_min + bound < kth);
+    if (!isfinite(kth)) proven = false;                 // -inf inside the list: leave it to the exact kernel
+    if (lane == 0) {
+        a.flags[row] = proven ? 0 : 1;
+        if (!proven) atomicAdd(a.n_flagged, 1);
+    }
+}
+
+__global__ void max_row_norm_kernel(const float *x, long long ld, int n, int d, float *out) {
+    const int lane = threadIdx.x & 31;
+    float best = 0.f;
+    for (int r = blockIdx.x * 8 + (threadIdx.x >> 5); r < n; r += gridDim.x * 8) {
+        float s = 0.f;
+        for (int k = lane; k < d; k += 32) { const float v = x[(long long)r * ld + k]; s += v * v; }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        best = fmaxf(best, sqrtf(s));
+    }
+    if (lane == 0) atomicMax(reinterpret_cast<int *>(out), __float_as_int(best));   // non-negative floats order as ints
+}
+
+static size_t tc_smem_bytes(int d, int kprime) {
+    const size_t tile = (size_t)TC_M * 128;
+    return (size_t)(d / TC_KB) * tile * (1 + TC_STAGES) + (size_t)kprime * TC_M * 8 + 128;
+}
+
+}  // namespace gr
+
+using namespace gr;
+
+// Tensor-core nomination + exact re-scoring.  Outputs: topk_ids/topk_scores for the proven rows,
+// flags[row] = 1 and *n_flagged for rows that must be re-ranked with gr_score_topk.  d must be a
+// multiple of 32 with tc_smem_bytes(d, kprime) <= 227 KB (d = 32 or 64), k <= kprime <= 64.
+// workspace: gr_topk_tc_workspace_bytes(n_eval, kprime).
+extern "C" size_t gr_topk_tc_workspace_bytes(int64_t n_eval, int32_t kprime) {
+    if (n_eval < 0 || kprime <= 0) return 0;
+    return (size_t)n_eval * kprime * 8 + (size_t)n_eval * 4 + 256;
+}
+
+extern "C" int gr_topk_tc_supported(int32_t d, int32_t kprime) {
+    return (d > 0 && d % TC_KB == 0 && kprime > 0 && kprime <= TC_KPRIME_MAX && tc_smem_bytes(d, kprime) <= 227 * 1024) ? 1 : 0;
+}
+
+extern "C" int gr_score_topk_tc(const float *user_emb, int64_t ldu, const float *item_emb, int64_t ldi, int32_t d,
+                                const int64_t *eval_users, int64_t n_eval, int64_t n_items,
+                                const int64_t *seen_indptr, const int32_t *seen_items, int32_t k, int32_t kprime,
+                                int64_t *topk_ids, float *topk_scores, int32_t *flags, int32_t *n_flagged,
+                                void *workspace, size_t workspace_bytes, void *stream) {
+    if (!user_emb || !item_emb || !eval_users || !topk_ids || !topk_scores || !flags || !n_flagged || !workspace)
+        return GR_ERR_INVALID;
+    if ((seen_indptr == nullptr) != (seen_items == nullptr)) return GR_ERR_INVALID;
+    if (n_eval < 0 || n_items <= 0 || k <= 0 || k > kprime) return GR_ERR_INVALID;
+    if (!gr_topk_tc_supported(d, kprime) || (ldu & 3) || (ldi & 3) || ldu < d || ldi < d) return GR_ERR_UNSUPPORTED;
+    if (!aligned16(user_emb) || !aligned16(item_emb)) return GR_ERR_INVALID;
+    if (n_eval > 0x7fffffffLL || n_items > 0x7fffffffLL) return GR_ERR_OVERFLOW;
+    if (workspace_bytes < gr_topk_tc_workspace_bytes(n_eval, kprime)) return GR_ERR_WORKSPACE;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    GR_CUDA_CHECK(cudaMemsetAsync(n_flagged, 0, 4, s));
+    if (n_eval == 0) return GR_OK;
+    float *cand_scores = static_cast<float *>(workspace);
+    int *cand_ids = reinterpret_cast<int *>(cand_scores + (size_t)n_eval * kprime);
+    int *cand_cnt = cand_ids + (size_t)n_eval * kprime;
+    float *max_norm = reinterpret_cast<float *>(cand_cnt + n_eval);
+    GR_CUDA_CHECK(cudaMemsetAsync(max_norm, 0, 4, s));
+    max_row_norm_kernel<<<sm_count() * 4, 256, 0, s>>>(item_emb, ldi, (int)n_items, d, max_norm);
+    GR_LAUNCH_CHECK();
+
+    TcArgs a;
+    a.user_emb = user_emb; a.ldu = ldu; a.item_emb = item_emb; a.ldi = ldi; a.d = d;
+    a.eval_users = eval_users; a.n_eval = (int)n_eval; a.item_lo = 0; a.item_hi = n_items;
+    a.seen_indptr = seen_indptr; a.seen_items = seen_items; a.kprime = kprime;
+    a.cand_scores = cand_scores; a.cand_ids = cand_ids; a.cand_cnt = cand_cnt;
+    { const char *e = getenv("GR_TC_DEBUG"); a.debug = e ? atoi(e) : 0; }
+    const size_t smem = tc_smem_bytes(d, kprime) + 1024;   // + slack for the 1024-byte alignment
+    GR_CUDA_CHECK(cudaFuncSetAttribute(topk_tc_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    topk_tc_candidates_kernel<<<(unsigned)((n_eval + TC_M - 1) / TC_M), TC_THREADS, smem, s>>>(a);
+    GR_LAUNCH_CHECK();
+
+    RescoreArgs r;
+    r.user_emb = user_emb; r.ldu = ldu; r.item_emb = item_emb; r.ldi = ldi; r.d = d;
+    r.eval_users = eval_users; r.n_eval = (int)n_eval; r.n_items = (int)n_items;
+    r.cand_scores = cand_scores; r.cand_ids = cand_ids; r.cand_cnt = cand_cnt; r.kprime = kprime; r.k = k;
+    r.eps = 1.0f / 256.0f;   // TF32 truncates both operands (< 2^-10 each): products within 2^-9; 2x margin
+    r.max_item_norm = max_norm; r.out_ids = topk_ids; r.out_scores = topk_scores; r.flags = flags; r.n_flagged = n_flagged;
+    topk_rescore_kernel<<<(unsigned)((n_eval + 7) / 8), 256, 0, s>>>(r);
+    GR_LAUNCH_CHECK();
+    return GR_OK;
+}

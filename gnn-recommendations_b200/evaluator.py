@@ -8,6 +8,7 @@ metrics the reference appends (evaluator.py:118-122) are analysis-only and not c
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional, Sequence
 
 import numpy as np
@@ -62,9 +63,20 @@ def choose_splits(n_eval: int, n_items: int) -> int:
     return int(max(1, min(want, 16, (n_items + 511) // 512)))
 
 
+# candidates kept per user by the tensor-core nomination pass: 40 keeps the selection heaps small enough
+# for two CTAs per SM (d = 64); requests with k + 8 > 40 use 64 (one CTA per SM)
+TC_KPRIME = int(os.environ.get("GR_TC_KPRIME", "40"))
+TC_MIN_ITEMS = 2048     # below this the exact kernel alone is faster
+
+
 def full_rank_topk(user_emb: torch.Tensor, item_emb: torch.Tensor, eval_users, seen_indptr, seen_items, k: int,
-                   n_splits: Optional[int] = None, return_scores: bool = False):
-    """Top-k item ids [n_eval, k] (int64, device) for the given eval users; canonical order."""
+                   n_splits: Optional[int] = None, return_scores: bool = False, tensor_cores: Optional[bool] = None,
+                   stats: Optional[dict] = None):
+    """Top-k item ids [n_eval, k] (int64, device) for the given eval users; canonical order.
+
+    ``tensor_cores``: None = automatic (tcgen05 TF32 nomination + exact re-scoring when the shape is
+    supported, exact FFMA kernel for the rows it cannot prove), False = exact kernel only, True =
+    require the tensor-core path.  Either way the lists and scores are bit-identical."""
     dev = user_emb.device
     if dev.type != "cuda":
         raise RuntimeError("full_rank_topk needs CUDA tensors (no CPU fallback)")
@@ -77,10 +89,46 @@ def full_rank_topk(user_emb: torch.Tensor, item_emb: torch.Tensor, eval_users, s
         seen_items = torch.as_tensor(seen_items, dtype=torch.int32).to(dev).contiguous()
         if seen_items.numel() == 0:
             seen_items = torch.zeros(1, dtype=torch.int32, device=dev)
-    n_splits = choose_splits(n_eval, n_items) if n_splits is None else int(n_splits)
+    l = lib()
     ids = torch.empty((n_eval, k), dtype=torch.int64, device=dev)
     scores = torch.empty((n_eval, k), dtype=torch.float32, device=dev)
-    l = lib()
+    kprime = TC_KPRIME if k + 8 <= TC_KPRIME else 64
+    can_tc = bool(l.gr_topk_tc_supported(d, kprime)) and k + 8 <= kprime and n_items >= kprime
+    if tensor_cores is True and not can_tc:
+        raise ValueError(f"tensor-core top-K path does not support d={d}, k={k}")
+    use_tc = can_tc and (tensor_cores is True or (tensor_cores is None and n_items >= TC_MIN_ITEMS and n_splits is None))
+    if use_tc and n_eval > 0:
+        flags = torch.empty(n_eval, dtype=torch.int32, device=dev)
+        n_flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        ws_bytes = l.gr_topk_tc_workspace_bytes(n_eval, kprime)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            check(l.gr_score_topk_tc(ptr(user_emb), user_emb.stride(0), ptr(item_emb), item_emb.stride(0), d,
+                                     ptr(eval_users), n_eval, n_items, ptr(seen_indptr), ptr(seen_items), k, kprime,
+                                     ptr(ids), ptr(scores), ptr(flags), ptr(n_flag), ptr(ws), ws_bytes,
+                                     stream_ptr()), "gr_score_topk_tc")
+        nf = int(n_flag.item())
+        if stats is not None:
+            stats["tensor_cores"], stats["rows"], stats["rows_reranked_exactly"] = True, n_eval, nf
+        if nf:
+            # rows whose completeness could not be proven: exact kernel on that subset
+            rows = torch.nonzero(flags, as_tuple=False).flatten()
+            sub_ip = sub_it = None
+            if seen_indptr is not None:
+                lens = seen_indptr[rows + 1] - seen_indptr[rows]
+                sub_ip = torch.zeros(rows.numel() + 1, dtype=torch.int64, device=dev)
+                torch.cumsum(lens, 0, out=sub_ip[1:])
+                src = torch.repeat_interleave(seen_indptr[rows] - sub_ip[:-1], lens) + \
+                    torch.arange(int(sub_ip[-1].item()), device=dev)
+                sub_it = seen_items[src] if src.numel() else torch.zeros(1, dtype=torch.int32, device=dev)
+            sub_ids, sub_sc = full_rank_topk(user_emb, item_emb, eval_users[rows], sub_ip, sub_it, k,
+                                             return_scores=True, tensor_cores=False)
+            ids[rows] = sub_ids
+            scores[rows] = sub_sc
+        return (ids, scores) if return_scores else ids
+    if stats is not None:
+        stats["tensor_cores"], stats["rows"], stats["rows_reranked_exactly"] = False, n_eval, n_eval
+    n_splits = choose_splits(n_eval, n_items) if n_splits is None else int(n_splits)
     ws_bytes = l.gr_score_topk_workspace_bytes(n_eval, k, n_splits)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):

@@ -233,6 +233,21 @@ int gr_score_topk(const float *user_emb, int64_t ldu, const float *item_emb, int
                   const int32_t *seen_items, int32_t k, int32_t n_splits, int64_t *topk_ids, float *topk_scores,
                   void *workspace, size_t workspace_bytes, void *stream);
 
+/* Tensor-core (tcgen05, TF32) NOMINATION pass for the same loop + exact re-scoring.
+ * All U x I scores are computed with tcgen05.mma.kind::tf32 (accumulators in TMEM); per user the
+ * kprime best approximate scores of unseen items are kept; those candidates are re-scored with the
+ * exact fmaf chain and ranked canonically; a row is PROVEN when a_min + eps*|u|*max|i| < (k-th exact
+ * score) (a_min = kprime-th approximate score), i.e. no item outside the candidates can enter the
+ * top-k.  Proven rows of topk_ids / topk_scores are bit-identical to gr_score_topk; flags[row] = 1
+ * (and *n_flagged, device int32) marks rows the caller must re-rank with gr_score_topk.
+ * gr_topk_tc_supported: d % 32 == 0, shared memory fits (d = 32 or 64), k <= kprime <= 64. */
+int gr_topk_tc_supported(int32_t d, int32_t kprime);
+size_t gr_topk_tc_workspace_bytes(int64_t n_eval, int32_t kprime);
+int gr_score_topk_tc(const float *user_emb, int64_t ldu, const float *item_emb, int64_t ldi, int32_t d,
+                     const int64_t *eval_users, int64_t n_eval, int64_t n_items, const int64_t *seen_indptr,
+                     const int32_t *seen_items, int32_t k, int32_t kprime, int64_t *topk_ids, float *topk_scores,
+                     int32_t *flags, int32_t *n_flagged, void *workspace, size_t workspace_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -194,3 +194,50 @@ def test_trainer_epoch_validate_evaluate_vs_reference(tiny, tmp_path):
     tr.save_checkpoint(1, vm)
     tr.load_checkpoint(tmp_path / "ckpt" / "checkpoint_epoch_1.pt")
     assert tr.current_epoch == 1
+
+
+# ----------------------------------------------------------------------------- tensor-core nomination
+@pytest.mark.parametrize("d,k,n_items,nu", [(64, 20, 3000, 300), (64, 10, 130, 70), (32, 20, 2500, 129), (64, 32, 4097, 257), (64, 50, 3000, 200)])
+def test_topk_tensor_core_path_is_bit_identical(d, k, n_items, nu):
+    """tcgen05 TF32 nomination + exact re-scoring (+ exact fallback for unproven rows) must reproduce
+    the exact kernel / C oracle bit for bit, including exact ties and seen-item masks."""
+    rng = np.random.default_rng(d * 1000 + k)
+    ue = (rng.standard_normal((nu, d)) * rng.uniform(0.05, 2.0, (nu, 1))).astype(np.float32)
+    ie = (rng.standard_normal((n_items, d)) * rng.uniform(0.1, 1.5, (n_items, 1))).astype(np.float32)
+    ie[rng.integers(0, n_items, 12)] = ie[1]                       # exact ties
+    eu = np.sort(rng.choice(nu, nu - 7, replace=False))
+    indptr, items = [0], []
+    for j, _ in enumerate(eu):
+        m = n_items - k + 3 if j == 5 else int(rng.integers(0, min(80, n_items - k)))   # row 5: fewer than k left
+        items += sorted(rng.choice(n_items, m, replace=False).tolist())
+        indptr.append(len(items))
+    indptr, items = np.asarray(indptr), np.asarray(items, dtype=np.int32)
+    want = coracle.score_topk(ue, ie, eu, indptr, items, k)
+    stats = {}
+    ids, sc = g.full_rank_topk(torch.from_numpy(ue).to(DEV), torch.from_numpy(ie).to(DEV), eu, indptr, items, k,
+                               return_scores=True, tensor_cores=True, stats=stats)
+    assert stats["tensor_cores"] and stats["rows_reranked_exactly"] < len(eu)
+    assert np.array_equal(ids.cpu().numpy(), want)
+    ids2, sc2 = g.full_rank_topk(torch.from_numpy(ue).to(DEV), torch.from_numpy(ie).to(DEV), eu, indptr, items, k,
+                                 return_scores=True, tensor_cores=False)
+    assert torch.equal(ids, ids2) and torch.equal(sc, sc2)
+
+
+def test_topk_tensor_core_c1_shape(c1gold, c1split):
+    nu, ni = c1split["n_users"], c1split["n_items"]
+    csr = g.NormAdjCSR.from_pairs(*c1split["train"], nu, ni, device=DEV, dis_lut=c1gold["dis_lut"])
+    rng = np.random.default_rng(42)
+    uw = (rng.standard_normal((nu, 64)) * 0.1).astype(np.float32)
+    iw = (rng.standard_normal((ni, 64)) * 0.1).astype(np.float32)
+    m = g.LightGCN(nu, ni, 64, 3, 0.1)
+    m.load_state_dict({"user_embedding.weight": torch.from_numpy(uw), "item_embedding.weight": torch.from_numpy(iw)})
+    m.to(DEV)
+    with torch.no_grad():
+        ue, ie = m(csr)
+    gt = ground_truth_dict(c1split["test"])
+    eu = sorted(gt)
+    ip, it = seen_csr(eu, nu, c1split["train"], c1split["valid"])
+    stats = {}
+    ids = g.full_rank_topk(ue, ie, eu, ip, it, 20, tensor_cores=True, stats=stats).cpu()
+    assert np.array_equal(ids.numpy(), c1gold["topk20_canonical"].astype(np.int64))
+    print("C1 tensor-core path: rows re-ranked exactly:", stats["rows_reranked_exactly"], "of", stats["rows"])
