@@ -437,7 +437,7 @@ def run_extras(g, dev):
                       "exact_only_ms": ms_exact, "exact_only_users_per_s": nu / (ms_exact * 1e-3),
                       "exact_only_fp32_tflop_per_s": 2.0 * nu * ni * d / (ms_exact * 1e-3) / 1e12,
                       "lists_identical_to_exact_kernel": same,
-                      "what": "full-ranking top-20 for all users: tcgen05 TF32 nomination (K'=40, two CTAs per SM) + exact fp32 "
+                      "what": "full-ranking top-20 for all users: tcgen05 TF32 nomination (K'=32, two CTAs per SM) + exact fp32 "
                               "re-scoring + exact re-rank of unproven rows; exact_only = FFMA kernel alone"}
     del csr, model, ue, ie
     # --- epoch time at C1: 1 954 steps of sample + propagate + fused BPR + backward + clip + Adam

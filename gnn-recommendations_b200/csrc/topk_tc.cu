@@ -18,7 +18,10 @@
 //   warp  8    MMA       : one elected lane issues d/8 tcgen05.mma (K = 8 per instruction) per tile
 //                          into one of two 128-column TMEM accumulators, tcgen05.commit to mbarriers
 //   warps 4-7  epilogue  : tcgen05.ld 32 columns at a time; thread = TMEM lane = one user: seen-item
-//                          cursor, threshold filter, insertion into its own sorted K' list (shared)
+//                          cursor, threshold filter, append to the user's candidate buffer in shared
+//                          memory; the whole warp prunes its buffers back to K' when one runs full
+// Two CTAs are resident per SM when the buffers fit (d = 64: K' <= 32), so eight epilogue warps
+// share the four schedulers and one CTA's MMA overlaps the other's selection.
 #include <math_constants.h>
 
 #include <cstdlib>
@@ -33,6 +36,7 @@ constexpr int TC_KB = 32;       // tf32 elements per 128-byte swizzle row
 constexpr int TC_STAGES = 1;     // one item-tile stage: two CTAs fit per SM and cover each other's bubbles
 constexpr int TC_THREADS = 288; // 4 producer + 4 epilogue + 1 MMA warps
 constexpr int TC_KPRIME_MAX = 64;
+constexpr int TC_SUB = 16;      // columns filtered and appended per step (buffer room needed)
 
 struct TcArgs {
     const float *user_emb;
@@ -45,10 +49,12 @@ struct TcArgs {
     long long item_lo, item_hi;
     const int64_t *seen_indptr;
     const int32_t *seen_items;
-    int kprime;
-    float *cand_scores;  // [n_eval][kprime] approximate scores (heap order, unsorted)
-    int *cand_ids;       // [n_eval][kprime]
-    int *cand_cnt;       // [n_eval]
+    int kprime;          // candidates kept per user
+    int cap;             // per-user buffer capacity in shared memory, >= kprime + TC_SUB
+    long long split_items;  // items per blockIdx.y (multiple of TC_N); gridDim.y item ranges fill the SMs evenly
+    float *cand_scores;  // [n_eval][gridDim.y][kprime] approximate scores (unsorted)
+    int *cand_ids;       // [n_eval][gridDim.y][kprime]
+    int *cand_cnt;       // [n_eval][gridDim.y]
     int debug;           // GR_TC_DEBUG bits (timing experiments): 1 = epilogue skips selection, 2 = producers skip loads
 };
 
@@ -144,75 +150,67 @@ __device__ __forceinline__ uint32_t sw128_offset(int row, int c16) {
 // instruction descriptor: D = F32, A = B = TF32, both K-major, N at bits [17,23) (N>>3), M at [24,29) (M>>4)
 constexpr uint32_t kIdescTf32 = (1u << 4) | (2u << 7) | (2u << 10) | ((TC_N >> 3) << 17) | ((TC_M >> 4) << 24);
 
-// Per-user candidate set = binary MIN-heap of the K' best (approximate score, id) pairs seen so far,
-// position-major in shared memory (entry p of user m at [p * 128 + m]).  "a worse than b" =
-// a.score < b.score, or equal scores and a.id > b.id (the canonical order prefers small ids).  The
-// root is the worst kept candidate, so the admission threshold is its score and a push is O(log K')
-// (a sorted list cost ~K'/2 shifts per push and, with warp divergence, dominated the kernel).
-struct HeapState {
+// Per-user candidate set = unsorted buffer of up to `cap` (approximate score, id) pairs in shared
+// memory, position-major (entry p of user m at [p * 128 + m], conflict-free for a warp).  Appending is
+// two predicated stores; the admission threshold `thr` is the K'-th best score at the last prune (stale
+// in between, which only admits a few extra entries).  When any lane of the warp lacks room for the next
+// TC_SUB columns the WHOLE warp prunes: every lane drops its worst entries until K' remain.  Doing it
+// warp-synchronously matters: a per-lane structure (heap, sorted list) makes the warp execute one
+// update per lane-event (~10 K divergent events per warp at 50 K items), this one ~30 prunes.
+// "a worse than b" = a.score < b.score, or equal scores and a.id > b.id (canonical order prefers small ids).
+struct SelState {
     int cnt;
     float thr;
 };
-__device__ __forceinline__ bool tc_worse(float sa, int ia, float sb, int ib) { return sa < sb || (sa == sb && ia > ib); }
 
-__device__ __noinline__ HeapState tc_heap_push(float *hs, int *hi, int m, int K, int cnt, float thr, float s, int id) {
-    if (cnt < K) {                       // filling: append and sift up
-        int i = cnt++;
-        while (i > 0) {
-            const int par = (i - 1) >> 1;
-            const float ps = hs[par * TC_M + m];
-            const int pi = hi[par * TC_M + m];
-            if (!tc_worse(s, id, ps, pi)) break;     // parent must be the worse one
-            hs[i * TC_M + m] = ps;
-            hi[i * TC_M + m] = pi;
-            i = par;
-        }
-        hs[i * TC_M + m] = s;
-        hi[i * TC_M + m] = id;
-    } else {                             // full: the new entry replaces the root, sift down
-        int i = 0;
-        while (true) {
-            int c = 2 * i + 1;
-            if (c >= K) break;
-            float cs = hs[c * TC_M + m];
-            if (c + 1 < K) {
-                const float rs = hs[(c + 1) * TC_M + m];
+__device__ __noinline__ SelState tc_prune(float *bs, int *bi, int m, int K, int cnt, float thr) {
+    while (cnt > K) {                    // remove the worst entry; lanes iterate cnt - K times
+        float sw = bs[m];
+        int iw = 0;
+        for (int j = 1; j < cnt; ++j) {
+            const float sj = bs[j * TC_M + m];
+            if (sj <= sw) {
                 // ids are only read on exact score ties
-                if (rs < cs || (rs == cs && hi[(c + 1) * TC_M + m] > hi[c * TC_M + m])) { ++c; cs = rs; }
+                if (sj < sw || bi[j * TC_M + m] > bi[iw * TC_M + m]) { sw = sj; iw = j; }
             }
-            // the new entry has the largest id so far: on a score tie it is the worse one and stays above
-            if (!(cs < s)) break;                    // both children are better than (or tie with) the new entry
-            hs[i * TC_M + m] = cs;
-            hi[i * TC_M + m] = hi[c * TC_M + m];
-            i = c;
         }
-        hs[i * TC_M + m] = s;
-        hi[i * TC_M + m] = id;
+        --cnt;
+        bs[iw * TC_M + m] = bs[cnt * TC_M + m];
+        bi[iw * TC_M + m] = bi[cnt * TC_M + m];
     }
-    HeapState st;
+    if (cnt == K) {                      // threshold = worst kept score
+        float sw = bs[m];
+        for (int j = 1; j < K; ++j) sw = fminf(sw, bs[j * TC_M + m]);
+        thr = sw;
+    }
+    SelState st;
     st.cnt = cnt;
-    st.thr = (cnt == K) ? hs[m] : -CUDART_INF_F;     // root score once the heap is full
+    st.thr = thr;
     return st;
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 2) topk_tc_candidates_kernel(const TcArgs a) {
-    extern __shared__ unsigned char smem_dyn[];
-    // SWIZZLE_128B operand tiles need 1024-byte alignment (the launch adds 1 KB of slack)
-    unsigned char *smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+    // SWIZZLE_128B operand tiles need 1024-byte alignment; the kernel has no static shared memory, so
+    // the dynamic window starts at the CTA's (1 KB-granular) allocation.  Checked, not assumed.
+    extern __shared__ __align__(1024) unsigned char smem_dyn[];
+    unsigned char *smem_raw = smem_dyn;
+    if ((smem_u32(smem_dyn) & 1023u) != 0) __trap();
     const int d = a.d;
     const int nkb = d / TC_KB;                       // k-blocks of 32 tf32
     const uint32_t tile_bytes = TC_M * 128;          // one k-block of a 128-row operand: 16 KB
     unsigned char *sA = smem_raw;                    // [nkb][128 rows][128 B]
     unsigned char *sB = sA + (size_t)nkb * tile_bytes;            // [stages][nkb][128 rows][128 B]
-    float *ls = reinterpret_cast<float *>(sB + (size_t)TC_STAGES * nkb * tile_bytes);   // [kprime][128]
-    int *li = reinterpret_cast<int *>(ls + (size_t)a.kprime * TC_M);                      // [kprime][128]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(li + (size_t)a.kprime * TC_M);
+    float *ls = reinterpret_cast<float *>(sB + (size_t)TC_STAGES * nkb * tile_bytes);   // [cap][128]
+    int *li = reinterpret_cast<int *>(ls + (size_t)a.cap * TC_M);                         // [cap][128]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(li + (size_t)a.cap * TC_M);
     uint64_t *b_full = bars, *b_empty = bars + 2, *t_full = bars + 4, *t_empty = bars + 6, *a_full = bars + 8;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 9);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int row0 = blockIdx.x * TC_M;
-    const long long n_it = a.item_hi - a.item_lo;
+    const long long item_lo = a.item_lo + (long long)blockIdx.y * a.split_items;
+    const long long item_hi = min(a.item_hi, item_lo + a.split_items);
+    const long long n_it = item_hi > item_lo ? item_hi - item_lo : 0;
     const int n_tiles = (int)((n_it + TC_N - 1) / TC_N);
 
     if (tid == 0) {
@@ -248,7 +246,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) topk_tc_candidates_kernel(const
             const int s = t % TC_STAGES;
             if (t >= TC_STAGES) mbar_wait_relaxed(&b_empty[s], ((t / TC_STAGES) - 1) & 1);
             unsigned char *dst = sB + (size_t)s * nkb * tile_bytes;
-            const long long i0 = a.item_lo + (long long)t * TC_N;
+            const long long i0 = item_lo + (long long)t * TC_N;
             // 8 independent 16-byte loads in flight per thread, then their swizzled stores
             for (int base = (a.debug & 2) && t >= TC_STAGES ? TC_N * f4_per_row : 0; base < TC_N * f4_per_row; base += 128 * 8) {
                 float4 v[8];
@@ -257,7 +255,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) topk_tc_candidates_kernel(const
                     const int idx = base + q * 128 + tid;
                     const int r = idx / f4_per_row, f = idx % f4_per_row;
                     v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (idx < TC_N * f4_per_row && i0 + r < a.item_hi)
+                    if (idx < TC_N * f4_per_row && i0 + r < item_hi)
                         v[q] = __ldg(reinterpret_cast<const float4 *>(a.item_emb + (i0 + r - a.item_lo) * a.ldi) + f);
                 }
 #pragma unroll
@@ -298,16 +296,16 @@ __global__ void __launch_bounds__(TC_THREADS, 2) topk_tc_candidates_kernel(const
         // ===== epilogue: thread = TMEM lane = one user row =====
         const int m = (warp & 3) * 32 + lane;
         const bool user_ok = row0 + m < a.n_eval;
-        const int K = a.kprime;
+        const int K = a.kprime, cap = a.cap;
         int cnt = 0;
-        float thr = -CUDART_INF_F;   // K'-th kept score once the list is full
+        float thr = -CUDART_INF_F;   // K'-th kept score at the last prune
         int sc = 0, se = 0;
         if (user_ok && a.seen_indptr) {
             long long lo = a.seen_indptr[row0 + m], hi = a.seen_indptr[row0 + m + 1];
             se = (int)hi;
             while (lo < hi) {   // first seen id >= item_lo
                 const long long mid = (lo + hi) >> 1;
-                if (a.seen_items[mid] < a.item_lo) lo = mid + 1; else hi = mid;
+                if (a.seen_items[mid] < item_lo) lo = mid + 1; else hi = mid;
             }
             sc = (int)lo;
         }
@@ -316,12 +314,12 @@ __global__ void __launch_bounds__(TC_THREADS, 2) topk_tc_candidates_kernel(const
             const int acc = t & 1;
             mbar_wait(&t_full[acc], (t >> 1) & 1);
             tc_fence_after();
-            const long long i0 = a.item_lo + (long long)t * TC_N;
+            const long long i0 = item_lo + (long long)t * TC_N;
 #pragma unroll 1
             for (int c = 0; c < TC_N / 32; ++c) {
                 float v[32];
                 tmem_ld32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(acc * TC_N + c * 32), v);
-                if (!user_ok || (a.debug & 1)) continue;
+                if (a.debug & 1) continue;
                 const long long cbase = i0 + c * 32;
                 unsigned seen = 0;
                 while (next_seen < cbase + 32) {          // next_seen is prefetched: no load on the common path
@@ -329,30 +327,47 @@ __global__ void __launch_bounds__(TC_THREADS, 2) topk_tc_candidates_kernel(const
                     ++sc;
                     next_seen = sc < se ? (long long)a.seen_items[sc] : (1LL << 62);
                 }
-                unsigned pass = 0;
-                const long long room = a.item_hi - cbase;  // columns beyond the catalogue are padding
+                const long long room = item_hi - cbase;  // columns beyond the catalogue are padding
+                unsigned valid = user_ok ? ~seen : 0u;
+                if (room < 32) valid &= (room <= 0) ? 0u : ((1u << (int)room) - 1u);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) pass |= (unsigned)(v[j] > thr || cnt < K) << j;
-                pass &= ~seen;
-                if (room < 32) pass &= (room <= 0) ? 0u : ((1u << (int)room) - 1u);
-                if (pass) {
+                for (int h = 0; h < 32 / TC_SUB; ++h) {   // the warp stays converged through this loop
+                    unsigned pass = 0;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (((pass >> j) & 1u) && (cnt < K || v[j] > thr)) {
-                            const HeapState st = tc_heap_push(ls, li, m, K, cnt, thr, v[j], (int)(cbase + j));
-                            cnt = st.cnt;
-                            thr = st.thr;
+                    for (int j = 0; j < TC_SUB; ++j) pass |= (unsigned)(v[h * TC_SUB + j] > thr) << j;
+                    pass &= valid >> (h * TC_SUB);
+                    if (!__any_sync(0xffffffffu, pass != 0)) continue;
+                    if (__any_sync(0xffffffffu, cnt + __popc(pass) > cap)) {
+                        const SelState st = tc_prune(ls, li, m, K, cnt, thr);
+                        cnt = st.cnt;
+                        thr = st.thr;
+                        unsigned again = 0;
+#pragma unroll
+                        for (int j = 0; j < TC_SUB; ++j) again |= (unsigned)(v[h * TC_SUB + j] > thr) << j;
+                        pass &= again;
+                    }
+#pragma unroll
+                    for (int j = 0; j < TC_SUB; ++j)
+                        if ((pass >> j) & 1u) {
+                            ls[cnt * TC_M + m] = v[h * TC_SUB + j];
+                            li[cnt * TC_M + m] = (int)(cbase + h * TC_SUB + j);
+                            ++cnt;
                         }
                 }
             }
             tc_fence_before();
             mbar_arrive(&t_empty[acc]);
         }
+        {
+            const SelState st = tc_prune(ls, li, m, K, cnt, thr);
+            cnt = st.cnt;
+        }
         if (user_ok) {
-            a.cand_cnt[row0 + m] = cnt;
+            const size_t seg = (size_t)(row0 + m) * gridDim.y + blockIdx.y;
+            a.cand_cnt[seg] = cnt;
             for (int p = 0; p < K; ++p) {
-                a.cand_scores[(size_t)(row0 + m) * K + p] = p < cnt ? ls[p * TC_M + m] : -CUDART_INF_F;
-                a.cand_ids[(size_t)(row0 + m) * K + p] = p < cnt ? li[p * TC_M + m] : -1;
+                a.cand_scores[seg * K + p] = p < cnt ? ls[p * TC_M + m] : -CUDART_INF_F;
+                a.cand_ids[seg * K + p] = p < cnt ? li[p * TC_M + m] : -1;
             }
         }
     }
@@ -376,7 +391,7 @@ struct RescoreArgs {
     const float *cand_scores;
     const int *cand_ids;
     const int *cand_cnt;
-    int kprime, k;
+    int kprime, k, n_seg;
     float eps;
     const float *max_item_norm;  // device scalar
     int64_t *out_ids;
@@ -385,19 +400,22 @@ struct RescoreArgs {
     int *n_flagged;   // device counter
 };
 
+// One warp per user; NQ candidates per lane (S segments of K' candidates, S * K' <= 32 * NQ).
+template <int NQ>
 __global__ void __launch_bounds__(256) topk_rescore_kernel(const RescoreArgs a) {
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (row >= a.n_eval) return;
     const float *u = a.user_emb + a.eval_users[row] * a.ldu;
-    const int cnt = a.cand_cnt[row];
-    const int K = a.k, KP = a.kprime;
-    int id[2];
-    float sc[2];
+    const int K = a.k, KP = a.kprime, S = a.n_seg;
+    const int total = S * KP;
+    int id[NQ];
+    float sc[NQ];
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
+    for (int q = 0; q < NQ; ++q) {
         const int c = lane + 32 * q;
-        id[q] = (c < cnt) ? a.cand_ids[(size_t)row * KP + c] : -1;
+        id[q] = -1;
+        if (c < total && (c % KP) < a.cand_cnt[(size_t)row * S + c / KP]) id[q] = a.cand_ids[(size_t)row * total + c];
         sc[q] = -CUDART_INF_F;
         if (id[q] >= 0) {
             const float *it = a.item_emb + (long long)id[q] * a.ldi;
@@ -414,10 +432,10 @@ __global__ void __launch_bounds__(256) topk_rescore_kernel(const RescoreArgs a) 
     float kth = -CUDART_INF_F;
     int have_k = 0;
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
+    for (int q = 0; q < NQ; ++q) {
         int rank = 0;
 #pragma unroll
-        for (int q2 = 0; q2 < 2; ++q2) {
+        for (int q2 = 0; q2 < NQ; ++q2) {
             for (int o = 0; o < 32; ++o) {
                 const float os = __shfl_sync(0xffffffffu, sc[q2], o);
                 const int oid = __shfl_sync(0xffffffffu, id[q2], o);
@@ -435,15 +453,21 @@ __global__ void __launch_bounds__(256) topk_rescore_kernel(const RescoreArgs a) 
             have_k = 1;
         }
     }
-    // proof: outside items have approx score <= a_min (the worst kept candidate), exact <= a_min + bound
-    float a_min = CUDART_INF_F;
-    for (int c = lane; c < cnt; c += 32) a_min = fminf(a_min, a.cand_scores[(size_t)row * KP + c]);
+    // proof: an item outside segment s's candidates has approximate score <= that segment's worst kept
+    // candidate (only full segments rejected anything), so exact <= a_out + bound for every outside item
+    float a_out = -CUDART_INF_F;
+    for (int sgm = 0; sgm < S; ++sgm) {
+        if (a.cand_cnt[(size_t)row * S + sgm] < KP) continue;
+        float a_min = CUDART_INF_F;
+        for (int c = lane; c < KP; c += 32) a_min = fminf(a_min, a.cand_scores[((size_t)row * S + sgm) * KP + c]);
 #pragma unroll
-    for (int o = 16; o; o >>= 1) a_min = fminf(a_min, __shfl_xor_sync(0xffffffffu, a_min, o));
+        for (int o = 16; o; o >>= 1) a_min = fminf(a_min, __shfl_xor_sync(0xffffffffu, a_min, o));
+        a_out = fmaxf(a_out, a_min);
+    }
     const float bound = a.eps * sqrtf(un) * __ldg(a.max_item_norm) * 1.0001f;
     bool proven;
-    if (cnt < KP) proven = have_k && cnt >= K;          // every unmasked item was a candidate
-    else proven = have_k && (a_min + bound < kth);
+    if (a_out == -CUDART_INF_F) proven = have_k;        // every unmasked item was a candidate
+    else proven = have_k && (a_out + bound < kth);
     if (!isfinite(kth)) proven = false;                 // -inf inside the list: leave it to the exact kernel
     if (lane == 0) {
         a.flags[row] = proven ? 0 : 1;
@@ -464,9 +488,22 @@ __global__ void max_row_norm_kernel(const float *x, long long ld, int n, int d, 
     if (lane == 0) atomicMax(reinterpret_cast<int *>(out), __float_as_int(best));   // non-negative floats order as ints
 }
 
-static size_t tc_smem_bytes(int d, int kprime) {
+static size_t tc_smem_bytes(int d, int cap) {
     const size_t tile = (size_t)TC_M * 128;
-    return (size_t)(d / TC_KB) * tile * (1 + TC_STAGES) + (size_t)kprime * TC_M * 8 + 128;
+    return (size_t)(d / TC_KB) * tile * (1 + TC_STAGES) + (size_t)cap * TC_M * 8 + 128;
+}
+constexpr size_t kSmemTwoCtas = (228 * 1024) / 2 - 1024;   // per CTA when two share an SM (1 KB reserved each)
+constexpr size_t kSmemOneCta = 227 * 1024;
+// buffer capacity: the largest that still lets two CTAs share an SM, else K' + 2 * TC_SUB in one CTA per SM
+static int tc_capacity(int d, int kprime) {
+    if (d <= 0 || d % TC_KB != 0) return 0;
+    const size_t fixed = tc_smem_bytes(d, 0);
+    const size_t per = (size_t)TC_M * 8;
+    if (fixed + (size_t)(kprime + TC_SUB) * per <= kSmemTwoCtas) return (int)((kSmemTwoCtas - fixed) / per);
+    if (fixed + (size_t)(kprime + TC_SUB) * per > kSmemOneCta) return 0;
+    const int want = kprime + 2 * TC_SUB;
+    const int most = (int)((kSmemOneCta - fixed) / per);
+    return want < most ? want : most;
 }
 
 }  // namespace gr
@@ -475,15 +512,34 @@ using namespace gr;
 
 // Tensor-core nomination + exact re-scoring.  Outputs: topk_ids/topk_scores for the proven rows,
 // flags[row] = 1 and *n_flagged for rows that must be re-ranked with gr_score_topk.  d must be a
-// multiple of 32 with tc_smem_bytes(d, kprime) <= 227 KB (d = 32 or 64), k <= kprime <= 64.
+// multiple of 32 (d = 32 or 64 fit shared memory), k <= kprime <= 64.
 // workspace: gr_topk_tc_workspace_bytes(n_eval, kprime).
+// item ranges per user tile: the count (with S * K' <= 128 candidates per user for the re-scoring pass)
+// that minimises the number of CTA waves per unit of work
+static int tc_splits(int64_t n_eval, int32_t d, int32_t kprime) {
+    const long long tiles = (n_eval + TC_M - 1) / TC_M;
+    if (tiles <= 0) return 1;
+    const int per_sm = (tc_smem_bytes(d, tc_capacity(d, kprime)) <= kSmemTwoCtas) ? 2 : 1;
+    const long long slots = (long long)sm_count() * per_sm;
+    const int s_max = 128 / kprime > 0 ? 128 / kprime : 1;
+    int best = 1;
+    double best_cost = 1e30;
+    for (int sp = 1; sp <= s_max; ++sp) {
+        const double cost = (double)((tiles * sp + slots - 1) / slots) / sp;
+        if (cost < best_cost * 0.95) { best_cost = cost; best = sp; }   // more ranges only for a >5 % gain
+    }
+    return best;
+}
+
+// sized for the largest number of item ranges (128 / K'), so it does not depend on the catalogue
 extern "C" size_t gr_topk_tc_workspace_bytes(int64_t n_eval, int32_t kprime) {
-    if (n_eval < 0 || kprime <= 0) return 0;
-    return (size_t)n_eval * kprime * 8 + (size_t)n_eval * 4 + 256;
+    if (n_eval < 0 || kprime <= 0 || kprime > TC_KPRIME_MAX) return 0;
+    const int s_max = 128 / kprime;
+    return (size_t)n_eval * s_max * kprime * 8 + (size_t)n_eval * s_max * 4 + 256;
 }
 
 extern "C" int gr_topk_tc_supported(int32_t d, int32_t kprime) {
-    return (d > 0 && d % TC_KB == 0 && kprime > 0 && kprime <= TC_KPRIME_MAX && tc_smem_bytes(d, kprime) <= 227 * 1024) ? 1 : 0;
+    return (d > 0 && d % TC_KB == 0 && kprime > 0 && kprime <= TC_KPRIME_MAX && tc_capacity(d, kprime) > 0) ? 1 : 0;
 }
 
 extern "C" int gr_score_topk_tc(const float *user_emb, int64_t ldu, const float *item_emb, int64_t ldi, int32_t d,
@@ -502,10 +558,15 @@ extern "C" int gr_score_topk_tc(const float *user_emb, int64_t ldu, const float 
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     GR_CUDA_CHECK(cudaMemsetAsync(n_flagged, 0, 4, s));
     if (n_eval == 0) return GR_OK;
+    const long long tiles_total = (n_items + TC_N - 1) / TC_N;
+    int n_seg = tc_splits(n_eval, d, kprime);
+    if (n_seg > tiles_total / 8) n_seg = (int)(tiles_total / 8 > 0 ? tiles_total / 8 : 1);   // >= 1024 items per range
+    const long long split_items = ((tiles_total + n_seg - 1) / n_seg) * TC_N;
+    n_seg = (int)((n_items + split_items - 1) / split_items);
     float *cand_scores = static_cast<float *>(workspace);
-    int *cand_ids = reinterpret_cast<int *>(cand_scores + (size_t)n_eval * kprime);
-    int *cand_cnt = cand_ids + (size_t)n_eval * kprime;
-    float *max_norm = reinterpret_cast<float *>(cand_cnt + n_eval);
+    int *cand_ids = reinterpret_cast<int *>(cand_scores + (size_t)n_eval * n_seg * kprime);
+    int *cand_cnt = cand_ids + (size_t)n_eval * n_seg * kprime;
+    float *max_norm = reinterpret_cast<float *>(cand_cnt + (size_t)n_eval * n_seg);
     GR_CUDA_CHECK(cudaMemsetAsync(max_norm, 0, 4, s));
     max_row_norm_kernel<<<sm_count() * 4, 256, 0, s>>>(item_emb, ldi, (int)n_items, d, max_norm);
     GR_LAUNCH_CHECK();
@@ -513,21 +574,27 @@ extern "C" int gr_score_topk_tc(const float *user_emb, int64_t ldu, const float 
     TcArgs a;
     a.user_emb = user_emb; a.ldu = ldu; a.item_emb = item_emb; a.ldi = ldi; a.d = d;
     a.eval_users = eval_users; a.n_eval = (int)n_eval; a.item_lo = 0; a.item_hi = n_items;
-    a.seen_indptr = seen_indptr; a.seen_items = seen_items; a.kprime = kprime;
+    a.seen_indptr = seen_indptr; a.seen_items = seen_items; a.kprime = kprime; a.cap = tc_capacity(d, kprime);
+    a.split_items = split_items;
     a.cand_scores = cand_scores; a.cand_ids = cand_ids; a.cand_cnt = cand_cnt;
     { const char *e = getenv("GR_TC_DEBUG"); a.debug = e ? atoi(e) : 0; }
-    const size_t smem = tc_smem_bytes(d, kprime) + 1024;   // + slack for the 1024-byte alignment
+    const size_t smem = tc_smem_bytes(d, a.cap);
     GR_CUDA_CHECK(cudaFuncSetAttribute(topk_tc_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    topk_tc_candidates_kernel<<<(unsigned)((n_eval + TC_M - 1) / TC_M), TC_THREADS, smem, s>>>(a);
+    topk_tc_candidates_kernel<<<dim3((unsigned)((n_eval + TC_M - 1) / TC_M), (unsigned)n_seg), TC_THREADS, smem, s>>>(a);
     GR_LAUNCH_CHECK();
 
     RescoreArgs r;
     r.user_emb = user_emb; r.ldu = ldu; r.item_emb = item_emb; r.ldi = ldi; r.d = d;
     r.eval_users = eval_users; r.n_eval = (int)n_eval; r.n_items = (int)n_items;
     r.cand_scores = cand_scores; r.cand_ids = cand_ids; r.cand_cnt = cand_cnt; r.kprime = kprime; r.k = k;
-    r.eps = 1.0f / 256.0f;   // TF32 truncates both operands (< 2^-10 each): products within 2^-9; 2x margin
+    r.n_seg = n_seg;
+    // TF32 drops 13 mantissa bits of both operands (relative error < 2^-10 each), so every product is within
+    // 2^-9 (1 + 2^-11) of the fp32 one and, by Cauchy-Schwarz, the score within 2^-9 |u| |i|; fp32
+    // accumulation adds ~d * 2^-24.  eps = 1.5 * 2^-9 leaves a 50 % margin.
+    r.eps = 1.5f / 512.0f;
     r.max_item_norm = max_norm; r.out_ids = topk_ids; r.out_scores = topk_scores; r.flags = flags; r.n_flagged = n_flagged;
-    topk_rescore_kernel<<<(unsigned)((n_eval + 7) / 8), 256, 0, s>>>(r);
+    if (n_seg * kprime <= 64) topk_rescore_kernel<2><<<(unsigned)((n_eval + 7) / 8), 256, 0, s>>>(r);
+    else topk_rescore_kernel<4><<<(unsigned)((n_eval + 7) / 8), 256, 0, s>>>(r);
     GR_LAUNCH_CHECK();
     return GR_OK;
 }

@@ -60,12 +60,20 @@ def seen_csr(eval_users: Sequence[int], n_users: int, *pair_sets):
 def choose_splits(n_eval: int, n_items: int) -> int:
     tiles = max(1, (n_eval + 63) // 64)
     want = (2 * 148 + tiles - 1) // tiles
-    return int(max(1, min(want, 16, (n_items + 511) // 512)))
+    return int(max(1, min(want, 64, (n_items + 511) // 512)))
 
 
-# candidates kept per user by the tensor-core nomination pass: 40 keeps the selection heaps small enough
-# for two CTAs per SM (d = 64); requests with k + 8 > 40 use 64 (one CTA per SM)
-TC_KPRIME = int(os.environ.get("GR_TC_KPRIME", "40"))
+# candidates kept per user by the tensor-core nomination pass: k + 12 rounded up to a multiple of 8
+# (k = 20 -> 32, which lets two CTAs share an SM at d = 64), at most 64; GR_TC_KPRIME overrides
+TC_KPRIME = int(os.environ.get("GR_TC_KPRIME", "0"))
+
+
+def tc_kprime(k: int) -> int:
+    if TC_KPRIME:
+        return TC_KPRIME
+    return min(64, max(24, (k + 12 + 7) // 8 * 8))
+
+
 TC_MIN_ITEMS = 2048     # below this the exact kernel alone is faster
 
 
@@ -92,7 +100,7 @@ def full_rank_topk(user_emb: torch.Tensor, item_emb: torch.Tensor, eval_users, s
     l = lib()
     ids = torch.empty((n_eval, k), dtype=torch.int64, device=dev)
     scores = torch.empty((n_eval, k), dtype=torch.float32, device=dev)
-    kprime = TC_KPRIME if k + 8 <= TC_KPRIME else 64
+    kprime = tc_kprime(k)
     can_tc = bool(l.gr_topk_tc_supported(d, kprime)) and k + 8 <= kprime and n_items >= kprime
     if tensor_cores is True and not can_tc:
         raise ValueError(f"tensor-core top-K path does not support d={d}, k={k}")
