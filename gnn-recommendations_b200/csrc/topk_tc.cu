@@ -18,9 +18,9 @@
 //   warp  8    MMA       : one elected lane issues d/8 tcgen05.mma (K = 8 per instruction) per tile
 //                          into one of two 128-column TMEM accumulators, tcgen05.commit to mbarriers
 //   warps 4-7  epilogue  : tcgen05.ld 32 columns at a time; thread = TMEM lane = one user: seen-item
-//                          cursor, threshold filter, append to the user's candidate buffer in shared
-//                          memory; the whole warp prunes its buffers back to K' when one runs full
-// Two CTAs are resident per SM when the buffers fit (d = 64: K' <= 32), so eight epilogue warps
+//                          cursor, threshold filter, lane-parallel pushes into the user's K' min-heap
+//                          in shared memory
+// Two CTAs are resident per SM when the heaps fit (d = 64: K' <= 32), so eight epilogue warps
 // share the four schedulers and one CTA's MMA overlaps the other's selection.
 #include <math_constants.h>
 
@@ -36,7 +36,6 @@ constexpr int TC_KB = 32;       // tf32 elements per 128-byte swizzle row
 constexpr int TC_STAGES = 1;     // one item-tile stage: two CTAs fit per SM and cover each other's bubbles
 constexpr int TC_THREADS = 288; // 4 producer + 4 epilogue + 1 MMA warps
 constexpr int TC_KPRIME_MAX = 64;
-constexpr int TC_SUB = 16;      // columns filtered and appended per step (buffer room needed)
 
 struct TcArgs {
     const float *user_emb;
@@ -50,7 +49,6 @@ struct TcArgs {
     const int64_t *seen_indptr;
     const int32_t *seen_items;
     int kprime;          // candidates kept per user
-    int cap;             // per-user buffer capacity in shared memory, >= kprime + TC_SUB
     long long split_items;  // items per blockIdx.y (multiple of TC_N); gridDim.y item ranges fill the SMs evenly
     float *cand_scores;  // [n_eval][gridDim.y][kprime] approximate scores (unsorted)
     int *cand_ids;       // [n_eval][gridDim.y][kprime]
@@ -150,42 +148,52 @@ __device__ __forceinline__ uint32_t sw128_offset(int row, int c16) {
 // instruction descriptor: D = F32, A = B = TF32, both K-major, N at bits [17,23) (N>>3), M at [24,29) (M>>4)
 constexpr uint32_t kIdescTf32 = (1u << 4) | (2u << 7) | (2u << 10) | ((TC_N >> 3) << 17) | ((TC_M >> 4) << 24);
 
-// Per-user candidate set = unsorted buffer of up to `cap` (approximate score, id) pairs in shared
-// memory, position-major (entry p of user m at [p * 128 + m], conflict-free for a warp).  Appending is
-// two predicated stores; the admission threshold `thr` is the K'-th best score at the last prune (stale
-// in between, which only admits a few extra entries).  When any lane of the warp lacks room for the next
-// TC_SUB columns the WHOLE warp prunes: every lane drops its worst entries until K' remain.  Doing it
-// warp-synchronously matters: a per-lane structure (heap, sorted list) makes the warp execute one
-// update per lane-event (~10 K divergent events per warp at 50 K items), this one ~30 prunes.
-// "a worse than b" = a.score < b.score, or equal scores and a.id > b.id (canonical order prefers small ids).
+// Per-user candidate set = binary MIN-heap on the approximate score of the K' best seen so far,
+// position-major in shared memory (entry p of user m at [p * 128 + m], conflict-free for a warp).  The
+// root is the worst kept score = the admission threshold.  Ties are broken arbitrarily: the nomination
+// only has to guarantee "every rejected or evicted item has approximate score <= the final root".
+// Pushes run LANE-PARALLEL: the warp stages the 32 columns it just read from TMEM in shared memory and
+// every lane pops its own passing columns, so the warp executes max-over-lanes pushes per chunk
+// (~1-2) instead of one divergent push per (lane, column) event (~8 K per warp at 50 K items).
 struct SelState {
     int cnt;
     float thr;
 };
 
-__device__ __noinline__ SelState tc_prune(float *bs, int *bi, int m, int K, int cnt, float thr) {
-    while (cnt > K) {                    // remove the worst entry; lanes iterate cnt - K times
-        float sw = bs[m];
-        int iw = 0;
-        for (int j = 1; j < cnt; ++j) {
-            const float sj = bs[j * TC_M + m];
-            if (sj <= sw) {
-                // ids are only read on exact score ties
-                if (sj < sw || bi[j * TC_M + m] > bi[iw * TC_M + m]) { sw = sj; iw = j; }
-            }
+__device__ __forceinline__ SelState tc_heap_push(float *hs, int *hi, int m, int K, int cnt, float s, int id) {
+    if (cnt < K) {                       // filling: append and sift up
+        int i = cnt++;
+        while (i > 0) {
+            const int par = (i - 1) >> 1;
+            const float ps = hs[par * TC_M + m];
+            if (!(s < ps)) break;                    // the parent must be the worse one
+            hs[i * TC_M + m] = ps;
+            hi[i * TC_M + m] = hi[par * TC_M + m];
+            i = par;
         }
-        --cnt;
-        bs[iw * TC_M + m] = bs[cnt * TC_M + m];
-        bi[iw * TC_M + m] = bi[cnt * TC_M + m];
-    }
-    if (cnt == K) {                      // threshold = worst kept score
-        float sw = bs[m];
-        for (int j = 1; j < K; ++j) sw = fminf(sw, bs[j * TC_M + m]);
-        thr = sw;
+        hs[i * TC_M + m] = s;
+        hi[i * TC_M + m] = id;
+    } else {                             // full: the new entry replaces the root, sift down
+        int i = 0;
+        while (true) {
+            int c = 2 * i + 1;
+            if (c >= K) break;
+            float cs = hs[c * TC_M + m];
+            if (c + 1 < K) {
+                const float rs = hs[(c + 1) * TC_M + m];
+                if (rs < cs) { ++c; cs = rs; }
+            }
+            if (!(cs < s)) break;
+            hs[i * TC_M + m] = cs;
+            hi[i * TC_M + m] = hi[c * TC_M + m];
+            i = c;
+        }
+        hs[i * TC_M + m] = s;
+        hi[i * TC_M + m] = id;
     }
     SelState st;
     st.cnt = cnt;
-    st.thr = thr;
+    st.thr = (cnt == K) ? hs[m] : -CUDART_INF_F;     // root score once the heap is full
     return st;
 }
 
@@ -200,9 +208,10 @@ __global__ void __launch_bounds__(TC_THREADS, 2) topk_tc_candidates_kernel(const
     const uint32_t tile_bytes = TC_M * 128;          // one k-block of a 128-row operand: 16 KB
     unsigned char *sA = smem_raw;                    // [nkb][128 rows][128 B]
     unsigned char *sB = sA + (size_t)nkb * tile_bytes;            // [stages][nkb][128 rows][128 B]
-    float *ls = reinterpret_cast<float *>(sB + (size_t)TC_STAGES * nkb * tile_bytes);   // [cap][128]
-    int *li = reinterpret_cast<int *>(ls + (size_t)a.cap * TC_M);                         // [cap][128]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(li + (size_t)a.cap * TC_M);
+    float *ls = reinterpret_cast<float *>(sB + (size_t)TC_STAGES * nkb * tile_bytes);   // heap scores [kprime][128]
+    int *li = reinterpret_cast<int *>(ls + (size_t)a.kprime * TC_M);                      // heap ids    [kprime][128]
+    float *stage = reinterpret_cast<float *>(li + (size_t)a.kprime * TC_M);               // chunk staging [32][128]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(stage + 32 * TC_M);
     uint64_t *b_full = bars, *b_empty = bars + 2, *t_full = bars + 4, *t_empty = bars + 6, *a_full = bars + 8;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 9);
 
@@ -296,9 +305,9 @@ __global__ void __launch_bounds__(TC_THREADS, 2) topk_tc_candidates_kernel(const
         // ===== epilogue: thread = TMEM lane = one user row =====
         const int m = (warp & 3) * 32 + lane;
         const bool user_ok = row0 + m < a.n_eval;
-        const int K = a.kprime, cap = a.cap;
+        const int K = a.kprime;
         int cnt = 0;
-        float thr = -CUDART_INF_F;   // K'-th kept score at the last prune
+        float thr = -CUDART_INF_F;   // root of the heap once it is full
         int sc = 0, se = 0;
         if (user_ok && a.seen_indptr) {
             long long lo = a.seen_indptr[row0 + m], hi = a.seen_indptr[row0 + m + 1];
@@ -328,39 +337,28 @@ __global__ void __launch_bounds__(TC_THREADS, 2) topk_tc_candidates_kernel(const
                     next_seen = sc < se ? (long long)a.seen_items[sc] : (1LL << 62);
                 }
                 const long long room = item_hi - cbase;  // columns beyond the catalogue are padding
-                unsigned valid = user_ok ? ~seen : 0u;
-                if (room < 32) valid &= (room <= 0) ? 0u : ((1u << (int)room) - 1u);
+                unsigned pass = 0;
 #pragma unroll
-                for (int h = 0; h < 32 / TC_SUB; ++h) {   // the warp stays converged through this loop
-                    unsigned pass = 0;
+                for (int j = 0; j < 32; ++j) pass |= (unsigned)(v[j] > thr) << j;
+                pass &= user_ok ? ~seen : 0u;
+                if (room < 32) pass &= (room <= 0) ? 0u : ((1u << (int)room) - 1u);
+                if (!__any_sync(0xffffffffu, pass != 0)) continue;     // the warp stays converged here
 #pragma unroll
-                    for (int j = 0; j < TC_SUB; ++j) pass |= (unsigned)(v[h * TC_SUB + j] > thr) << j;
-                    pass &= valid >> (h * TC_SUB);
-                    if (!__any_sync(0xffffffffu, pass != 0)) continue;
-                    if (__any_sync(0xffffffffu, cnt + __popc(pass) > cap)) {
-                        const SelState st = tc_prune(ls, li, m, K, cnt, thr);
+                for (int j = 0; j < 32; ++j) stage[j * TC_M + m] = v[j];   // own column of the staging tile
+                while (pass) {                                          // lanes pop their own passing columns
+                    const int j = __ffs(pass) - 1;
+                    pass &= pass - 1;
+                    const float sj = stage[j * TC_M + m];
+                    if (sj > thr) {
+                        const SelState st = tc_heap_push(ls, li, m, K, cnt, sj, (int)(cbase + j));
                         cnt = st.cnt;
                         thr = st.thr;
-                        unsigned again = 0;
-#pragma unroll
-                        for (int j = 0; j < TC_SUB; ++j) again |= (unsigned)(v[h * TC_SUB + j] > thr) << j;
-                        pass &= again;
                     }
-#pragma unroll
-                    for (int j = 0; j < TC_SUB; ++j)
-                        if ((pass >> j) & 1u) {
-                            ls[cnt * TC_M + m] = v[h * TC_SUB + j];
-                            li[cnt * TC_M + m] = (int)(cbase + h * TC_SUB + j);
-                            ++cnt;
-                        }
                 }
+                __syncwarp();
             }
             tc_fence_before();
             mbar_arrive(&t_empty[acc]);
-        }
-        {
-            const SelState st = tc_prune(ls, li, m, K, cnt, thr);
-            cnt = st.cnt;
         }
         if (user_ok) {
             const size_t seg = (size_t)(row0 + m) * gridDim.y + blockIdx.y;
@@ -488,23 +486,12 @@ __global__ void max_row_norm_kernel(const float *x, long long ld, int n, int d, 
     if (lane == 0) atomicMax(reinterpret_cast<int *>(out), __float_as_int(best));   // non-negative floats order as ints
 }
 
-static size_t tc_smem_bytes(int d, int cap) {
+static size_t tc_smem_bytes(int d, int kprime) {
     const size_t tile = (size_t)TC_M * 128;
-    return (size_t)(d / TC_KB) * tile * (1 + TC_STAGES) + (size_t)cap * TC_M * 8 + 128;
+    return (size_t)(d / TC_KB) * tile * (1 + TC_STAGES) + (size_t)kprime * TC_M * 8 + (size_t)32 * TC_M * 4 + 128;
 }
 constexpr size_t kSmemTwoCtas = (228 * 1024) / 2 - 1024;   // per CTA when two share an SM (1 KB reserved each)
 constexpr size_t kSmemOneCta = 227 * 1024;
-// buffer capacity: the largest that still lets two CTAs share an SM, else K' + 2 * TC_SUB in one CTA per SM
-static int tc_capacity(int d, int kprime) {
-    if (d <= 0 || d % TC_KB != 0) return 0;
-    const size_t fixed = tc_smem_bytes(d, 0);
-    const size_t per = (size_t)TC_M * 8;
-    if (fixed + (size_t)(kprime + TC_SUB) * per <= kSmemTwoCtas) return (int)((kSmemTwoCtas - fixed) / per);
-    if (fixed + (size_t)(kprime + TC_SUB) * per > kSmemOneCta) return 0;
-    const int want = kprime + 2 * TC_SUB;
-    const int most = (int)((kSmemOneCta - fixed) / per);
-    return want < most ? want : most;
-}
 
 }  // namespace gr
 
@@ -519,7 +506,7 @@ using namespace gr;
 static int tc_splits(int64_t n_eval, int32_t d, int32_t kprime) {
     const long long tiles = (n_eval + TC_M - 1) / TC_M;
     if (tiles <= 0) return 1;
-    const int per_sm = (tc_smem_bytes(d, tc_capacity(d, kprime)) <= kSmemTwoCtas) ? 2 : 1;
+    const int per_sm = (tc_smem_bytes(d, kprime) <= kSmemTwoCtas) ? 2 : 1;
     const long long slots = (long long)sm_count() * per_sm;
     const int s_max = 128 / kprime > 0 ? 128 / kprime : 1;
     int best = 1;
@@ -539,7 +526,7 @@ extern "C" size_t gr_topk_tc_workspace_bytes(int64_t n_eval, int32_t kprime) {
 }
 
 extern "C" int gr_topk_tc_supported(int32_t d, int32_t kprime) {
-    return (d > 0 && d % TC_KB == 0 && kprime > 0 && kprime <= TC_KPRIME_MAX && tc_capacity(d, kprime) > 0) ? 1 : 0;
+    return (d > 0 && d % TC_KB == 0 && kprime > 0 && kprime <= TC_KPRIME_MAX && tc_smem_bytes(d, kprime) <= kSmemOneCta) ? 1 : 0;
 }
 
 extern "C" int gr_score_topk_tc(const float *user_emb, int64_t ldu, const float *item_emb, int64_t ldi, int32_t d,
@@ -574,11 +561,11 @@ extern "C" int gr_score_topk_tc(const float *user_emb, int64_t ldu, const float 
     TcArgs a;
     a.user_emb = user_emb; a.ldu = ldu; a.item_emb = item_emb; a.ldi = ldi; a.d = d;
     a.eval_users = eval_users; a.n_eval = (int)n_eval; a.item_lo = 0; a.item_hi = n_items;
-    a.seen_indptr = seen_indptr; a.seen_items = seen_items; a.kprime = kprime; a.cap = tc_capacity(d, kprime);
+    a.seen_indptr = seen_indptr; a.seen_items = seen_items; a.kprime = kprime;
     a.split_items = split_items;
     a.cand_scores = cand_scores; a.cand_ids = cand_ids; a.cand_cnt = cand_cnt;
     { const char *e = getenv("GR_TC_DEBUG"); a.debug = e ? atoi(e) : 0; }
-    const size_t smem = tc_smem_bytes(d, a.cap);
+    const size_t smem = tc_smem_bytes(d, kprime);
     GR_CUDA_CHECK(cudaFuncSetAttribute(topk_tc_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     topk_tc_candidates_kernel<<<dim3((unsigned)((n_eval + TC_M - 1) / TC_M), (unsigned)n_seg), TC_THREADS, smem, s>>>(a);
     GR_LAUNCH_CHECK();
