@@ -547,6 +547,7 @@ extern "C" int gr_score_topk_tc(const float *user_emb, int64_t ldu, const float 
     if (n_eval == 0) return GR_OK;
     const long long tiles_total = (n_items + TC_N - 1) / TC_N;
     int n_seg = tc_splits(n_eval, d, kprime);
+    { const char *e = getenv("GR_TC_SPLITS"); if (e && atoi(e) > 0) n_seg = atoi(e) < 128 / kprime ? atoi(e) : 128 / kprime; }
     if (n_seg > tiles_total / 8) n_seg = (int)(tiles_total / 8 > 0 ? tiles_total / 8 : 1);   // >= 1024 items per range
     const long long split_items = ((tiles_total + n_seg - 1) / n_seg) * TC_N;
     n_seg = (int)((n_items + split_items - 1) / split_items);

@@ -237,7 +237,8 @@ int gr_score_topk(const float *user_emb, int64_t ldu, const float *item_emb, int
  * All U x I scores are computed with tcgen05.mma.kind::tf32 (accumulators in TMEM); per user the
  * kprime best approximate scores of unseen items are kept; those candidates are re-scored with the
  * exact fmaf chain and ranked canonically; a row is PROVEN when a_min + eps*|u|*max|i| < (k-th exact
- * score) (a_min = kprime-th approximate score), i.e. no item outside the candidates can enter the
+ * score) (a_min = kprime-th approximate score; with several item ranges per user, the largest a_min of
+ * the ranges that rejected anything), i.e. no item outside the candidates can enter or tie into the
  * top-k.  Proven rows of topk_ids / topk_scores are bit-identical to gr_score_topk; flags[row] = 1
  * (and *n_flagged, device int32) marks rows the caller must re-rank with gr_score_topk.
  * gr_topk_tc_supported: d % 32 == 0, shared memory fits (d = 32 or 64), k <= kprime <= 64. */
