@@ -16,7 +16,8 @@ from .orthogonal_bundle import BundleConnectionLayer, GroupShuffleLayer, Orthogo
 from .dataset import InteractionDataset  # noqa: F401
 from .evaluator import Evaluator, full_rank_topk  # noqa: F401
 from .losses import BPRLoss, bpr_fused  # noqa: F401
-from .metrics import compute_metrics_from_topk  # noqa: F401
+from .metrics import compute_metrics_from_topk, topk_metrics_device  # noqa: F401
+from .optim import fused_clip_adam_step, fused_clip_adam_supported  # noqa: F401
 from .sampler import BprSampler  # noqa: F401
 from .trainer import Trainer  # noqa: F401
 

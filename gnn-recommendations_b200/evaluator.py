@@ -15,7 +15,7 @@ import numpy as np
 import torch
 
 from ._lib import check, lib, ptr, stream_ptr
-from .metrics import compute_metrics_from_topk
+from .metrics import compute_metrics_from_topk, topk_metrics_device
 
 
 def _pairs(data):
@@ -158,15 +158,19 @@ class Evaluator:
         with torch.no_grad():
             adj = dataset.get_torch_adjacency(normalized=True).to(self.device)
             user_emb, item_emb = model.get_all_embeddings(adj)
-            ground_truth = ground_truth_dict(test_data)
-            eval_users = sorted(ground_truth.keys())
-            if not eval_users:
+            test_pairs = _pairs(test_data)
+            eval_users = np.unique(test_pairs[0])           # == sorted(ground_truth.keys()) (evaluator.py:87)
+            if len(eval_users) == 0:
                 return {}
             max_k = max(self.k_values) if self.k_values else 10
             # seen = train ∪ valid (evaluator.py:126-156)
             ip, it = seen_csr(eval_users, user_emb.shape[0], _pairs(dataset.train_data), _pairs(dataset.valid_data))
-            topk = full_rank_topk(user_emb, item_emb, eval_users, ip, it, max_k).cpu()
-        return compute_metrics_from_topk(topk, eval_users, ground_truth, dataset.n_items, self.k_values)
+            topk = full_rank_topk(user_emb, item_emb, eval_users, ip, it, max_k)
+            gp, gi = seen_csr(eval_users, user_emb.shape[0], test_pairs)             # ground truth rows
+            if max_k > 64:
+                return compute_metrics_from_topk(topk.cpu(), eval_users.tolist(), ground_truth_dict(test_data),
+                                                 dataset.n_items, self.k_values)
+            return topk_metrics_device(topk, gp, gi, dataset.n_items, self.k_values)
 
     def evaluate_batch(self, model, users, items, adj_matrix) -> torch.Tensor:
         model.eval()

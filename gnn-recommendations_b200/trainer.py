@@ -23,8 +23,9 @@ import torch
 import torch.optim as optim
 
 from .evaluator import _pairs, full_rank_topk, ground_truth_dict, seen_csr
+from .optim import fused_clip_adam_step, fused_clip_adam_supported
 from .losses import BPRLoss, bpr_fused
-from .metrics import compute_metrics_from_topk
+from .metrics import compute_metrics_from_topk, topk_metrics_device
 from .sampler import BprSampler
 
 
@@ -53,6 +54,7 @@ class Trainer:
                                                                eta_min=lr * 0.01) if self.use_scheduler else None)
         self.loss_fn = BPRLoss()
         self.max_grad_norm = float(config.get("max_grad_norm", 1.0))
+        self.fused_optimizer = bool(config.get("fused_optimizer", True))   # gr_clip_adam_fused (same update)
         self.early_stopping = config.get("early_stopping", {})
         self.patience = int(self.early_stopping.get("patience", 20))
         self.min_delta = float(self.early_stopping.get("min_delta", 0.0001))
@@ -118,9 +120,12 @@ class Trainer:
                 loss = loss + self.model.get_regularization_loss()
             self.optimizer.zero_grad()
             loss.backward()
-            if self.max_grad_norm > 0:
-                torch.nn.utils.clip_grad_norm_(self.model.parameters(), self.max_grad_norm)
-            self.optimizer.step()
+            if self.fused_optimizer and fused_clip_adam_supported(self.optimizer):
+                fused_clip_adam_step(self.optimizer, self.max_grad_norm)      # clip + Adam in two passes
+            else:
+                if self.max_grad_norm > 0:
+                    torch.nn.utils.clip_grad_norm_(self.model.parameters(), self.max_grad_norm)
+                self.optimizer.step()
             total += loss.detach().double()
             n_batches += 1
         return float(total.item()) / n_batches if n_batches > 0 else 0.0
@@ -150,16 +155,19 @@ class Trainer:
                 import pandas as pd
 
                 valid_data = pd.read_csv(valid_file, sep="\t", header=None, names=["userId", "itemId"])
-            ground_truth = ground_truth_dict(valid_data)
-            eval_users = sorted(ground_truth.keys())
-            if not eval_users:
+            valid_pairs = _pairs(valid_data)
+            eval_users = np.unique(valid_pairs[0])          # == sorted(ground_truth.keys()) (trainer.py:318)
+            if len(eval_users) == 0:
                 return {}
             k_values = self._parse_k_values(self.validation_metrics)
             max_k = max(k_values) if k_values else 10
             ip, it = seen_csr(eval_users, user_emb.shape[0], self._train_arrays())   # train only (:324)
-            topk = full_rank_topk(user_emb, item_emb, eval_users, ip, it, max_k).cpu()
-        return compute_metrics_from_topk(topk, eval_users, ground_truth, self.dataset.n_items,
-                                         k_values if k_values else [10])
+            topk = full_rank_topk(user_emb, item_emb, eval_users, ip, it, max_k)
+            gp, gi = seen_csr(eval_users, user_emb.shape[0], valid_pairs)           # ground truth rows
+            if max_k > 64:                                   # longer lists than the device reduction handles
+                return compute_metrics_from_topk(topk.cpu(), eval_users.tolist(), ground_truth_dict(valid_data),
+                                                 self.dataset.n_items, k_values if k_values else [10])
+            return topk_metrics_device(topk, gp, gi, self.dataset.n_items, k_values if k_values else [10])
 
     # ------------------------------------------------------------------ warm start / export
     def _maybe_warm_start_embeddings(self):

@@ -207,6 +207,23 @@ int gr_bpr_fused(const float *emb, int64_t ld, int64_t n_users, int64_t n_items,
                  const int64_t *pos, const int64_t *neg, int64_t batch, int32_t d, float grad_scale, float *grad,
                  int64_t ldg, float *loss, void *workspace, size_t workspace_bytes, void *stream);
 
+/* Replaces `torch.nn.utils.clip_grad_norm_(model.parameters(), max_grad_norm)` + `optimizer.step()`
+ * of `optim.Adam(lr, weight_decay)` (src/training/trainer.py:273-276, 81-85) for a list of dense fp32
+ * tensors: one pass for the total gradient norm (deterministic), one pass that applies
+ *   g = clip*g + wd*p;  m += (g-m)(1-beta1);  v = v*beta2 + (1-beta2) g*g;
+ *   p -= step_size * m / (sqrt(v)/bias_correction2_sqrt + eps)
+ * with clip = min(1, max_norm/(norm+1e-6)) (max_norm <= 0: no clipping).  step_size = lr/(1-beta1^t) and
+ * bias_correction2_sqrt = sqrt(1-beta2^t) are computed by the caller in double, as torch does; the
+ * scalars are doubles and rounded to fp32 once inside (1-beta in double first), like torch's.
+ * The *_host arguments are host arrays of n_tensors device pointers / element counts (16-byte aligned
+ * tensors).  norm_out (device float, optional) receives the total norm.  Gradients are not modified. */
+size_t gr_clip_adam_workspace_bytes(const int64_t *numel_host, int32_t n_tensors);
+int gr_clip_adam_fused(void *const *params_host, const void *const *grads_host, void *const *exp_avg_host,
+                       void *const *exp_avg_sq_host, const int64_t *numel_host, int32_t n_tensors, double max_norm,
+                       double step_size, double beta1, double beta2, double eps, double weight_decay,
+                       double bias_correction2_sqrt, float *norm_out, void *workspace, size_t workspace_bytes,
+                       void *stream);
+
 /* ------------------------------------------------------------------------------------------
  * Full-ranking evaluation
  * ------------------------------------------------------------------------------------------ */
@@ -248,6 +265,23 @@ int gr_score_topk_tc(const float *user_emb, int64_t ldu, const float *item_emb, 
                      const int64_t *eval_users, int64_t n_eval, int64_t n_items, const int64_t *seen_indptr,
                      const int32_t *seen_items, int32_t k, int32_t kprime, int64_t *topk_ids, float *topk_scores,
                      int32_t *flags, int32_t *n_flagged, void *workspace, size_t workspace_bytes, void *stream);
+
+/* Replaces the per-user python loops of compute_metrics_from_topk (src/training/metrics.py:355-432).
+ * topk_ids [n_eval][kmax] (kmax <= 64, -1 = padding); ground truth as CSR over the SAME rows
+ * (gt_indptr [n_eval+1], gt_items sorted and unique per row, empty row = user without ground truth,
+ * skipped as metrics.py:390-394 does); k_values_host: nk <= 8 cut-offs (each clamped to kmax);
+ * disc [kmax] = 1/log2(rank+2) and idcg [kmax+1] = running ideal DCG, device float64 tables built by
+ * the caller with numpy so that per-user values carry the reference's bits.
+ * out_sums  (device, nk*3+1 doubles): per k sums of recall, ndcg, precision over users with ground
+ *           truth (fixed-order reduction), then the number of such users.
+ * out_counts (device, nk*3 int64): per k the number of distinct recommended ids, the total number of
+ *           recommendations, and sum_i (i+1)*c_(i) over the ascending item counts (Gini numerator,
+ *           metrics.py:415-430) - all exact integers. */
+size_t gr_topk_metrics_workspace_bytes(int64_t n_eval, int64_t n_items, int32_t nk);
+int gr_topk_metrics(const int64_t *topk_ids, int64_t n_eval, int32_t kmax, const int64_t *gt_indptr,
+                    const int32_t *gt_items, int64_t n_items, const int32_t *k_values_host, int32_t nk,
+                    const double *disc, const double *idcg, double *out_sums, int64_t *out_counts, void *workspace,
+                    size_t workspace_bytes, void *stream);
 
 #ifdef __cplusplus
 }

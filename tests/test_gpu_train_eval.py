@@ -159,6 +159,13 @@ def test_topk_c1_shape_vs_reference(c1gold, c1split):
     met = g.compute_metrics_from_topk(ids, eu, gt, ni, [10, 20])
     for k in ("recall@20", "ndcg@20", "recall@10", "ndcg@10"):
         assert abs(met[k] - float(c1gold[f"metrics/{k}"])) <= 1e-12, k
+    gp, gi = seen_csr(eu, nu, c1split["test"])
+    dmet = g.topk_metrics_device(ids.to(DEV), gp, gi, ni, [10, 20])
+    assert set(dmet) == set(met)
+    for k in met:
+        assert abs(dmet[k] - met[k]) <= 1e-12, k
+    for k in ("recall@20", "ndcg@20", "recall@10", "ndcg@10"):
+        assert abs(dmet[k] - float(c1gold[f"metrics/{k}"])) <= 1e-12, k
 
 
 # ----------------------------------------------------------------------------- Trainer / Evaluator
@@ -241,3 +248,68 @@ def test_topk_tensor_core_c1_shape(c1gold, c1split):
     ids = g.full_rank_topk(ue, ie, eu, ip, it, 20, tensor_cores=True, stats=stats).cpu()
     assert np.array_equal(ids.numpy(), c1gold["topk20_canonical"].astype(np.int64))
     print("C1 tensor-core path: rows re-ranked exactly:", stats["rows_reranked_exactly"], "of", stats["rows"])
+
+
+# ----------------------------------------------------------------------------- on-device metrics / fused optimizer
+@pytest.mark.parametrize("nu,ni,kmax,ks", [(500, 300, 20, [5, 10, 20]), (257, 1000, 50, [10, 20, 50]), (64, 40, 64, [1, 64, 100])])
+def test_topk_metrics_device_matches_reference_loops(nu, ni, kmax, ks):
+    """gr_topk_metrics vs the reference's python loops (oracle restatement of metrics.py:355-432):
+    users without ground truth, duplicate ground-truth entries, k > list length."""
+    rng = np.random.default_rng(nu + kmax)
+    topk = np.stack([rng.permutation(ni)[:kmax] for _ in range(nu)]).astype(np.int64)
+    users = np.sort(rng.choice(10 * nu, nu, replace=False))
+    gt = {}
+    for r, u in enumerate(users.tolist()):
+        if r % 7 == 3:
+            continue                                            # no ground truth: skipped by the reference
+        n_rel = int(rng.integers(1, 2 * kmax))
+        rel = rng.choice(ni, min(n_rel, ni), replace=False).tolist()
+        if r % 5 == 0:
+            rel += topk[r, :3].tolist() + rel[:2]               # guaranteed hits + duplicates
+        gt[u] = rel
+    want = po.metrics_from_topk(topk, users.tolist(), gt, ni, ks)
+    indptr, items = [0], []
+    for u in users.tolist():
+        items += sorted(set(gt.get(u, ())))
+        indptr.append(len(items))
+    got = g.topk_metrics_device(torch.from_numpy(topk).to(DEV), np.asarray(indptr), np.asarray(items, dtype=np.int32), ni, ks)
+    assert set(got) == set(want)
+    for k, v in want.items():
+        assert abs(got[k] - v) <= 1e-13, (k, got[k], v)
+
+
+@pytest.mark.parametrize("max_norm,gscale", [(1.0, 10.0), (1.0, 1e-3), (0.0, 1.0)])
+def test_fused_clip_adam_matches_torch(max_norm, gscale):
+    """gr_clip_adam_fused vs clip_grad_norm_ + optim.Adam on CPU (what trainer.py:273-276 runs)."""
+    from gnn_recommendations_b200.optim import fused_clip_adam_step, fused_clip_adam_supported
+    shapes = [(1000, 64), (37, 5), (3,), (4096,), (129, 33)]
+    gen = torch.Generator().manual_seed(7)
+    ref = [torch.nn.Parameter(torch.randn(*s, generator=gen) * 0.1) for s in shapes]
+    dev = [torch.nn.Parameter(p.detach().clone().to(DEV)) for p in ref]
+    o_ref = torch.optim.Adam(ref, lr=1e-3, weight_decay=1e-4)
+    o_dev = torch.optim.Adam(dev, lr=1e-3, weight_decay=1e-4)
+    for step in range(4):
+        for p, q in zip(ref, dev):
+            gr = torch.randn(p.shape, generator=gen) * gscale
+            p.grad = gr.clone()
+            q.grad = gr.clone().to(DEV)
+        want_norm = torch.nn.utils.clip_grad_norm_(ref, max_norm) if max_norm > 0 else None
+        o_ref.step()
+        assert fused_clip_adam_supported(o_dev)
+        norm = fused_clip_adam_step(o_dev, max_norm)
+        if want_norm is not None:
+            assert abs(float(norm) - float(want_norm)) <= 1e-6 * float(want_norm)
+        for p, q in zip(ref, dev):
+            np.testing.assert_allclose(q.detach().cpu().numpy(), p.detach().numpy(), rtol=2e-6, atol=1e-8)
+            # a 1-ulp difference in the clip coefficient moves every g by 1 ulp; m cancels, so bound absolutely
+            for key in ("exp_avg", "exp_avg_sq"):
+                want = o_ref.state[p][key].numpy()
+                np.testing.assert_allclose(o_dev.state[q][key].cpu().numpy(), want, rtol=2e-6, atol=1e-6 * float(np.abs(want).max()))
+        assert float(o_dev.state[dev[0]]["step"]) == step + 1
+    # the state layout is torch's own: a stock step continues from it
+    sd = o_dev.state_dict()
+    o2 = torch.optim.Adam(dev, lr=1e-3, weight_decay=1e-4)
+    o2.load_state_dict(sd)
+    for q in dev:
+        q.grad = torch.zeros_like(q)
+    o2.step()
