@@ -13,7 +13,7 @@ from .lightgcn import LightGCN, lightgcn_propagate  # noqa: F401
 from .ngcf import NGCF, NGCFLayer  # noqa: F401
 from .gat import GAT, GATLayer  # noqa: F401
 from .orthogonal_bundle import BundleConnectionLayer, GroupShuffleLayer, OrthogonalBundleGNN  # noqa: F401
-from .dataset import InteractionDataset  # noqa: F401
+from .dataset import InteractionDataset, temporal_split_device  # noqa: F401
 from .evaluator import Evaluator, full_rank_topk  # noqa: F401
 from .losses import BPRLoss, bpr_fused  # noqa: F401
 from .metrics import compute_metrics_from_topk, topk_metrics_device  # noqa: F401

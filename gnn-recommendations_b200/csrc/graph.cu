@@ -1,6 +1,8 @@
 // Graph builder: COO -> CSR, (user,item) pairs -> symmetric-normalised CSR, row schedule.
 // Integer work, HBM-bound; everything is bit-exact with scipy's canonical CSR
 // (src/data/graph_builder.py:16-144 of the reference).
+#include <initializer_list>
+
 #include "gr_common.cuh"
 
 namespace gr {
@@ -519,6 +521,132 @@ extern "C" int gr_csr_normalize(const int32_t *indptr, const int32_t *indices, c
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     normalize_kernel<<<grid_for(nnz, 256), 256, 0, s>>>(indptr, indices, mult, deg, lut, lut_len, n_rows, nnz, mode,
                                                         vals, status);
+    GR_LAUNCH_CHECK();
+    return GR_OK;
+}
+
+// =============================================================================================
+// Per-user temporal split (src/data/dataset.py:327-357)
+// =============================================================================================
+namespace gr {
+
+// key = user << ts_bits | (timestamp - ts_min); payload = original row.  status |= 1 on a range violation.
+__global__ void split_keys_kernel(const int64_t *user, const int64_t *ts, long long n, long long n_users, long long ts_min,
+                                  long long ts_max, int ts_bits, uint64_t *keys, uint32_t *pay, int *status) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const long long u = user[i], t = ts[i];
+    if (u < 0 || u >= n_users || t < ts_min || t > ts_max) {
+        atomicOr(status, 1);
+        keys[i] = ~0ULL;
+        pay[i] = (uint32_t)i;
+        return;
+    }
+    keys[i] = ((uint64_t)u << ts_bits) | (uint64_t)(t - ts_min);
+    pay[i] = (uint32_t)i;
+}
+
+// label of sorted position j: 2 = test (user's last row, needs >= 2 rows), 1 = valid (second-last row,
+// needs >= 3 rows), 0 = train (dataset.py:340-352).  One flag array per label for the scans.
+__global__ void split_label_kernel(const uint64_t *keys, long long n, int ts_bits, uint32_t *f_train, uint32_t *f_valid,
+                                   uint32_t *f_test) {
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const uint64_t u = keys[j] >> ts_bits;
+    const bool has_prev = j > 0 && (keys[j - 1] >> ts_bits) == u;
+    const bool next_same = j + 1 < n && (keys[j + 1] >> ts_bits) == u;
+    const bool next2_same = j + 2 < n && (keys[j + 2] >> ts_bits) == u;
+    const bool is_last = !next_same;
+    const bool is_second_last = next_same && !next2_same;
+    const bool test = is_last && has_prev;
+    const bool valid = is_second_last && has_prev;
+    f_test[j] = test;
+    f_valid[j] = valid;
+    f_train[j] = !(test || valid);
+}
+
+__global__ void split_emit_kernel(const uint64_t *keys, const uint32_t *pay, const int64_t *item, long long n, int ts_bits,
+                                  const uint32_t *p_train, const uint32_t *p_valid, const uint32_t *p_test,
+                                  int64_t *train_u, int64_t *train_i, int64_t *valid_u, int64_t *valid_i,
+                                  int64_t *test_u, int64_t *test_i, int64_t *counts) {
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const uint64_t u = keys[j] >> ts_bits;
+    const bool has_prev = j > 0 && (keys[j - 1] >> ts_bits) == u;
+    const bool next_same = j + 1 < n && (keys[j + 1] >> ts_bits) == u;
+    const bool next2_same = j + 2 < n && (keys[j + 2] >> ts_bits) == u;
+    const bool test = !next_same && has_prev;
+    const bool valid = next_same && !next2_same && has_prev;
+    const int64_t it = item[pay[j]];
+    if (test) {
+        test_u[p_test[j]] = (int64_t)u;
+        test_i[p_test[j]] = it;
+    } else if (valid) {
+        valid_u[p_valid[j]] = (int64_t)u;
+        valid_i[p_valid[j]] = it;
+    } else {
+        train_u[p_train[j]] = (int64_t)u;
+        train_i[p_train[j]] = it;
+    }
+    if (j == n - 1) {   // exclusive prefix + own flag = totals
+        counts[0] = (int64_t)p_train[j] + (!(test || valid));
+        counts[1] = (int64_t)p_valid[j] + valid;
+        counts[2] = (int64_t)p_test[j] + test;
+    }
+}
+
+}  // namespace gr
+
+extern "C" size_t gr_temporal_split_workspace_bytes(int64_t n) {
+    if (n < 0) return 0;
+    return 2 * align256((size_t)n * 8) + 2 * align256((size_t)n * 4) + 3 * align256((size_t)n * 4) +
+           align256(radix_sort_workspace_bytes(n)) + align256(scan_workspace_bytes(n)) + 512;
+}
+
+extern "C" int gr_temporal_split(const int64_t *user, const int64_t *item, const int64_t *timestamp, int64_t n,
+                                 int64_t n_users, int64_t ts_min, int64_t ts_max, int64_t *train_u, int64_t *train_i,
+                                 int64_t *valid_u, int64_t *valid_i, int64_t *test_u, int64_t *test_i, int64_t *counts,
+                                 int32_t *status, void *workspace, size_t workspace_bytes, void *stream) {
+    if (!user || !item || !timestamp || !train_u || !train_i || !valid_u || !valid_i || !test_u || !test_i || !counts ||
+        !status || !workspace)
+        return GR_ERR_INVALID;
+    if (n < 0 || n_users <= 0 || ts_max < ts_min) return GR_ERR_INVALID;
+    if (n >= (1LL << 32)) return GR_ERR_OVERFLOW;
+    if (workspace_bytes < gr_temporal_split_workspace_bytes(n)) return GR_ERR_WORKSPACE;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    GR_CUDA_CHECK(cudaMemsetAsync(status, 0, 4, s));
+    GR_CUDA_CHECK(cudaMemsetAsync(counts, 0, 3 * 8, s));
+    if (n == 0) return GR_OK;
+    const int ts_bits = bits_for((uint64_t)(ts_max - ts_min));
+    const int user_bits = bits_for((uint64_t)(n_users - 1));
+    if (ts_bits + user_bits > 63) return GR_ERR_OVERFLOW;     // ~0 stays reserved for rejected rows
+    char *w = static_cast<char *>(workspace);
+    uint64_t *ka = reinterpret_cast<uint64_t *>(w); w += align256((size_t)n * 8);
+    uint64_t *kb = reinterpret_cast<uint64_t *>(w); w += align256((size_t)n * 8);
+    uint32_t *pa = reinterpret_cast<uint32_t *>(w); w += align256((size_t)n * 4);
+    uint32_t *pb = reinterpret_cast<uint32_t *>(w); w += align256((size_t)n * 4);
+    uint32_t *f0 = reinterpret_cast<uint32_t *>(w); w += align256((size_t)n * 4);
+    uint32_t *f1 = reinterpret_cast<uint32_t *>(w); w += align256((size_t)n * 4);
+    uint32_t *f2 = reinterpret_cast<uint32_t *>(w); w += align256((size_t)n * 4);
+    void *sort_ws = w; w += align256(radix_sort_workspace_bytes(n));
+    void *scan_ws = w;
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    split_keys_kernel<<<grid, 256, 0, s>>>(user, timestamp, n, n_users, ts_min, ts_max, ts_bits, ka, pa, status);
+    GR_LAUNCH_CHECK();
+    bool in_a = true;
+    int rc = radix_sort_u64(ka, kb, pa, pb, n, 0, ts_bits + user_bits, sort_ws, align256(radix_sort_workspace_bytes(n)),
+                            &in_a, s);
+    if (rc != GR_OK) return rc;
+    const uint64_t *keys = in_a ? ka : kb;
+    const uint32_t *pay = in_a ? pa : pb;
+    split_label_kernel<<<grid, 256, 0, s>>>(keys, n, ts_bits, f0, f1, f2);
+    GR_LAUNCH_CHECK();
+    for (uint32_t *f : {f0, f1, f2}) {
+        rc = exclusive_scan_u32(f, n, scan_ws, s);
+        if (rc != GR_OK) return rc;
+    }
+    split_emit_kernel<<<grid, 256, 0, s>>>(keys, pay, item, n, ts_bits, f0, f1, f2, train_u, train_i, valid_u, valid_i,
+                                           test_u, test_i, counts);
     GR_LAUNCH_CHECK();
     return GR_OK;
 }

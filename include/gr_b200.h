@@ -207,6 +207,20 @@ int gr_bpr_fused(const float *emb, int64_t ld, int64_t n_users, int64_t n_items,
                  const int64_t *pos, const int64_t *neg, int64_t batch, int32_t d, float grad_scale, float *grad,
                  int64_t ldg, float *loss, void *workspace, size_t workspace_bytes, void *stream);
 
+/* Replaces the per-user temporal split (src/data/dataset.py:327-357: `sort_values(['userId','timestamp'])`,
+ * then per user the last row -> test (users with >= 2 rows), the second-last -> valid (users with
+ * >= 3 rows), the rest -> train).  user / item / timestamp: [n] int64 device arrays; ts_min / ts_max:
+ * the timestamp range (the caller's min/max; rows outside set *status bit 0).  Rows are ordered by one
+ * stable radix sort of (user, timestamp - ts_min) keys, so equal timestamps keep their input order as
+ * pandas' lexsort does.  Outputs (caller-allocated, [n] for train, [min(n, n_users)] for valid/test):
+ * train pairs in (user, timestamp) order - the order Trainer.train_epoch indexes (trainer.py:223-230) -
+ * valid / test pairs in user order; counts (device int64[3]) = sizes of the three sets. */
+size_t gr_temporal_split_workspace_bytes(int64_t n);
+int gr_temporal_split(const int64_t *user, const int64_t *item, const int64_t *timestamp, int64_t n, int64_t n_users,
+                      int64_t ts_min, int64_t ts_max, int64_t *train_u, int64_t *train_i, int64_t *valid_u,
+                      int64_t *valid_i, int64_t *test_u, int64_t *test_i, int64_t *counts, int32_t *status,
+                      void *workspace, size_t workspace_bytes, void *stream);
+
 /* Replaces `torch.nn.utils.clip_grad_norm_(model.parameters(), max_grad_norm)` + `optimizer.step()`
  * of `optim.Adam(lr, weight_decay)` (src/training/trainer.py:273-276, 81-85) for a list of dense fp32
  * tensors: one pass for the total gradient norm (deterministic), one pass that applies

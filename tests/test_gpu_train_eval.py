@@ -313,3 +313,75 @@ def test_fused_clip_adam_matches_torch(max_norm, gscale):
     for q in dev:
         q.grad = torch.zeros_like(q)
     o2.step()
+
+
+# ----------------------------------------------------------------------------- device temporal split / interaction store
+def _sha(a):
+    import hashlib
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def test_temporal_split_device_c1_matches_reference_hashes(c1gold, c1split):
+    """gr_temporal_split at the ML-1M shape: train pairs hash-equal to the reference's split()
+    (dataset.py:327-357; hashes generated from the unmodified reference, tests/golden/make_golden.py)."""
+    from gnn_recommendations_b200.dataset import temporal_split_device
+    u, i, ts = c1split["all"]
+    sp = temporal_split_device(u, i, ts, c1split["n_users"], device=DEV)
+    tu, ti = (x.cpu().numpy() for x in sp["train"])
+    assert len(tu) == int(c1gold["n_train"])
+    assert _sha(tu) == str(c1gold["sha_train_u"]) and _sha(ti) == str(c1gold["sha_train_i"])
+    for part in ("valid", "test"):
+        for a, b in zip(sp[part], c1split[part]):
+            assert np.array_equal(a.cpu().numpy(), b)
+
+
+def test_temporal_split_device_edge_cases():
+    """users with 1, 2 and 3+ rows, missing users, equal timestamps (stable), negative timestamps."""
+    from gnn_recommendations_b200.dataset import temporal_split_device
+    from gnn_recommendations_b200.synthetic import temporal_split
+    rng = np.random.default_rng(5)
+    n_users = 400
+    rows = []
+    for u in range(n_users):
+        k = [0, 1, 2, 3, 7][u % 5] if u % 11 else 40
+        rows += [u] * k
+    user = np.asarray(rows, dtype=np.int64)
+    perm = rng.permutation(len(user))
+    user = user[perm]
+    item = rng.integers(0, 1000, len(user)).astype(np.int64)
+    ts = rng.integers(-50, 50, len(user)).astype(np.int64)          # many ties inside a user
+    want = temporal_split(user, item, ts)                            # np.lexsort: stable, as pandas
+    got = temporal_split_device(user, item, ts, n_users, device=DEV)
+    for part in ("train", "valid", "test"):
+        for a, b in zip(got[part], want[part]):
+            assert np.array_equal(a.cpu().numpy(), b), part
+    with pytest.raises(ValueError):
+        temporal_split_device(np.array([0, n_users]), np.array([1, 2]), np.array([0, 1]), n_users, device=DEV)
+    empty = temporal_split_device(np.zeros(0, np.int64), np.zeros(0, np.int64), np.zeros(0, np.int64), 5, device=DEV)
+    assert all(len(a) == 0 for pair in empty.values() for a in pair)
+
+
+def test_interaction_store_round_trip(tiny, tmp_path):
+    """save_processed / load_processed: the reference's on-disk contract (dataset.py:366-394, 461-466,
+    493-522): TSV `userId<TAB>itemId` without header, stats.json keys, scipy npz graphs."""
+    import json
+    import scipy.sparse as sp
+    ds = dataset_from(tiny)
+    ds.processed_data_path = tmp_path / "data" / "processed" / "tiny"
+    ds.graphs_path = tmp_path / "data" / "graphs" / "tiny"
+    ds.save_processed()
+    first = (ds.processed_data_path / "train.txt").read_text().splitlines()[0]
+    assert first == f"{int(tiny['train_u'][0])}\t{int(tiny['train_i'][0])}"
+    stats = json.loads((ds.processed_data_path / "stats.json").read_text())
+    assert stats["n_users"] == int(tiny["n_users"]) and stats["train_size"] == len(tiny["train_u"])
+    assert stats["valid_size"] == len(tiny["valid_u"]) and stats["test_size"] == len(tiny["test_u"])
+    back = g.InteractionDataset.load_processed("tiny", root_dir=str(tmp_path), device=DEV)
+    for name in ("train", "valid", "test"):
+        assert getattr(back, f"{name}_data").equals(getattr(ds, f"{name}_data"))
+    assert back.n_users == ds.n_users and back.n_items == ds.n_items
+    norm = sp.load_npz(str(ds.graphs_path / "norm_adj_matrix.npz"))
+    assert norm.format == "coo" and norm.dtype == np.float32 and norm.shape == (ds.n_users + ds.n_items,) * 2
+    assert np.array_equal(norm.row, tiny["adj_row"]) and np.array_equal(norm.col, tiny["adj_col"])
+    assert np.array_equal(norm.data, tiny["adj_val"])
+    raw = sp.load_npz(str(ds.graphs_path / "adj_matrix.npz"))
+    assert raw.nnz == norm.nnz and np.all(raw.data == 1.0)
