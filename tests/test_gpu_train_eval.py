@@ -385,3 +385,24 @@ def test_interaction_store_round_trip(tiny, tmp_path):
     assert np.array_equal(norm.data, tiny["adj_val"])
     raw = sp.load_npz(str(ds.graphs_path / "adj_matrix.npz"))
     assert raw.nnz == norm.nnz and np.all(raw.data == 1.0)
+
+
+def test_ultragcn_under_trainer(tiny, tmp_path):
+    """UltraGCN has no propagation (ultragcn.py:75-91): under the Trainer it is the BPR step + top-K on
+    the raw tables, i.e. exactly LightGCN with zero layers — same seed, same epoch, same weights."""
+    ds = dataset_from(tiny)
+    nu, ni = int(tiny["n_users"]), int(tiny["n_items"])
+    out = []
+    for cls, kw in ((g.UltraGCN, {}), (g.LightGCN, {"n_layers": 0})):
+        torch.manual_seed(42)
+        m = cls(nu, ni, embedding_dim=64, init_scale=0.1, **kw)
+        tr = g.Trainer(m, ds, dict(CFG, checkpoint_dir=str(tmp_path / cls.__name__)), device=torch.device(DEV))
+        torch.manual_seed(123)
+        loss = tr.train_epoch()
+        assert np.isfinite(loss)
+        out.append((loss, m.user_embedding.weight.detach().cpu().numpy().copy(), tr.validate()))
+    # the BPR gradient scatter uses red.global.add (order not fixed), so equal up to a few ulps
+    assert abs(out[0][0] - out[1][0]) <= 1e-7
+    np.testing.assert_allclose(out[0][1], out[1][1], rtol=1e-5, atol=1e-7)
+    assert set(out[0][2]) == set(out[1][2])
+    assert not np.array_equal(out[0][1], tiny["lightgcn/user_embedding.weight"])      # it trained

@@ -119,3 +119,30 @@ def test_dataset_boundary_attributes(tiny):
                               (tiny["test_u"], tiny["test_i"]), int(tiny["n_users"]), int(tiny["n_items"]))
     assert list(ds.train_data.columns) == ["userId", "itemId"] and len(ds.train_data) == len(tiny["train_u"])
     assert ds.n_users == 300 and ds.n_items == 200
+
+
+# ----------------------------------------------------------------------------- UltraGCN (no propagation)
+def test_ultragcn_matches_reference_golden():
+    """Same-seed parameters, predict, compute_loss (BPR + constraint + L2) and its gradients vs the
+    unmodified reference (tests/golden/make_golden_ultragcn.py; ultragcn.py:21-247)."""
+    import os
+    z = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "ultragcn.npz")))
+    nu, ni, d = int(z["n_users"]), int(z["n_items"]), int(z["d"])
+    torch.manual_seed(42)
+    m = g.UltraGCN(nu, ni, embedding_dim=d, lambda_1=0.7, lambda_2=1.3, gamma=1e-3, init_scale=0.1)
+    assert np.array_equal(m.user_embedding.weight.detach().numpy(), z["user_w"])
+    assert np.array_equal(m.item_embedding.weight.detach().numpy(), z["item_w"])
+    users, pos, neg = (torch.from_numpy(z[k]) for k in ("users", "pos", "neg"))
+    np.testing.assert_allclose(m.predict(users, pos).detach().numpy(), z["predict"], rtol=1e-6, atol=1e-8)
+    ue, ie = m.get_all_embeddings(None)
+    assert ue is m.user_embedding.weight and ie is m.item_embedding.weight
+    adj = torch.from_numpy(z["adj"])
+    for tag, a in (("noadj", None), ("dense", adj), ("sparse", adj.to_sparse())):
+        m.zero_grad()
+        total, parts = m.compute_loss(users, pos, neg, a)
+        total.backward()
+        assert abs(total.item() - float(z[f"{tag}/total"])) <= 1e-6 * abs(float(z[f"{tag}/total"])), tag
+        assert abs(parts["constraint_loss"] - float(z[f"{tag}/constraint"])) <= 1e-6 * max(1e-3, abs(float(z[f"{tag}/constraint"])))
+        np.testing.assert_allclose(m.user_embedding.weight.grad.numpy(), z[f"{tag}/grad_user"], rtol=1e-5, atol=1e-7)
+        np.testing.assert_allclose(m.item_embedding.weight.grad.numpy(), z[f"{tag}/grad_item"], rtol=1e-5, atol=1e-7)
+    assert g.MODEL_REGISTRY["ultragcn"] is g.UltraGCN
