@@ -360,16 +360,244 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) spmm_stream_rows(const Spmm
 // ---------------------------------------------------------------------------------------------
 // long rows: one CTA per row, warp-specialised cp.async pipeline through shared memory
 //
-//   4 producer warps  : per 64-entry chunk, copy the 64 gathered x rows (cp.async 16 B) into a
-//                       ring stage; producer 0 also streams the row's (col,val) arrays into a
-//                       second small ring 16 chunks ahead (cp.async 4 B), so gathers never wait
-//                       on the index stream.
-//   d/32 consumer warps: one feature per lane, run the fmaf chain out of shared memory
-//                       (conflict-free 128 B reads, values broadcast as float4).
-//   one __syncthreads per chunk hands a landed stage to the consumers and a drained one back.
+//   4 producer warps  : warp p owns chunks p, p+4, ...: it copies the chunk's 32 gathered x rows
+//                       (cp.async 16 B) and 32 values into a ring stage.  Column indices are read
+//                       straight from global memory (one coalesced load per chunk, four turns ahead)
+//                       and broadcast by shuffle, so a gather never waits on them.
+//                       `cp.async.mbarrier.arrive.noinc` publishes the stage on full[stage] when
+//                       the copies land; a stage is reused once the consumers released empty[stage].
+//   d/32 consumer warps: one feature per lane.  They wait on full[stage], pull the chunk into
+//                       registers, release the stage at once, and run the dependent fmaf chain of
+//                       the PREVIOUS chunk between those loads — no CTA-wide barrier in steady
+//                       state, so producers run ahead by the ring depth and the chain (4 cycles per
+//                       entry) is the only serial resource.  The first version met at one
+//                       __syncthreads per chunk with the producers' issue code in between:
+//                       13 cycles per entry at d = 64 (ncu: sm__cycles_active.max 371 K for a
+//                       27 950-entry row).
 // ---------------------------------------------------------------------------------------------
 template <int D>
 struct LongCfg {
+    static constexpr int CONS = D / 32;
+    static constexpr int PROD = 4;
+    static constexpr int THREADS = (CONS + PROD) * 32;
+    static constexpr int CHUNK = 32;     // two register sets of 32 gathered values + 32 coefficients per lane
+    static constexpr int STAGE_BYTES = CHUNK * D * 4 + CHUNK * 4;   // gathered rows + values
+    static constexpr int STAGES = D <= 64 ? 16 : (D == 128 ? 12 : 6);   // 128-197 KB of gathers in flight
+    static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 2 * STAGES * 8 + 16;   // + barriers + ticket
+};
+
+// ticket / exit counters of the persistent long-row kernel, re-armed by the last CTA of each launch
+// (one gr_spmm_csr_f32 in flight per device at a time)
+__device__ unsigned int g_long_ticket = 0, g_long_done = 0;
+
+__device__ __forceinline__ unsigned lr_smem(const void *p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void lr_mbar_init(uint64_t *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(lr_smem(bar)), "r"(count));
+}
+__device__ __forceinline__ void lr_mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(lr_smem(bar)) : "memory");
+}
+// arrives on `bar` once all cp.async issued so far by this thread have landed (does not add to the
+// expected count: the barrier is initialised with one arrival per producer thread)
+__device__ __forceinline__ void lr_cp_async_arrive(uint64_t *bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(lr_smem(bar)) : "memory");
+}
+__device__ __forceinline__ void lr_mbar_wait(uint64_t *bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "LR_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra LR_DONE;\n\t"
+        "bra LR_WAIT;\n\t"
+        "LR_DONE:\n\t}" ::"r"(lr_smem(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+template <int D, int PEERS>
+__global__ void __launch_bounds__(LongCfg<D>::THREADS, 1) spmm_long_rows(const SpmmArgs a) {
+    using L = LongCfg<D>;
+    constexpr int STAGES = L::STAGES, CH = L::CHUNK, F4 = D / 4, CONS = L::CONS, PROD = L::PROD;
+    constexpr int ITEMS = (CH * F4) / 32;    // 16-byte copies per producer lane per chunk
+    static_assert(CH == 32 && ITEMS >= 1, "one column index per producer lane");
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)STAGES * L::STAGE_BYTES);
+    uint64_t *empty = full + STAGES;
+    int &s_ticket = *reinterpret_cast<int *>(empty + STAGES);
+    auto stage_x = [&](int s) { return reinterpret_cast<float4 *>(smem_raw + (size_t)s * L::STAGE_BYTES); };
+    auto stage_v = [&](int s) { return reinterpret_cast<float *>(smem_raw + (size_t)s * L::STAGE_BYTES + (size_t)CH * D * 4); };
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const bool is_cons = warp < CONS;
+    const int p = warp - CONS;  // producer index, < 0 for consumers
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            lr_mbar_init(&full[s], 32);           // one cp.async-arrive per lane of the owning producer warp
+            lr_mbar_init(&empty[s], CONS * 32);   // one release per consumer thread
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    // chunks processed so far by this CTA (over all its rows): stage = g % STAGES, phase = g / STAGES
+    unsigned g = 0;
+
+    // persistent CTAs: rows are handed out in row_order (longest first) through a ticket counter,
+    // so the hottest row starts first and no CTA queues work behind it.
+    for (;;) {
+    if (threadIdx.x == 0) s_ticket = (int)atomicAdd(&g_long_ticket, 1u);
+    __syncthreads();
+    const int ticket = s_ticket;
+    __syncthreads();   // everyone has read the ticket before thread 0 may overwrite it
+    int r, start, len, part = -1;
+    if (a.items) {
+        if (ticket >= a.n_items) break;
+        r = a.items[ticket];
+        start = a.indptr[r] + a.items[a.n_items + ticket];
+        len = a.items[2 * a.n_items + ticket];
+        part = a.items[3 * a.n_items + ticket];
+    } else {
+        if (ticket >= a.order_end - a.order_begin) break;
+        r = a.row_order[a.order_begin + ticket];
+        start = a.indptr[r];
+        len = a.indptr[r + 1] - start;
+    }
+    const int nchunks = (len + CH - 1) / CH;
+    const int *ci = a.indices + start;
+    const float *cv = a.vals + start;
+
+    float acc = 0.f;
+    if (!is_cons) {
+        // ===== producers: warp p owns chunks p, p + PROD, ... =====
+        // lane l holds the column index of entry l of the warp's next two chunks (one coalesced
+        // 128-byte load each, issued two turns ahead), broadcast by shuffle when the gathers are issued
+        auto load_col = [&](int chunk) {
+            const int e = chunk * CH + lane;
+            return (chunk < nchunks && e < len) ? __ldg(ci + e) : -1;
+        };
+        // four turns ahead: one turn (~500 cycles) does not cover an L2 round trip
+        int col0 = load_col(p), col1 = load_col(p + PROD), col2 = load_col(p + 2 * PROD), col3 = load_col(p + 3 * PROD);
+        for (int c = p; c < nchunks; c += PROD) {
+            const unsigned gc = g + (unsigned)c;
+            const int s = (int)(gc % STAGES);
+            if (gc >= (unsigned)STAGES) lr_mbar_wait(&empty[s], ((gc / STAGES) - 1) & 1);
+            float4 *xs = stage_x(s);
+#pragma unroll
+            for (int t = 0; t < ITEMS; ++t) {
+                const int item = lane + 32 * t;
+                const int e = item / F4, f = item % F4;
+                const int cc = __shfl_sync(0xffffffffu, col0, e);
+                if (cc >= 0) cp_async16_plain(xs + (size_t)e * F4 + f, a.x + (long long)cc * a.ldx4 + f);
+            }
+            if (c * CH + lane < len) cp_async4_plain(stage_v(s) + lane, cv + c * CH + lane);
+            lr_cp_async_arrive(&full[s]);
+            col0 = col1;
+            col1 = col2;
+            col2 = col3;
+            col3 = load_col(c + 4 * PROD);
+        }
+    } else {
+        // ===== consumers =====
+        float xa[CH], xb[CH];
+        float4 va[CH / 4], vb[CH / 4];
+        const int f = warp * 32 + lane;
+        // pulls chunk c into registers and releases its stage; a partial (last) chunk is chained in place
+        auto fetch = [&](int c, float (&dx)[CH], float4 (&dv)[CH / 4], bool &pending) {
+            const unsigned gc = g + (unsigned)c;
+            const int s = (int)(gc % STAGES);
+            lr_mbar_wait(&full[s], (gc / STAGES) & 1);
+            const float *xr = reinterpret_cast<const float *>(stage_x(s)) + f;
+            const int n = min(CH, len - c * CH);
+            if (n == CH) {
+                const float4 *vr = reinterpret_cast<const float4 *>(stage_v(s));
+#pragma unroll
+                for (int k = 0; k < CH; ++k) dx[k] = xr[k * D];
+#pragma unroll
+                for (int k4 = 0; k4 < CH / 4; ++k4) dv[k4] = vr[k4];
+                pending = true;
+            } else {
+                pending = false;
+            }
+            return n;
+        };
+        auto chain = [&](const float (&sx)[CH], const float4 (&sv)[CH / 4]) {
+#pragma unroll
+            for (int k4 = 0; k4 < CH / 4; ++k4) {
+                acc = __fmaf_rn(sv[k4].x, sx[4 * k4 + 0], acc);
+                acc = __fmaf_rn(sv[k4].y, sx[4 * k4 + 1], acc);
+                acc = __fmaf_rn(sv[k4].z, sx[4 * k4 + 2], acc);
+                acc = __fmaf_rn(sv[k4].w, sx[4 * k4 + 3], acc);
+            }
+        };
+        auto tail = [&](int c, int n) {       // partial last chunk: straight from shared memory, then release
+            const int s = (int)((g + (unsigned)c) % STAGES);
+            const float *xr = reinterpret_cast<const float *>(stage_x(s)) + f;
+            const float *v1 = stage_v(s);
+            for (int k = 0; k < n; ++k) acc = __fmaf_rn(v1[k], xr[k * D], acc);
+        };
+        bool pa = false, pb = false;
+        for (int c = 0; c < nchunks; c += 2) {
+            // even chunk -> set A, while the chain of set B (chunk c-1) issues
+            int n = fetch(c, xa, va, pa);
+            if (pb) { chain(xb, vb); pb = false; }
+            if (n < CH) tail(c, n);
+            lr_mbar_arrive(&empty[(g + (unsigned)c) % STAGES]);
+            if (c + 1 < nchunks) {
+                n = fetch(c + 1, xb, vb, pb);
+                if (pa) { chain(xa, va); pa = false; }
+                if (n < CH) tail(c + 1, n);
+                lr_mbar_arrive(&empty[(g + (unsigned)c + 1u) % STAGES]);
+            }
+        }
+        if (pa) chain(xa, va);
+        if (pb) chain(xb, vb);
+    }
+    g += (unsigned)nchunks;
+
+    if (is_cons && part >= 0) {
+        a.part_buf[(long long)part * D + warp * 32 + lane] = acc;
+    } else if (is_cons) {
+        const int f = warp * 32 + lane;
+        if (a.y) reinterpret_cast<float *>(a.y + (long long)r * a.ldy4)[f] = acc;
+        if constexpr (PEERS == kPeersP2P) {
+#pragma unroll 1
+            for (int p = 0; p < a.n_peers; ++p)
+                reinterpret_cast<float *>(a.peer_y[p] + (a.peer_row_off + r) * a.ldy4)[f] = acc;
+        } else if constexpr (PEERS == kPeersMulticast) {
+            st_multimem_f1(reinterpret_cast<float *>(a.peer_y[0] + (a.peer_row_off + r) * a.ldy4) + f, acc);
+        }
+        if (a.out) {
+            float o = acc;
+            if (a.addend) o = __fadd_rn(reinterpret_cast<const float *>(a.addend + (long long)r * a.lda4)[f], o);
+            reinterpret_cast<float *>(a.out + (long long)r * a.ldo4)[f] = apply_scale(o, a.scale, a.scale_mode);
+        }
+    }
+    }  // ticket loop
+    // the last CTA to leave re-arms the counters, so every launch (and every profiler replay)
+    // starts from ticket 0 without host involvement
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&g_long_done, 1u) == gridDim.x - 1) {
+            g_long_ticket = 0;
+            g_long_done = 0;
+            __threadfence();
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// long rows, d <= 64: the same roles with ONE CTA-wide barrier per 64-entry chunk (index ring filled
+// 16 chunks ahead by cp.async).  A single CTA gathers at most ~20-25 B/cycle from L2 (measured: 13
+// cycles per 256-byte entry, hottest row of the Amazon-Book shape), which bounds a hot row long before
+// the 4-cycle fmaf chain does; at d = 64 this simpler pipeline reaches that bound and measured faster
+// than the mbarrier version (C4: 22.0 vs 17.9 G edges/s), at d >= 128 the mbarrier version wins
+// (C5/8: 34.7 vs 37.6 ms per step).
+// ---------------------------------------------------------------------------------------------
+template <int D>
+struct LongCfgBar {
     static constexpr int CONS = D / 32;
     static constexpr int PROD = 4;
     static constexpr int THREADS = (CONS + PROD) * 32;
@@ -382,13 +610,9 @@ struct LongCfg {
     static_assert(STAGES - 1 <= IDX_AHEAD && STAGES + IDX_AHEAD + 1 <= IDX_RING, "index ring too small");
 };
 
-// ticket / exit counters of the persistent long-row kernel, re-armed by the last CTA of each launch
-// (one gr_spmm_csr_f32 in flight per device at a time)
-__device__ unsigned int g_long_ticket = 0, g_long_done = 0;
-
 template <int D, int PEERS>
-__global__ void __launch_bounds__(LongCfg<D>::THREADS, 1) spmm_long_rows(const SpmmArgs a) {
-    using L = LongCfg<D>;
+__global__ void __launch_bounds__(LongCfgBar<D>::THREADS, 1) spmm_long_rows_bar(const SpmmArgs a) {
+    using L = LongCfgBar<D>;
     constexpr int STAGES = L::STAGES, CH = L::CHUNK, F4 = D / 4, CONS = L::CONS, PROD = L::PROD;
     constexpr int IR = L::IDX_RING, IA = L::IDX_AHEAD;
     constexpr int NB = CH / PROD;            // entries per producer warp per chunk
@@ -593,19 +817,22 @@ static int get_side(SideStream **out) {
 template <int D>
 static int launch(const SpmmArgs &base, int n_long, long long n_rows, int slot, cudaStream_t stream) {
     using C = RowCfg<D>;
-    using L = LongCfg<D>;
     SideStream *side = nullptr;
     const bool use_long = base.row_order != nullptr && n_long > 0;
     if (use_long) {
         int rc = get_side(&side);
         if (rc != GR_OK) return rc;
+        // d <= 64: barrier pipeline; d >= 128: mbarrier pipeline (see the comments at the kernels)
+        constexpr bool kBar = D <= 64;
+        constexpr int kThreads = kBar ? LongCfgBar<D>::THREADS : LongCfg<D>::THREADS;
+        constexpr size_t kSmem = kBar ? LongCfgBar<D>::SMEM + 16 : LongCfg<D>::SMEM;
+        auto k_none = kBar ? spmm_long_rows_bar<D, kPeersNone> : spmm_long_rows<D, kPeersNone>;
+        auto k_p2p = kBar ? spmm_long_rows_bar<D, kPeersP2P> : spmm_long_rows<D, kPeersP2P>;
+        auto k_mc = kBar ? spmm_long_rows_bar<D, kPeersMulticast> : spmm_long_rows<D, kPeersMulticast>;
         if (!side->smem_attr_set[slot]) {
-            GR_CUDA_CHECK(cudaFuncSetAttribute(spmm_long_rows<D, kPeersNone>,
-                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::SMEM + 16));
-            GR_CUDA_CHECK(cudaFuncSetAttribute(spmm_long_rows<D, kPeersP2P>,
-                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::SMEM + 16));
-            GR_CUDA_CHECK(cudaFuncSetAttribute(spmm_long_rows<D, kPeersMulticast>,
-                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::SMEM + 16));
+            GR_CUDA_CHECK(cudaFuncSetAttribute(k_none, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
+            GR_CUDA_CHECK(cudaFuncSetAttribute(k_p2p, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
+            GR_CUDA_CHECK(cudaFuncSetAttribute(k_mc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
             side->smem_attr_set[slot] = true;
         }
         GR_CUDA_CHECK(cudaEventRecord(side->fork, stream));
@@ -618,11 +845,11 @@ static int launch(const SpmmArgs &base, int n_long, long long n_rows, int slot, 
         if (long_ctas > n_work) long_ctas = n_work;
         if (long_ctas < 1) long_ctas = 1;
         if (la.n_peers > 0 && la.peer_multicast)
-            spmm_long_rows<D, kPeersMulticast><<<long_ctas, L::THREADS, L::SMEM + 16, side->stream>>>(la);
+            k_mc<<<long_ctas, kThreads, kSmem, side->stream>>>(la);
         else if (la.n_peers > 0)
-            spmm_long_rows<D, kPeersP2P><<<long_ctas, L::THREADS, L::SMEM + 16, side->stream>>>(la);
+            k_p2p<<<long_ctas, kThreads, kSmem, side->stream>>>(la);
         else
-            spmm_long_rows<D, kPeersNone><<<long_ctas, L::THREADS, L::SMEM + 16, side->stream>>>(la);
+            k_none<<<long_ctas, kThreads, kSmem, side->stream>>>(la);
         GR_LAUNCH_CHECK();
         if (la.items && la.n_split > 0) {
             spmm_combine_parts<<<la.n_split, 128, 0, side->stream>>>(la, D);
