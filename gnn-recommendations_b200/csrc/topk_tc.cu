@@ -77,7 +77,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 }
 // waiting role that is NOT on the critical path (producers, MMA issuer): back off between polls so the
 // spin does not take issue slots from the epilogue warp sharing the scheduler
-__device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, uint32_t parity, unsigned sleep_ns = 200) {
     uint32_t done = 0;
     while (true) {
         asm volatile(
@@ -88,7 +88,7 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, uint32_t parity
             : "r"(smem_u32(bar)), "r"(parity), "r"(2000u)
             : "memory");
         if (done) break;
-        __nanosleep(200);
+        __nanosleep(sleep_ns);
     }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -216,6 +216,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) topk_tc_candidates_kernel(const
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 9);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned sleep_ns = (a.debug >> 8) ? (unsigned)(a.debug >> 8) : 200u;
     const int row0 = blockIdx.x * TC_M;
     const long long item_lo = a.item_lo + (long long)blockIdx.y * a.split_items;
     const long long item_hi = min(a.item_hi, item_lo + a.split_items);
@@ -253,7 +254,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) topk_tc_candidates_kernel(const
         mbar_arrive(a_full);
         for (int t = 0; t < n_tiles; ++t) {
             const int s = t % TC_STAGES;
-            if (t >= TC_STAGES) mbar_wait_relaxed(&b_empty[s], ((t / TC_STAGES) - 1) & 1);
+            if (t >= TC_STAGES) mbar_wait_relaxed(&b_empty[s], ((t / TC_STAGES) - 1) & 1, sleep_ns);
             unsigned char *dst = sB + (size_t)s * nkb * tile_bytes;
             const long long i0 = item_lo + (long long)t * TC_N;
             // 8 independent 16-byte loads in flight per thread, then their swizzled stores
@@ -281,11 +282,11 @@ __global__ void __launch_bounds__(TC_THREADS, 2) topk_tc_candidates_kernel(const
     } else if (warp == 8) {
         // ===== MMA issuer =====
         if (lane == 0) {
-            mbar_wait_relaxed(a_full, 0);
+            mbar_wait_relaxed(a_full, 0, sleep_ns);
             for (int t = 0; t < n_tiles; ++t) {
                 const int s = t % TC_STAGES, acc = t & 1;
-                mbar_wait_relaxed(&b_full[s], (t / TC_STAGES) & 1);
-                if (t >= 2) mbar_wait_relaxed(&t_empty[acc], ((t >> 1) - 1) & 1);
+                mbar_wait_relaxed(&b_full[s], (t / TC_STAGES) & 1, sleep_ns);
+                if (t >= 2) mbar_wait_relaxed(&t_empty[acc], ((t >> 1) - 1) & 1, sleep_ns);
                 tc_fence_after();
                 const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB + (size_t)s * nkb * tile_bytes);
                 const uint32_t tmem_d = tmem_base + (uint32_t)acc * TC_N;
