@@ -204,7 +204,8 @@ def test_trainer_epoch_validate_evaluate_vs_reference(tiny, tmp_path):
 
 
 # ----------------------------------------------------------------------------- tensor-core nomination
-@pytest.mark.parametrize("d,k,n_items,nu", [(64, 20, 3000, 300), (64, 10, 130, 70), (32, 20, 2500, 129), (64, 32, 4097, 257), (64, 50, 3000, 200)])
+@pytest.mark.parametrize("d,k,n_items,nu", [(64, 20, 3000, 300), (64, 10, 130, 70), (32, 20, 2500, 129), (64, 32, 4097, 257), (64, 50, 3000, 200),
+                                             (128, 20, 2100, 140), (128, 40, 1500, 260)])
 def test_topk_tensor_core_path_is_bit_identical(d, k, n_items, nu):
     """tcgen05 TF32 nomination + exact re-scoring (+ exact fallback for unproven rows) must reproduce
     the exact kernel / C oracle bit for bit, including exact ties and seen-item masks."""
