@@ -348,10 +348,65 @@ def run_b200(args):
             torch.cuda.current_stream().synchronize()
             return float(out_host[0, 0])
 
-        ms_e2e = timed(e2e_step, args.steps, min(args.warmup, 3))
+        ms_serial = timed(e2e_step, args.steps, min(args.warmup, 3))
+        ms_e2e, mode = ms_serial, "one step at a time"
+
+        if world == 1:
+            # The same steps software-pipelined, as a serving loop runs them: the upload of step i+1
+            # (copy stream) and the download of step i-1 (second copy stream) overlap the propagation
+            # of step i.  Every step still uploads its own COO and downloads its own embeddings; one
+            # device COO buffer is enough because the CSR conversion has consumed it (host-synchronous)
+            # before the next upload is enqueued.
+            s_h2d, s_d2h = torch.cuda.Stream(), torch.cuda.Stream()
+            cur = torch.cuda.current_stream()
+            idx_d = torch.empty(idx_host.shape, dtype=torch.int64, device=dev)
+            val_d = torch.empty(val_host.shape, dtype=torch.float32, device=dev)
+
+            def pipelined_step():
+                with torch.cuda.stream(s_h2d):
+                    idx_d.copy_(idx_host, non_blocking=True)
+                    val_d.copy_(val_host, non_blocking=True)
+                    up = torch.cuda.Event()
+                    up.record(s_h2d)
+                cur.wait_event(up)
+                adj = torch.sparse_coo_tensor(idx_d, val_d, shape, check_invariants=False)
+                loc = g.NormAdjCSR.from_torch_coo(adj)      # synchronises: idx_d / val_d are free again
+                with torch.no_grad():
+                    ue, ie = model.get_all_embeddings(loc)
+                done = torch.cuda.Event()
+                done.record(cur)
+                with torch.cuda.stream(s_d2h):
+                    s_d2h.wait_event(done)
+                    out_host[:nu].copy_(ue, non_blocking=True)
+                    out_host[nu:].copy_(ie, non_blocking=True)
+                ue.record_stream(s_d2h)
+                ie.record_stream(s_d2h)
+
+            def drain():
+                cur.wait_stream(s_d2h)
+                cur.wait_stream(s_h2d)
+
+            for _ in range(min(args.warmup, 3)):
+                pipelined_step()
+            drain()
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(args.steps):
+                pipelined_step()
+            drain()
+            e1.record()
+            barrier()
+            ms_e2e = e0.elapsed_time(e1) / args.steps
+            mode = ("software-pipelined: upload of step i+1 and download of step i-1 on copy streams overlap the "
+                    "propagation of step i; timed over all steps incl. pipeline fill and drain")
+            assert float(out_host[0, 0]) == float(out_host[0, 0])
+            del idx_d, val_d
         e2e = {"value": L * nnz / (ms_e2e * 1e-3), "unit": "edges/s", "ms_per_step": ms_e2e,
                "h2d_bytes_per_step": int(idx_host.numel() * 8 + val_host.numel() * 4),
                "d2h_bytes_per_step": int(out_host.numel() * 4),
+               "schedule": mode,
+               "serial_ms_per_step": ms_serial, "serial_value": L * nnz / (ms_serial * 1e-3),
                "path": "torch COO (int64 indices, f32 values) in pinned host memory -> .to(device) -> "
                        "model.get_all_embeddings(adj) -> embeddings copied to pinned host memory"}
         del idx_host, val_host, out_host
