@@ -263,3 +263,100 @@ def full_rank_topk_sharded(user_emb: torch.Tensor, item_emb_local: torch.Tensor,
         dist.all_gather_into_tensor(all_pi, pi.contiguous(), group=group)
         ps, pi = all_ps, all_pi
     return merge_fn(ps, pi, k)
+
+
+# ------------------------------------------------------------------------------------------------
+# row-partitioned LightGCN training step (BPR step + backward)
+# ------------------------------------------------------------------------------------------------
+class ShardedLightGCN:
+    """LightGCN whose embedding table (and its Adam state) is row-partitioned like the graph.
+
+    One step = trainer.py:237-279 on G ranks:
+      forward   row-partitioned propagation (one exchange per layer);
+      BPR       the batch is replicated: the 3B propagated rows it touches are collected with one
+                all-reduce of a [3B, d] buffer (each row has exactly one owner, the others add zeros),
+                every rank evaluates the same fused B x B loss on that compact table and keeps the
+                gradient rows it owns;
+      backward  d loss / d E0 = mean_l Â^l g (Â is symmetric, so the backward of the layer mean IS the
+                forward operator applied to the gradient): the same row-partitioned propagation;
+      step      global gradient norm by one scalar all-reduce, then the fused clip + Adam pass on the
+                local rows only — no gradient all-reduce, no replicated parameters.
+    ``propagate`` and ``bpr`` are injectable for the CPU (gloo) tests of the host logic.
+    """
+
+    def __init__(self, local: NormAdjCSR, part: RowPartition, rank: int, x0_local: torch.Tensor, n_users: int,
+                 n_layers: int, lr: float = 1e-3, weight_decay: float = 1e-4, max_grad_norm: float = 1.0,
+                 exchange: Optional["PeerExchange"] = None, group=None, propagate: Optional[Callable] = None,
+                 bpr: Optional[Callable] = None, fused_optimizer: bool = True):
+        self.local, self.part, self.rank, self.group = local, part, rank, group
+        self.n_users, self.n_layers = int(n_users), int(n_layers)
+        self.max_grad_norm = float(max_grad_norm)
+        self.weight = torch.nn.Parameter(x0_local.detach().clone())        # rows rank, rank+G, ... of [E_user; E_item]
+        self.optimizer = torch.optim.Adam([self.weight], lr=lr, weight_decay=weight_decay)
+        self.exchange = exchange
+        self._propagate = propagate
+        self._bpr = bpr
+        self.fused_optimizer = fused_optimizer
+
+    # ---- pieces ---------------------------------------------------------------------------------
+    def propagate(self, x_local: torch.Tensor) -> torch.Tensor:
+        if self._propagate is not None:
+            return self._propagate(x_local)
+        if self.exchange is not None:
+            return lightgcn_propagate_fused(self.local, self.exchange, x_local, self.n_layers)
+        return lightgcn_propagate_sharded(self.local, self.part, self.rank, x_local, self.n_layers, self.group)
+
+    def _all_reduce(self, t: torch.Tensor) -> torch.Tensor:
+        import torch.distributed as dist
+
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            dist.all_reduce(t, group=self.group)
+        return t
+
+    def batch_rows(self, users: torch.Tensor, pos: torch.Tensor, neg: torch.Tensor):
+        """global row ids of the 3B embedding rows of a batch, their owner mask and local indices."""
+        need = torch.cat([users.view(-1), self.n_users + pos.view(-1), self.n_users + neg.view(-1)]).long()
+        mine = (need % self.part.world_size) == self.rank
+        return need, mine, need // self.part.world_size
+
+    def train_step(self, users: torch.Tensor, pos: torch.Tensor, neg: torch.Tensor) -> float:
+        B = int(users.numel())
+        dev = self.weight.device
+        with torch.no_grad():
+            out_local = self.propagate(self.weight.detach())
+            need, mine, loc = self.batch_rows(users.to(dev), pos.to(dev), neg.to(dev))
+            table = torch.zeros((3 * B, out_local.shape[1]), dtype=out_local.dtype, device=dev)
+            table[mine] = out_local[loc[mine]]
+            self._all_reduce(table)
+        # the same B x B loss every rank: users 0..B-1, positives B..2B-1, negatives 2B..3B-1 of the table
+        ar = torch.arange(B, device=dev)
+        table.requires_grad_(True)
+        if self._bpr is not None:
+            loss = self._bpr(table, B, ar, ar, (B + ar).view(-1, 1))
+        else:
+            from .losses import bpr_fused
+
+            loss = bpr_fused(table, B, ar, ar, (B + ar).view(-1, 1))
+        loss.backward()
+        with torch.no_grad():
+            g_local = torch.zeros_like(self.weight)
+            g_local.index_add_(0, loc[mine], table.grad[mine])              # duplicates accumulate
+            grad = self.propagate(g_local)                                   # mean_l Â^l g
+            self.weight.grad = grad
+            if self.max_grad_norm > 0:
+                sq = self._all_reduce(grad.double().pow(2).sum().view(1))
+                coef = self.max_grad_norm / (float(sq.sqrt()) + 1e-6)
+                if coef < 1.0:
+                    grad.mul_(coef)
+                else:
+                    grad.mul_(1.0)
+            if self.fused_optimizer and grad.is_cuda:
+                from .optim import fused_clip_adam_step
+
+                fused_clip_adam_step(self.optimizer, 0.0)                    # already clipped with the GLOBAL norm
+            else:
+                self.optimizer.step()
+        return float(loss.detach())
+
+    def gathered_weight(self) -> torch.Tensor:
+        return gather_rows(self.part, self.rank, self.weight.detach(), self.group)

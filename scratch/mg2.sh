@@ -1,5 +1,4 @@
 #!/bin/bash
-mkdir -p gpurun_out
-timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/multigpu_check.py C1 2>&1 | grep -v "^W\|Warning" | tail -6
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 3 --warmup 3 --workload C5/8 2>&1 | tail -1 | cut -c1-700
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 2 --impl reference --steps 1 --warmup 0 2>&1 | tail -1 | cut -c1-400
+for shape in C1 C4; do
+timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/multigpu_check.py $shape 2>&1 | grep -v "^W\|Warning\|\*\*\*\|OMP_NUM" | tail -4
+done

@@ -13,8 +13,9 @@ import torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 import gnn_recommendations_b200 as g  # noqa: E402
-from gnn_recommendations_b200.dist import (PeerExchange, RowPartition, full_rank_topk_sharded, gather_rows,  # noqa: E402
-                                           item_shard, lightgcn_propagate_fused, lightgcn_propagate_sharded)
+from gnn_recommendations_b200.dist import (PeerExchange, RowPartition, ShardedLightGCN, full_rank_topk_sharded,  # noqa: E402
+                                           gather_rows, item_shard, lightgcn_propagate_fused,
+                                           lightgcn_propagate_sharded)
 from gnn_recommendations_b200.evaluator import ground_truth_dict, seen_csr  # noqa: E402
 from gnn_recommendations_b200.synthetic import SHAPES, synth_split  # noqa: E402
 
@@ -52,12 +53,39 @@ def main():
     lo, hi = item_shard(ni, world, rank)
     got = full_rank_topk_sharded(gathered[:nu], gathered[nu + lo: nu + hi], lo, hi, eu, ip, it, 20, world, n_splits=2)
     ok_topk = bool(torch.equal(got, want))
-    flags = torch.tensor([int(ok_prop), int(ok_topk), int(ok_fused)], device=dev)
+    # row-partitioned training steps (ShardedLightGCN) vs the single-GPU step on the full graph
+    import time
+
+    from gnn_recommendations_b200.losses import bpr_fused
+    from gnn_recommendations_b200.optim import fused_clip_adam_step
+    B, n_steps = 512, 20
+    sharded = ShardedLightGCN(local_csr, part, rank, x0_mine, nu, L, exchange=ex)
+    w_full = torch.nn.Parameter(x0.clone())
+    opt = torch.optim.Adam([w_full], lr=1e-3, weight_decay=1e-4)
+    rng = np.random.default_rng(11)
+    batches = [(torch.from_numpy(rng.integers(0, nu, B)).to(dev), torch.from_numpy(rng.integers(0, ni, B)).to(dev),
+                torch.from_numpy(rng.integers(0, ni, B)).view(-1, 1).to(dev)) for _ in range(n_steps)]
+    ok_train, t_sh, t_1 = True, 0.0, 0.0
+    for users, pos, neg in batches:
+        torch.cuda.synchronize(); dist.barrier(); t0 = time.perf_counter()
+        loss_sh = sharded.train_step(users, pos, neg)
+        torch.cuda.synchronize(); dist.barrier(); t_sh += time.perf_counter() - t0
+        t0 = time.perf_counter()
+        opt.zero_grad()
+        xp = g.lightgcn._LightGCNPropagate.apply(w_full, full, L)
+        loss_1 = bpr_fused(xp, nu, users, pos, neg)
+        loss_1.backward()
+        fused_clip_adam_step(opt, 1.0)
+        torch.cuda.synchronize(); t_1 += time.perf_counter() - t0
+        ok_train = ok_train and abs(loss_sh - float(loss_1)) <= 1e-6 * abs(float(loss_1))
+    ok_train = ok_train and bool(torch.allclose(sharded.gathered_weight(), w_full.detach(), rtol=1e-4, atol=2e-6))
+    flags = torch.tensor([int(ok_prop), int(ok_topk), int(ok_fused), int(ok_train)], device=dev)
     dist.all_reduce(flags, op=dist.ReduceOp.MIN)
     if rank == 0:
         print(f"multigpu_check shape={shape} world={world} rows/rank={[part.n_local(r) for r in range(world)]} "
               f"propagation_bit_identical={bool(flags[0])} topk_bit_identical={bool(flags[1])} "
-              f"fused_peer_exchange_bit_identical={bool(flags[2])}", flush=True)
+              f"fused_peer_exchange_bit_identical={bool(flags[2])} sharded_training_matches={bool(flags[3])} "
+              f"train_step_ms: sharded {1e3 * t_sh / n_steps:.3f} vs 1 GPU {1e3 * t_1 / n_steps:.3f}", flush=True)
     dist.destroy_process_group()
     sys.exit(0 if bool(flags.min()) else 1)
 

@@ -12,8 +12,8 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from gnn_recommendations_b200 import _lib
-from gnn_recommendations_b200.dist import (RowPartition, full_rank_topk_sharded, gather_rows, item_shard,
-                                           lightgcn_propagate_sharded)
+from gnn_recommendations_b200.dist import (RowPartition, ShardedLightGCN, full_rank_topk_sharded, gather_rows,
+                                           item_shard, lightgcn_propagate_sharded)
 from gnn_recommendations_b200.synthetic import synth_split
 from oracle import pyoracle as po
 
@@ -107,6 +107,73 @@ def _worker(rank, world, port, out):
         out[rank] = (ok_prop, ok_topk)
     finally:
         dist.destroy_process_group()
+
+
+def _train_worker(rank, world, port, out):
+    """Two row-partitioned training steps (ShardedLightGCN) vs the single-process step of the reference
+    (trainer.py:237-279 restated with the oracle's ops: propagate, B x B BPR, clip, Adam)."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        sp = synth_split("tiny", 42)
+        nu, ni = sp["n_users"], sp["n_items"]
+        adj = po.build_norm_adj(*sp["train"], nu, ni)
+        gen = torch.Generator().manual_seed(0)
+        x0 = torch.randn(nu + ni, 32, generator=gen) * 0.1
+        part = RowPartition(torch.from_numpy(adj["indptr"]), world)
+        local = _cpu_local_csr(part, adj, rank)
+
+        def spmm(x, y, addend, o, scale, mode):
+            t = torch.sparse.mm(local.coo, x)
+            if y is not None:
+                y.copy_(t)
+            if o is not None:
+                r = t if addend is None else addend + t
+                o.copy_(r / scale if mode == _lib.GR_SCALE_DIV else r)
+
+        def propagate(x_local):
+            return lightgcn_propagate_sharded(local, part, rank, x_local, 3, spmm=spmm)
+
+        def bpr(table, n_users_b, users, pos, neg):
+            return po.bpr_loss_reference(table[:n_users_b], table[n_users_b:], users, pos, neg)
+
+        model = ShardedLightGCN(local, part, rank, part.take_rows(x0, rank), nu, 3, lr=1e-2, weight_decay=1e-4,
+                                max_grad_norm=1.0, propagate=propagate, bpr=bpr, fused_optimizer=False)
+        # single-process reference
+        uw = torch.nn.Parameter(x0[:nu].clone())
+        iw = torch.nn.Parameter(x0[nu:].clone())
+        opt = torch.optim.Adam([uw, iw], lr=1e-2, weight_decay=1e-4)
+        coo = po.to_torch_coo(adj)
+        rng = np.random.default_rng(7)
+        ok = True
+        for step in range(2):
+            users = torch.from_numpy(rng.integers(0, nu, 48))
+            users[1] = users[0]                                   # duplicates accumulate
+            pos = torch.from_numpy(rng.integers(0, ni, 48))
+            neg = torch.from_numpy(rng.integers(0, ni, 48)).view(-1, 1)
+            loss = model.train_step(users, pos, neg)
+            opt.zero_grad()
+            ue, ie = po.lightgcn_forward(coo, uw, iw, 3)
+            ref_loss = po.bpr_loss_reference(ue, ie, users, pos, neg)
+            ref_loss.backward()
+            torch.nn.utils.clip_grad_norm_([uw, iw], 1.0)
+            opt.step()
+            ok = ok and abs(loss - float(ref_loss)) <= 1e-6 * abs(float(ref_loss))
+            got = model.gathered_weight()
+            want = torch.cat([uw.detach(), iw.detach()])
+            ok = ok and bool(torch.allclose(got, want, rtol=1e-5, atol=2e-6))   # Adam amplifies 1e-10 gradient differences
+        out[rank] = ok
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_world2_sharded_training_step_matches_single_process():
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_train_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    assert dict(out) == {0: True, 1: True}
 
 
 @pytest.mark.timeout(300)
