@@ -407,3 +407,35 @@ def test_ultragcn_under_trainer(tiny, tmp_path):
     np.testing.assert_allclose(out[0][1], out[1][1], rtol=1e-5, atol=1e-7)
     assert set(out[0][2]) == set(out[1][2])
     assert not np.array_equal(out[0][1], tiny["lightgcn/user_embedding.weight"])      # it trained
+
+
+# ----------------------------------------------------------------------------- one reference epoch, other model families
+@pytest.mark.parametrize("name", ["ngcf", "gat", "orthogonal_bundle"])
+def test_trainer_epoch_other_models_vs_reference(name, tiny, tmp_path):
+    """One full Trainer epoch (11 steps: sampler, forward, B x B BPR, backward, clip, Adam) from the
+    reference's initial parameters must land on the reference's post-epoch parameters
+    (tests/golden/make_golden_epochs.py; dropout 0 — the reference's dropout uses the CPU generator)."""
+    import os
+    z = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "epochs.npz")))
+    nu, ni = int(tiny["n_users"]), int(tiny["n_items"])
+    make = {"ngcf": lambda: g.NGCF(nu, ni, embedding_dim=64, dropout=0.0, init_scale=0.1),
+            "gat": lambda: g.GAT(nu, ni, embedding_dim=64, n_layers=2, n_heads=4, dropout=0.0, init_scale=0.1),
+            "orthogonal_bundle": lambda: g.OrthogonalBundleGNN(nu, ni, embedding_dim=64, n_layers=3, block_size=8,
+                                                                dropout=0.0, init_scale=0.1)}[name]
+    torch.manual_seed(42)
+    m = make()
+    init = {k[len(name) + 6:]: torch.from_numpy(v) for k, v in z.items() if k.startswith(f"{name}/init/")}
+    assert set(init) == set(m.state_dict()), (sorted(set(init) ^ set(m.state_dict())))
+    m.load_state_dict(init)
+    tr = g.Trainer(m, dataset_from(tiny), dict(CFG, checkpoint_dir=str(tmp_path / "ckpt")), device=torch.device(DEV))
+    torch.manual_seed(123)
+    loss = tr.train_epoch()
+    want_loss = float(z[f"{name}/loss"])
+    assert abs(loss - want_loss) <= 2e-5 * abs(want_loss), (loss, want_loss)
+    for k, v in m.state_dict().items():
+        want = z[f"{name}/epoch/{k}"]
+        if not np.issubdtype(want.dtype, np.floating):
+            assert np.array_equal(v.cpu().numpy(), want), k
+            continue
+        moved = np.abs(want - z[f"{name}/init/{k}"]).max()
+        np.testing.assert_allclose(v.detach().cpu().numpy(), want, rtol=2e-3, atol=max(5e-6, 0.02 * float(moved)), err_msg=k)
