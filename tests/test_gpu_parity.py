@@ -289,3 +289,40 @@ def test_spmm_split_rows_deterministic_segment_sums():
         add = torch.randn(ref["n"], d, generator=torch.Generator().manual_seed(1))
         _, out = csr.spmm(x.to(DEV), addend=add.to(DEV), scale=4.0, scale_mode=_lib.GR_SCALE_DIV, want_y=False)
         assert np.array_equal(bits(out.cpu().numpy()), bits((add.numpy() + got) / np.float32(4.0)))
+
+
+# ----------------------------------------------------------------------------- BASELINE configs[1..3] at full size
+@pytest.mark.parametrize("shape", ["C2", "C3", "C4"])
+def test_full_size_dataset_shapes_vs_oracle(shape):
+    """Gowalla / Yelp2018 / Amazon-Book shapes (BASELINE.json configs 1-3) end to end on the GPU:
+    temporal split, graph build (CSR bit-exact), LightGCN propagation (bit-exact), full-ranking top-20
+    of a user sample by the exact and the tensor-core path (identical to the C oracle)."""
+    from gnn_recommendations_b200.dataset import temporal_split_device
+    from gnn_recommendations_b200.evaluator import seen_csr
+    from gnn_recommendations_b200.synthetic import synth_split
+    from oracle import coracle
+    sp = synth_split(shape, 42)
+    nu, ni = sp["n_users"], sp["n_items"]
+    dsp = temporal_split_device(*sp["all"], nu, device=DEV)
+    for part in ("train", "valid", "test"):
+        for a, b in zip(dsp[part], sp[part]):
+            assert np.array_equal(a.cpu().numpy(), b), (shape, part)
+    tu, ti = sp["train"]
+    ref = po.build_norm_adj(tu, ti, nu, ni)
+    csr = g.NormAdjCSR.from_pairs(tu, ti, nu, ni, device=DEV)
+    assert np.array_equal(csr.indptr.cpu().numpy().astype(np.int64), ref["indptr"])
+    assert np.array_equal(csr.indices.cpu().numpy(), ref["indices"])
+    assert np.array_equal(csr.vals.cpu().numpy().view(np.uint32), ref["vals"].view(np.uint32))
+    gen = torch.Generator().manual_seed(0)
+    uw, iw = torch.randn(nu, 64, generator=gen) * 0.1, torch.randn(ni, 64, generator=gen) * 0.1
+    oue, oie = po.lightgcn_forward(po.to_torch_coo(ref), uw, iw, 3)
+    x = g.lightgcn_propagate(csr, torch.cat([uw, iw]).to(DEV), 3)
+    assert torch.equal(x[:nu].cpu(), oue) and torch.equal(x[nu:].cpu(), oie), shape
+    eu = np.unique(sp["test"][0])[::37][:600]
+    ip, it = seen_csr(eu, nu, sp["train"], sp["valid"])
+    want = coracle.score_topk(oue.numpy(), oie.numpy(), eu, ip, it, 20)
+    exact = g.full_rank_topk(x[:nu], x[nu:], eu, ip, it, 20, tensor_cores=False)
+    assert np.array_equal(exact.cpu().numpy(), want), shape
+    stats = {}
+    tc = g.full_rank_topk(x[:nu], x[nu:], eu, ip, it, 20, tensor_cores=True, stats=stats)
+    assert stats["tensor_cores"] and torch.equal(tc, exact), shape
