@@ -146,3 +146,36 @@ def test_ultragcn_matches_reference_golden():
         np.testing.assert_allclose(m.user_embedding.weight.grad.numpy(), z[f"{tag}/grad_user"], rtol=1e-5, atol=1e-7)
         np.testing.assert_allclose(m.item_embedding.weight.grad.numpy(), z[f"{tag}/grad_item"], rtol=1e-5, atol=1e-7)
     assert g.MODEL_REGISTRY["ultragcn"] is g.UltraGCN
+
+
+# ----------------------------------------------------------------------------- host helpers of the later stages
+def test_tc_kprime_and_splits_rules():
+    from gnn_recommendations_b200.evaluator import choose_splits, tc_kprime
+    assert [tc_kprime(k) for k in (1, 10, 20, 24, 32, 50, 52, 60)] == [24, 24, 32, 40, 48, 64, 64, 64]
+    assert all(tc_kprime(k) >= k + 8 for k in range(1, 57))
+    assert choose_splits(52643, 91599) == 1 and choose_splits(29, 91599) == 64 and choose_splits(64, 600) == 2
+
+
+def test_discount_tables_follow_the_reference_loops():
+    from gnn_recommendations_b200.metrics import discount_tables
+    disc, idcg = discount_tables(50)
+    acc = 0.0
+    for rank in range(50):
+        assert disc[rank] == 1.0 / np.log2(rank + 2)          # metrics.py:404
+        acc += 1.0 / np.log2(rank + 2)                        # metrics.py:405-409
+        assert idcg[rank + 1] == acc
+    assert idcg[0] == 0.0
+
+
+def test_later_stages_refuse_cpu_inputs():
+    """No CPU fallback anywhere on the product path."""
+    from gnn_recommendations_b200.dataset import temporal_split_device
+    from gnn_recommendations_b200.optim import fused_clip_adam_supported
+    with pytest.raises(RuntimeError):
+        g.topk_metrics_device(torch.zeros((4, 5), dtype=torch.int64), np.zeros(5, np.int64), np.zeros(0, np.int32), 10)
+    with pytest.raises(RuntimeError):
+        temporal_split_device(np.zeros(3, np.int64), np.zeros(3, np.int64), np.zeros(3, np.int64), 4, device="cpu")
+    p = torch.nn.Parameter(torch.zeros(8))
+    p.grad = torch.ones(8)
+    assert not fused_clip_adam_supported(torch.optim.Adam([p]))          # CPU tensors: stock path only
+    assert not fused_clip_adam_supported(torch.optim.SGD([p], lr=0.1))
