@@ -48,6 +48,10 @@ SIGNATURES = {
     "gr_topk_merge": (C.c_int, [_p, _p, _i32, _i64, _i32, _p, _p, _p]),
     "gr_score_topk": (C.c_int, [_p, _i64, _p, _i64, _i32, _p, _i64, _i64, _p, _p, _i32, _i32, _p, _p, _p, _sz,
                                 _p]),
+    "gr_build_local_csr_workspace_bytes": (_sz, [_i64]),
+    "gr_build_local_csr_pattern": (C.c_int, [_p, _p, _i64, _i64, _i64, _i32, _i32, _i32, _i64, _i64, _p, _p, _p, _p,
+                                             _p, _p, _p, _p, _sz, _p]),
+    "gr_csr_normalize_local": (C.c_int, [_p, _p, _p, _p, _p, _i64, _i64, _i64, _i32, _i32, _i32, _i64, _p, _p, _p]),
     "gr_temporal_split_workspace_bytes": (_sz, [_i64]),
     "gr_temporal_split": (C.c_int, [_p, _p, _p, _i64, _i64, _i64, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "gr_clip_adam_workspace_bytes": (_sz, [_p, _i32]),

@@ -650,3 +650,179 @@ extern "C" int gr_temporal_split(const int64_t *user, const int64_t *item, const
     GR_LAUNCH_CHECK();
     return GR_OK;
 }
+
+// =============================================================================================
+// Partitioned graph build: the rows rank, rank + G, ... of Â straight from the pairs
+// =============================================================================================
+namespace gr {
+
+// Every rank walks all pairs (global degrees need them all) but keeps only the directed entries whose
+// row it owns.  key = local row (r / G) << col_bits | global column; appended through a counter — the
+// order is irrelevant, the sort that follows fixes it.
+__global__ void pair_keys_local_kernel(const int64_t *user, const int64_t *item, long long n_pairs, long long n_users,
+                                       long long n_items, int self_loop, int col_bits, int world, int rank,
+                                       uint64_t *keys, unsigned long long *counter, long long cap, int *deg,
+                                       int *status) {
+    const long long n = n_users + n_items;
+    const long long total = 2 * n_pairs + (self_loop ? n : 0);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += stride) {
+        long long r, c;
+        if (k < 2 * n_pairs) {
+            const long long p = k < n_pairs ? k : k - n_pairs;
+            long long u = user[p], i = item[p];
+            if (u < 0 || u >= n_users || i < 0 || i >= n_items) {
+                atomicOr(status, 2);
+                u = 0;
+                i = 0;
+            }
+            r = k < n_pairs ? u : n_users + i;
+            c = k < n_pairs ? n_users + i : u;
+        } else {
+            r = c = k - 2 * n_pairs;
+        }
+        atomicAdd(&deg[r], 1);
+        if (r % world == rank) {
+            const unsigned long long pos = atomicAdd(counter, 1ULL);
+            if ((long long)pos < cap) keys[pos] = ((uint64_t)(r / world) << col_bits) | (uint64_t)c;
+            else atomicOr(status, 8);
+        }
+    }
+}
+
+// as unique_emit_kernel, but rows are local and the column ids leave in the owner-major padded numbering
+// of the exchange buffers ((c % G) * H + c / G); the ORDER inside a row stays ascending global column,
+// i.e. the single-GPU chain order.
+__global__ void unique_emit_local_kernel(const uint64_t *keys, const uint32_t *pos, long long n, int col_bits,
+                                         long long n_rows, int world, long long block_rows, int *indptr, int *indices,
+                                         float *mult, long long *nnz_out) {
+    const uint64_t col_mask = (1ull << col_bits) - 1ull;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
+        const uint64_t key = keys[k];
+        const bool head = (k == 0) || key != keys[k - 1];
+        if (!head) continue;
+        const uint32_t p = pos[k];
+        long long e = k + 1;
+        while (e < n && keys[e] == key) ++e;
+        const long long c = (long long)(key & col_mask);
+        indices[p] = (int)((c % world) * block_rows + c / world);
+        mult[p] = (float)(e - k);
+        const long long r = (long long)(key >> col_bits);
+        const long long prev = k ? (long long)(keys[k - 1] >> col_bits) : -1;
+        for (long long rr = prev + 1; rr <= r; ++rr) indptr[rr] = (int)p;
+        if (e == n) {
+            const uint32_t total = p + 1;
+            for (long long rr = r + 1; rr <= n_rows; ++rr) indptr[rr] = (int)total;
+            *nnz_out = (long long)total;
+        }
+    }
+}
+
+__global__ void normalize_local_kernel(const int *indptr, const int *indices, const float *mult, const int *deg,
+                                       const float *lut, long long lut_len, long long n_rows, long long nnz, int mode,
+                                       int world, int rank, long long block_rows, float *vals, int *status) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < nnz; k += stride) {
+        long long lo = 0, hi = n_rows;
+        while (hi - lo > 1) {
+            const long long mid = (lo + hi) >> 1;
+            if (indptr[mid] <= k) lo = mid; else hi = mid;
+        }
+        const long long pc = indices[k];
+        const long long gr_ = lo * world + rank;                               // global row
+        const long long gc = (pc % block_rows) * world + pc / block_rows;      // global column
+        const int dr = deg[gr_], dc = deg[gc];
+        if (dr >= lut_len || dc >= lut_len) {
+            atomicOr(status, 4);
+            continue;
+        }
+        const float a = mult[k];
+        float v;
+        if (mode == 0) v = __fmul_rn(__fmul_rn(lut[dr], a), lut[dc]);
+        else if (mode == 1) v = __fmul_rn(lut[dr], a);
+        else v = a;
+        vals[k] = v;
+    }
+}
+
+}  // namespace gr
+
+extern "C" size_t gr_build_local_csr_workspace_bytes(int64_t n_local_entries) {
+    if (n_local_entries < 0) return 0;
+    const int64_t t = n_local_entries > 0 ? n_local_entries : 1;
+    return 2 * align256((size_t)t * 8) + align256((size_t)t * 4) + align256(radix_sort_workspace_bytes(t)) +
+           align256(scan_workspace_bytes(t)) + 512;
+}
+
+extern "C" int gr_build_local_csr_pattern(const int64_t *user, const int64_t *item, int64_t n_pairs, int64_t n_users,
+                                          int64_t n_items, int32_t self_loop, int32_t world, int32_t rank,
+                                          int64_t block_rows, int64_t n_local_entries, int32_t *indptr,
+                                          int32_t *indices, float *mult, int32_t *deg, int64_t *nnz_out,
+                                          int32_t *max_deg_out, int32_t *status, void *workspace,
+                                          size_t workspace_bytes, void *stream) {
+    if (n_pairs < 0 || n_users < 0 || n_items < 0 || world <= 0 || rank < 0 || rank >= world || block_rows <= 0 ||
+        n_local_entries < 0 || !indptr || !deg || !nnz_out || !max_deg_out || !status || !workspace)
+        return GR_ERR_INVALID;
+    const int64_t n = n_users + n_items;
+    const int64_t total = 2 * n_pairs + (self_loop ? n : 0);
+    if (n >= 0x7fffffffLL || n_local_entries > 0x7fffffffLL || block_rows * world >= 0x7fffffffLL) return GR_ERR_OVERFLOW;
+    if (workspace_bytes < gr_build_local_csr_workspace_bytes(n_local_entries)) return GR_ERR_WORKSPACE;
+    const int64_t n_local = n > rank ? (n - rank + world - 1) / world : 0;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    GR_CUDA_CHECK(cudaMemsetAsync(deg, 0, (size_t)n * 4, s));
+    GR_CUDA_CHECK(cudaMemsetAsync(nnz_out, 0, 8, s));
+    GR_CUDA_CHECK(cudaMemsetAsync(max_deg_out, 0, 4, s));
+    GR_CUDA_CHECK(cudaMemsetAsync(indptr, 0, (size_t)(n_local + 1) * 4, s));
+    if (total == 0) return GR_OK;
+    if (!user || !item || (n_local_entries > 0 && (!indices || !mult))) return GR_ERR_INVALID;
+    const int64_t t = n_local_entries > 0 ? n_local_entries : 1;
+    char *w = static_cast<char *>(workspace);
+    uint64_t *ka = reinterpret_cast<uint64_t *>(w); w += align256((size_t)t * 8);
+    uint64_t *kb = reinterpret_cast<uint64_t *>(w); w += align256((size_t)t * 8);
+    uint32_t *flags = reinterpret_cast<uint32_t *>(w); w += align256((size_t)t * 4);
+    void *sort_ws = w; w += align256(radix_sort_workspace_bytes(t));
+    void *scan_ws = w; w += align256(scan_workspace_bytes(t));
+    unsigned long long *counter = reinterpret_cast<unsigned long long *>(w);
+    GR_CUDA_CHECK(cudaMemsetAsync(counter, 0, 8, s));
+
+    const int col_bits = bits_for((uint64_t)(n > 0 ? n - 1 : 0));
+    const int row_bits = bits_for((uint64_t)(n_local > 0 ? n_local - 1 : 0));
+    pair_keys_local_kernel<<<grid_for(total, 256), 256, 0, s>>>(user, item, n_pairs, n_users, n_items, self_loop,
+                                                                col_bits, world, rank, ka, counter, n_local_entries, deg,
+                                                                status);
+    GR_LAUNCH_CHECK();
+    max_deg_kernel<<<grid_for(n, 256), 256, 0, s>>>(deg, n, max_deg_out);
+    GR_LAUNCH_CHECK();
+    if (n_local_entries == 0) return GR_OK;
+    bool in_a = true;
+    int rc = radix_sort_u64(ka, kb, nullptr, nullptr, n_local_entries, 0, col_bits + row_bits, sort_ws,
+                            align256(radix_sort_workspace_bytes(t)), &in_a, s);
+    if (rc != GR_OK) return rc;
+    const uint64_t *sorted = in_a ? ka : kb;
+    unique_flags_kernel<<<grid_for(n_local_entries, 256), 256, 0, s>>>(sorted, n_local_entries, flags);
+    GR_LAUNCH_CHECK();
+    rc = exclusive_scan_u32(flags, n_local_entries, scan_ws, s);
+    if (rc != GR_OK) return rc;
+    unique_emit_local_kernel<<<grid_for(n_local_entries, 256), 256, 0, s>>>(
+        sorted, flags, n_local_entries, col_bits, n_local, world, block_rows, indptr, indices, mult,
+        reinterpret_cast<long long *>(nnz_out));
+    GR_LAUNCH_CHECK();
+    return GR_OK;
+}
+
+extern "C" int gr_csr_normalize_local(const int32_t *indptr, const int32_t *indices, const float *mult,
+                                      const int32_t *deg, const float *lut, int64_t lut_len, int64_t n_local_rows,
+                                      int64_t nnz, int32_t mode, int32_t world, int32_t rank, int64_t block_rows,
+                                      float *vals, int32_t *status, void *stream) {
+    if (nnz < 0 || n_local_rows < 0 || mode < 0 || mode > 2 || world <= 0 || rank < 0 || rank >= world ||
+        block_rows <= 0 || !status)
+        return GR_ERR_INVALID;
+    if (nnz == 0) return GR_OK;
+    if (!indptr || !indices || !mult || !deg || !vals || (mode != 2 && (!lut || lut_len <= 0))) return GR_ERR_INVALID;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    normalize_local_kernel<<<grid_for(nnz, 256), 256, 0, s>>>(indptr, indices, mult, deg, lut, lut_len, n_local_rows, nnz,
+                                                              mode, world, rank, block_rows, vals, status);
+    GR_LAUNCH_CHECK();
+    return GR_OK;
+}

@@ -38,6 +38,17 @@ class RowPartition:
         self.block_rows = max(4, (rows + 3) // 4 * 4)        # common padded block height H
         self.padded_rows = self.block_rows * self.world_size
 
+    @classmethod
+    def for_nodes(cls, n_nodes: int, world_size: int) -> "RowPartition":
+        """Partition of an [n_nodes, n_nodes] matrix that has not been built (see build_local_csr)."""
+        self = cls.__new__(cls)
+        self.n = int(n_nodes)
+        self.world_size = int(world_size)
+        rows = -(-self.n // self.world_size)
+        self.block_rows = max(4, (rows + 3) // 4 * 4)
+        self.padded_rows = self.block_rows * self.world_size
+        return self
+
     def n_local(self, rank: int) -> int:
         return len(range(rank, self.n, self.world_size))
 
@@ -65,6 +76,65 @@ class RowPartition:
         vals = full.vals[src].contiguous()
         return NormAdjCSR(indptr.to(torch.int32), indices, vals, int(rows.numel()), self.padded_rows,
                           long_threshold=full.long_threshold)
+
+
+def build_local_csr(part: RowPartition, rank: int, user, item, n_users: int, n_items: int,
+                    normalization: str = "symmetric", self_loop: bool = False, device="cuda",
+                    dis_lut: Optional[np.ndarray] = None, long_threshold: Optional[int] = None) -> NormAdjCSR:
+    """Partitioned graph build: this rank's rows of Â straight from the (user,item) pairs,
+    without materialising the full matrix.  Equal, bit for bit, to ``part.local_csr(NormAdjCSR.from_pairs(..), rank)``
+    (same entries, same order inside a row, same values from the global degrees)."""
+    from ._lib import check, lib, ptr, stream_ptr
+    from .graph_builder import _NORM_MODES, _require_cuda, degree_lut
+
+    if normalization not in _NORM_MODES:
+        raise ValueError(f"Неизвестный тип нормализации: {normalization}")
+    device = _require_cuda(device)
+    user = torch.as_tensor(user, dtype=torch.int64).to(device).contiguous()
+    item = torch.as_tensor(item, dtype=torch.int64).to(device).contiguous()
+    if user.numel() != item.numel():
+        raise ValueError("user and item must have the same length")
+    n_pairs, n, G = int(user.numel()), n_users + n_items, part.world_size
+    if n != part.n:
+        raise ValueError("partition was made for a different number of nodes")
+    n_local = part.n_local(rank)
+    n_entries = int(((user % G) == rank).sum() + (((n_users + item) % G) == rank).sum()) + (n_local if self_loop else 0)
+    l = lib()
+    ws_bytes = l.gr_build_local_csr_workspace_bytes(n_entries)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
+    indptr = torch.empty(n_local + 1, dtype=torch.int32, device=device)
+    indices = torch.empty(max(n_entries, 1), dtype=torch.int32, device=device)
+    mult = torch.empty(max(n_entries, 1), dtype=torch.float32, device=device)
+    deg = torch.empty(n, dtype=torch.int32, device=device)
+    nnz_d = torch.zeros(1, dtype=torch.int64, device=device)
+    maxdeg_d = torch.zeros(1, dtype=torch.int32, device=device)
+    status = torch.zeros(1, dtype=torch.int32, device=device)
+    with torch.cuda.device(device):
+        check(l.gr_build_local_csr_pattern(ptr(user), ptr(item), n_pairs, n_users, n_items, int(self_loop), G, rank,
+                                           part.block_rows, n_entries, ptr(indptr), ptr(indices), ptr(mult), ptr(deg),
+                                           ptr(nnz_d), ptr(maxdeg_d), ptr(status), ptr(ws), ws_bytes, stream_ptr()),
+              "gr_build_local_csr_pattern")
+        nnz, max_deg, st = int(nnz_d.item()), int(maxdeg_d.item()), int(status.item())
+        if st & 2:
+            raise ValueError("user/item id out of range")
+        if st & 8:
+            raise _lib.GrError("local entry count mismatch")
+        del ws
+        mode = _NORM_MODES[normalization]
+        if dis_lut is None:
+            dis_lut = degree_lut(max_deg, -0.5 if mode == 0 else -1.0)
+        if len(dis_lut) <= max_deg and mode != 2:
+            raise ValueError(f"dis_lut has {len(dis_lut)} entries, max degree is {max_deg}")
+        lut = torch.from_numpy(np.ascontiguousarray(dis_lut, dtype=np.float32)).to(device)
+        indices = indices[:nnz].clone()
+        vals = torch.empty(nnz, dtype=torch.float32, device=device)
+        check(l.gr_csr_normalize_local(ptr(indptr), ptr(indices), ptr(mult), ptr(deg), ptr(lut), int(lut.numel()),
+                                       n_local, nnz, mode, G, rank, part.block_rows, ptr(vals), ptr(status),
+                                       stream_ptr()), "gr_csr_normalize_local")
+        if int(status.item()) & 4:
+            raise _lib.GrError("degree exceeds the look-up table")
+    kw = {} if long_threshold is None else {"long_threshold": long_threshold}
+    return NormAdjCSR(indptr, indices, vals, n_local, part.padded_rows, **kw)
 
 
 class PeerExchange:

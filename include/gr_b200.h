@@ -207,6 +207,26 @@ int gr_bpr_fused(const float *emb, int64_t ld, int64_t n_users, int64_t n_items,
                  const int64_t *pos, const int64_t *neg, int64_t batch, int32_t d, float grad_scale, float *grad,
                  int64_t ldg, float *loss, void *workspace, size_t workspace_bytes, void *stream);
 
+/* Partitioned build (no reference counterpart): the rows rank, rank+world, ... of the
+ * same matrix gr_build_csr_pattern + gr_csr_normalize produce, straight from the (user,item) pairs, for
+ * the cyclic row distribution of the multi-GPU propagation.  Every rank passes ALL pairs (the degrees are
+ * global); only the directed entries of its own rows are kept, sorted and merged.  Local row j is global
+ * row rank + j*world; column ids leave in the owner-major padded numbering of the exchange buffers,
+ * (c % world) * block_rows + c / world, while the order inside a row stays ascending GLOBAL column (the
+ * single-GPU chain order), so the partitioned propagation stays bit-identical.  n_local_entries: the
+ * exact number of directed entries (with duplicates, with self loops) whose row this rank owns - the
+ * caller counts it; status bit 3 flags a wrong count.  deg: [n_users + n_items] global degrees (output).
+ * gr_csr_normalize_local forms the values from the global degrees with the same LUT rule. */
+size_t gr_build_local_csr_workspace_bytes(int64_t n_local_entries);
+int gr_build_local_csr_pattern(const int64_t *user, const int64_t *item, int64_t n_pairs, int64_t n_users,
+                               int64_t n_items, int32_t self_loop, int32_t world, int32_t rank, int64_t block_rows,
+                               int64_t n_local_entries, int32_t *indptr, int32_t *indices, float *mult, int32_t *deg,
+                               int64_t *nnz_out, int32_t *max_deg_out, int32_t *status, void *workspace,
+                               size_t workspace_bytes, void *stream);
+int gr_csr_normalize_local(const int32_t *indptr, const int32_t *indices, const float *mult, const int32_t *deg,
+                           const float *lut, int64_t lut_len, int64_t n_local_rows, int64_t nnz, int32_t mode,
+                           int32_t world, int32_t rank, int64_t block_rows, float *vals, int32_t *status, void *stream);
+
 /* Replaces the per-user temporal split (src/data/dataset.py:327-357: `sort_values(['userId','timestamp'])`,
  * then per user the last row -> test (users with >= 2 rows), the second-last -> valid (users with
  * >= 3 rows), the rest -> train).  user / item / timestamp: [n] int64 device arrays; ts_min / ts_max:

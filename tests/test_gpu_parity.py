@@ -326,3 +326,27 @@ def test_full_size_dataset_shapes_vs_oracle(shape):
     stats = {}
     tc = g.full_rank_topk(x[:nu], x[nu:], eu, ip, it, 20, tensor_cores=True, stats=stats)
     assert stats["tensor_cores"] and torch.equal(tc, exact), shape
+
+
+# ----------------------------------------------------------------------------- partitioned graph build
+@pytest.mark.parametrize("shape,world,self_loop", [("tiny", 2, False), ("tiny", 3, True), ("C1", 4, False), ("C1", 8, False)])
+def test_partitioned_graph_build_equals_rows_of_the_full_build(shape, world, self_loop):
+    """gr_build_local_csr_pattern + gr_csr_normalize_local: every rank's rows straight from the pairs ==
+    the same rows cut out of the full single-GPU matrix, bit for bit (entries, order inside a row, values),
+    incl. duplicate pairs; then the partitioned propagation on those matrices == the single-GPU result."""
+    from gnn_recommendations_b200.dist import RowPartition, build_local_csr
+    from gnn_recommendations_b200.synthetic import synth_split
+    sp = synth_split(shape, 42)
+    nu, ni = sp["n_users"], sp["n_items"]
+    tu, ti = sp["train"]
+    tu, ti = np.concatenate([tu, tu[:50]]), np.concatenate([ti, ti[:50]])      # duplicates are summed
+    full = g.NormAdjCSR.from_pairs(tu, ti, nu, ni, self_loop=self_loop, device=DEV)
+    part = RowPartition.for_nodes(nu + ni, world)
+    assert part.block_rows == RowPartition(full.indptr, world).block_rows
+    for rank in range(world):
+        want = part.local_csr(full, rank)
+        got = build_local_csr(part, rank, tu, ti, nu, ni, self_loop=self_loop, device=DEV)
+        assert torch.equal(got.indptr, want.indptr), (shape, world, rank)
+        assert torch.equal(got.indices, want.indices), (shape, world, rank)
+        assert torch.equal(got.vals.view(torch.int32), want.vals.view(torch.int32)), (shape, world, rank)
+        assert (got.n_rows, got.n_cols) == (want.n_rows, want.n_cols)
