@@ -14,6 +14,7 @@ from .ngcf import NGCF, NGCFLayer  # noqa: F401
 from .gat import GAT, GATLayer  # noqa: F401
 from .orthogonal_bundle import BundleConnectionLayer, GroupShuffleLayer, OrthogonalBundleGNN  # noqa: F401
 from .ultragcn import UltraGCN  # noqa: F401
+from .kgtore import KGTORe  # noqa: F401
 from .dataset import InteractionDataset, temporal_split_device  # noqa: F401
 from .evaluator import Evaluator, full_rank_topk  # noqa: F401
 from .losses import BPRLoss, bpr_fused  # noqa: F401
@@ -24,7 +25,7 @@ from .trainer import Trainer  # noqa: F401
 
 # name -> class, as scripts/run_all_experiments.py:38-45 registers them (the plug-in point of the
 # reference's driver: create_model() looks the class up here and filters YAML kwargs by signature)
-MODEL_REGISTRY = {"lightgcn": LightGCN, "ngcf": NGCF, "gat": GAT, "ultragcn": UltraGCN,
-                  "orthogonal_bundle": OrthogonalBundleGNN}      # "kgtore" is not provided
+MODEL_REGISTRY = {"lightgcn": LightGCN, "ngcf": NGCF, "gat": GAT, "ultragcn": UltraGCN, "kgtore": KGTORe,
+                  "orthogonal_bundle": OrthogonalBundleGNN}
 
 __version__ = "0.1.0"

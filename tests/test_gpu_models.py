@@ -112,3 +112,40 @@ def test_rowmap_kernel_vs_torch():
         close(got1.cpu().numpy(), (x1.double() @ wa.double()).cpu().numpy())
     x, w = torch.randn(300, 128, generator=gen).to(DEV), torch.randn(128, 256, generator=gen).to(DEV)
     close(rowmap(x, w).cpu().numpy(), (x.double() @ w.double()).cpu().numpy())
+
+
+# ----------------------------------------------------------------------------- KGTORe
+def test_kgtore_matches_reference_golden(tiny):
+    """Same-seed parameters bit-equal; eval-mode forward, predict and every parameter gradient vs the
+    unmodified reference (tests/golden/make_golden_kgtore.py; kgtore.py:170-394)."""
+    import os
+    z = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "kgtore.npz")))
+    nu, ni = int(tiny["n_users"]), int(tiny["n_items"])
+    torch.manual_seed(42)
+    m = g.KGTORe(nu, ni, embedding_dim=64, kg_embedding_dim=32, tree_depth=3, n_layers=2, dropout=0.1, init_scale=0.1)
+    sd = m.state_dict()
+    assert set(sd) == {k[5:] for k in z if k.startswith("init/")}
+    for k, v in sd.items():
+        assert np.array_equal(v.numpy(), z[f"init/{k}"]), k           # constructor RNG order == reference's
+    assert m.get_parameters_count() == int(z["n_params"])
+    m = m.to(DEV).eval()
+    csr = g.NormAdjCSR.from_pairs(tiny["train_u"], tiny["train_i"], nu, ni, device=DEV)
+    ue, ie = m(csr)
+    np.testing.assert_allclose(ue.detach().cpu().numpy(), z["user_emb"], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(ie.detach().cpu().numpy(), z["item_emb"], rtol=1e-5, atol=1e-7)
+    users, items = torch.from_numpy(z["users"]).to(DEV), torch.from_numpy(z["items"]).to(DEV)
+    scores = m.predict(users, items, csr)
+    np.testing.assert_allclose(scores.detach().cpu().numpy(), z["scores"], rtol=1e-5, atol=1e-7)
+    loss = (scores ** 2).sum() + ue.abs().mean()
+    m.zero_grad()
+    loss.backward()
+    assert abs(float(loss) - float(z["loss"])) <= 1e-5 * abs(float(z["loss"]))
+    for k, p in m.named_parameters():
+        want = z[f"grad/{k}"]
+        if want.size == 0:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
+            continue
+        np.testing.assert_allclose(p.grad.cpu().numpy(), want, rtol=2e-4, atol=2e-4 * float(np.abs(want).max()) + 1e-9, err_msg=k)
+    with pytest.raises(ValueError):
+        m.get_all_embeddings(None)
+    assert g.MODEL_REGISTRY["kgtore"] is g.KGTORe
