@@ -6,15 +6,18 @@
 // reference's CPU torch.sparse.mm uses (lightgcn.py:88), so the result is bit-identical.
 // Parallelism therefore comes from rows and features only, never from splitting a row's
 // entries:
-//   * short rows: one row per sub-warp (d/4 lanes, one float4 per lane), 8 independent
-//     128-bit gathers in flight per lane, (col,val) pairs loaded coalesced once per 8..32
-//     entries and broadcast with shuffles, next chunk prefetched;
-//   * long ("hot item") rows: one CTA per row; all 8 warps stream the gathered x rows into
-//     an 8-stage shared-memory ring with cp.async (up to 112 KB in flight per SM), d/32
-//     consumer warps run the chain out of shared memory, one feature per lane.
-// Rows arrive sorted by descending length (gr_row_schedule) so the hardware CTA scheduler
-// performs longest-processing-time-first list scheduling; the hot rows start first on a
-// high-priority side stream and overlap the short-row kernel.
+//   * short rows (spmm_stream_rows): groups of consecutive rows (~256-512 entries) per sub-warp of
+//     d/4 lanes, walked as one continuous entry stream: (col,val) chunks loaded coalesced and
+//     shuffle-broadcast, 8 independent 128-bit gathers in flight per lane across row boundaries;
+//   * long ("hot item") rows (spmm_long_rows / spmm_long_rows_bar, >= 1024 entries): persistent CTAs
+//     take rows longest-first from a ticket counter; producer warps stream the gathered x rows into
+//     a shared-memory ring with cp.async, d/32 consumer warps run the chain out of shared memory,
+//     one feature per lane.  They run on a high-priority side stream and overlap the short-row kernel.
+//   * rows beyond 131 072 entries are cut into 65 536-entry segments whose partial chains are added
+//     in segment order (spmm_combine_parts) — deterministic, identical on 1 and N GPUs.
+// The epilogue of every kernel can also store the finished row into the layer buffers of the other
+// ranks (NVLink P2P stores or one NVSwitch multicast store): the all-gather of the row-partitioned
+// propagation is fused into the SpMM.
 #include <cstdlib>
 #include <mutex>
 
