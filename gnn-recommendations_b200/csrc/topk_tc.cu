@@ -11,10 +11,12 @@
 // can enter or tie into the top-K.  Users for which the proof fails are flagged and re-ranked by the
 // exact kernel; results are therefore always bit-identical to the exact path.
 //
-// One CTA = 128 eval users (UMMA M = 128) against all items in tiles of 128 (UMMA N = 128):
+// One CTA = 128 eval users (UMMA M = 128) against one item range (blockIdx.y; 1-4 ranges per user tile fill
+// the SMs evenly) in tiles of 128 items (UMMA N = 128):
 //   warps 0-3  producers : item tile fp32 rows -> shared memory in the K-major SWIZZLE_128B
 //                          canonical layout (32 tf32 per 128-byte row, 8-row atoms, 16-byte chunks
-//                          XOR-swizzled), fence.proxy.async, mbarrier arrive; 2-stage ring
+//                          XOR-swizzled), fence.proxy.async, mbarrier arrive; one stage (two CTAs
+//                          per SM cover each other's load latency)
 //   warp  8    MMA       : one elected lane issues d/8 tcgen05.mma (K = 8 per instruction) per tile
 //                          into one of two 128-column TMEM accumulators, tcgen05.commit to mbarriers
 //   warps 4-7  epilogue  : tcgen05.ld 32 columns at a time; thread = TMEM lane = one user: seen-item
