@@ -838,8 +838,13 @@ static int launch(const SpmmArgs &base, int n_long, long long n_rows, int slot, 
             GR_CUDA_CHECK(cudaFuncSetAttribute(k_mc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
             side->smem_attr_set[slot] = true;
         }
-        GR_CUDA_CHECK(cudaEventRecord(side->fork, stream));
-        GR_CUDA_CHECK(cudaStreamWaitEvent(side->stream, side->fork, 0));
+        // GR_LONG_SERIAL=1: long rows first on the caller's stream instead of concurrently on the side stream
+        static const bool serial_long = [] { const char *e = getenv("GR_LONG_SERIAL"); return e && atoi(e) != 0; }();
+        cudaStream_t ls = serial_long ? stream : side->stream;
+        if (!serial_long) {
+            GR_CUDA_CHECK(cudaEventRecord(side->fork, stream));
+            GR_CUDA_CHECK(cudaStreamWaitEvent(side->stream, side->fork, 0));
+        }
         SpmmArgs la = base;
         la.order_begin = 0;
         la.order_end = n_long;
@@ -848,17 +853,17 @@ static int launch(const SpmmArgs &base, int n_long, long long n_rows, int slot, 
         if (long_ctas > n_work) long_ctas = n_work;
         if (long_ctas < 1) long_ctas = 1;
         if (la.n_peers > 0 && la.peer_multicast)
-            k_mc<<<long_ctas, kThreads, kSmem, side->stream>>>(la);
+            k_mc<<<long_ctas, kThreads, kSmem, ls>>>(la);
         else if (la.n_peers > 0)
-            k_p2p<<<long_ctas, kThreads, kSmem, side->stream>>>(la);
+            k_p2p<<<long_ctas, kThreads, kSmem, ls>>>(la);
         else
-            k_none<<<long_ctas, kThreads, kSmem, side->stream>>>(la);
+            k_none<<<long_ctas, kThreads, kSmem, ls>>>(la);
         GR_LAUNCH_CHECK();
         if (la.items && la.n_split > 0) {
-            spmm_combine_parts<<<la.n_split, 128, 0, side->stream>>>(la, D);
+            spmm_combine_parts<<<la.n_split, 128, 0, ls>>>(la, D);
             GR_LAUNCH_CHECK();
         }
-        GR_CUDA_CHECK(cudaEventRecord(side->join, side->stream));
+        if (!serial_long) GR_CUDA_CHECK(cudaEventRecord(side->join, side->stream));
     }
     const long long rest = n_rows - (use_long ? n_long : 0);
     if (base.group_ptr != nullptr) {
@@ -886,7 +891,10 @@ static int launch(const SpmmArgs &base, int n_long, long long n_rows, int slot, 
         spmm_warp_rows<D><<<(unsigned)ctas, kWarpsPerCta * 32, 0, stream>>>(wa);
         GR_LAUNCH_CHECK();
     }
-    if (use_long) GR_CUDA_CHECK(cudaStreamWaitEvent(stream, side->join, 0));
+    if (use_long) {
+        static const bool serial_long = [] { const char *e = getenv("GR_LONG_SERIAL"); return e && atoi(e) != 0; }();
+        if (!serial_long) GR_CUDA_CHECK(cudaStreamWaitEvent(stream, side->join, 0));
+    }
     return GR_OK;
 }
 
