@@ -415,11 +415,9 @@ class ShardedLightGCN:
             self.weight.grad = grad
             if self.max_grad_norm > 0:
                 sq = self._all_reduce(grad.double().pow(2).sum().view(1))
-                coef = self.max_grad_norm / (float(sq.sqrt()) + 1e-6)
+                coef = self.max_grad_norm / (float(sq.sqrt()) + 1e-6)      # clip_grad_norm_: clamped to 1
                 if coef < 1.0:
                     grad.mul_(coef)
-                else:
-                    grad.mul_(1.0)
             if self.fused_optimizer and grad.is_cuda:
                 from .optim import fused_clip_adam_step
 
