@@ -55,7 +55,9 @@ struct TcArgs {
     float *cand_scores;  // [n_eval][gridDim.y][kprime] approximate scores (unsorted)
     int *cand_ids;       // [n_eval][gridDim.y][kprime]
     int *cand_cnt;       // [n_eval][gridDim.y]
-    int debug;           // GR_TC_DEBUG bits (timing experiments): 1 = epilogue skips selection, 2 = producers skip loads
+    int *error;          // device flag: 1 = the kernel could not run (re-scoring flags every row)
+    int debug;           // GR_TC_DEBUG bits (experiments): 1 = epilogue skips selection, 2 = producers skip loads,
+                         // 4 = take the could-not-run path, bits 8.. = producer back-off in ns
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
@@ -204,7 +206,10 @@ __global__ void __launch_bounds__(TC_THREADS, 2) topk_tc_candidates_kernel(const
     // the dynamic window starts at the CTA's (1 KB-granular) allocation.  Checked, not assumed.
     extern __shared__ __align__(1024) unsigned char smem_dyn[];
     unsigned char *smem_raw = smem_dyn;
-    if ((smem_u32(smem_dyn) & 1023u) != 0) __trap();
+    if ((smem_u32(smem_dyn) & 1023u) != 0 || (a.debug & 4)) {   // never seen (debug bit 4 forces it for the test); the re-scoring pass then hands every row to the exact kernel
+        if (threadIdx.x == 0) *a.error = 1;
+        return;
+    }
     const int d = a.d;
     const int nkb = d / TC_KB;                       // k-blocks of 32 tf32
     const uint32_t tile_bytes = TC_M * 128;          // one k-block of a 128-row operand: 16 KB
@@ -395,6 +400,7 @@ struct RescoreArgs {
     int kprime, k, n_seg;
     float eps;
     const float *max_item_norm;  // device scalar
+    const int *error;            // set by the nomination kernel when it could not run
     int64_t *out_ids;
     float *out_scores;
     int *flags;       // [n_eval] 1 = not proven, re-rank exactly
@@ -407,6 +413,13 @@ __global__ void __launch_bounds__(256) topk_rescore_kernel(const RescoreArgs a) 
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (row >= a.n_eval) return;
+    if (*a.error) {                                     // no candidates: every row goes to the exact kernel
+        if (lane == 0) {
+            a.flags[row] = 1;
+            atomicAdd(a.n_flagged, 1);
+        }
+        return;
+    }
     const float *u = a.user_emb + a.eval_users[row] * a.ldu;
     const int K = a.k, KP = a.kprime, S = a.n_seg;
     const int total = S * KP;
@@ -565,7 +578,8 @@ extern "C" int gr_score_topk_tc(const float *user_emb, int64_t ldu, const float 
     int *cand_ids = reinterpret_cast<int *>(cand_scores + (size_t)n_eval * n_seg * kprime);
     int *cand_cnt = cand_ids + (size_t)n_eval * n_seg * kprime;
     float *max_norm = reinterpret_cast<float *>(cand_cnt + (size_t)n_eval * n_seg);
-    GR_CUDA_CHECK(cudaMemsetAsync(max_norm, 0, 4, s));
+    int *tc_error = reinterpret_cast<int *>(max_norm + 1);
+    GR_CUDA_CHECK(cudaMemsetAsync(max_norm, 0, 8, s));      // max norm + error flag
     max_row_norm_kernel<<<sm_count() * 4, 256, 0, s>>>(item_emb, ldi, (int)n_items, d, max_norm);
     GR_LAUNCH_CHECK();
 
@@ -574,7 +588,7 @@ extern "C" int gr_score_topk_tc(const float *user_emb, int64_t ldu, const float 
     a.eval_users = eval_users; a.n_eval = (int)n_eval; a.item_lo = 0; a.item_hi = n_items;
     a.seen_indptr = seen_indptr; a.seen_items = seen_items; a.kprime = kprime;
     a.split_items = split_items;
-    a.cand_scores = cand_scores; a.cand_ids = cand_ids; a.cand_cnt = cand_cnt;
+    a.cand_scores = cand_scores; a.cand_ids = cand_ids; a.cand_cnt = cand_cnt; a.error = tc_error;
     { const char *e = getenv("GR_TC_DEBUG"); a.debug = e ? atoi(e) : 0; }
     const size_t smem = tc_smem_bytes(d, kprime);
     GR_CUDA_CHECK(cudaFuncSetAttribute(topk_tc_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -590,7 +604,7 @@ extern "C" int gr_score_topk_tc(const float *user_emb, int64_t ldu, const float 
     // 2^-9 (1 + 2^-11) of the fp32 one and, by Cauchy-Schwarz, the score within 2^-9 |u| |i|; fp32
     // accumulation adds ~d * 2^-24.  eps = 1.5 * 2^-9 leaves a 50 % margin.
     r.eps = 1.5f / 512.0f;
-    r.max_item_norm = max_norm; r.out_ids = topk_ids; r.out_scores = topk_scores; r.flags = flags; r.n_flagged = n_flagged;
+    r.max_item_norm = max_norm; r.error = tc_error; r.out_ids = topk_ids; r.out_scores = topk_scores; r.flags = flags; r.n_flagged = n_flagged;
     if (n_seg * kprime <= 64) topk_rescore_kernel<2><<<(unsigned)((n_eval + 7) / 8), 256, 0, s>>>(r);
     else topk_rescore_kernel<4><<<(unsigned)((n_eval + 7) / 8), 256, 0, s>>>(r);
     GR_LAUNCH_CHECK();

@@ -439,3 +439,19 @@ def test_trainer_epoch_other_models_vs_reference(name, tiny, tmp_path):
             continue
         moved = np.abs(want - z[f"{name}/init/{k}"]).max()
         np.testing.assert_allclose(v.detach().cpu().numpy(), want, rtol=2e-3, atol=max(5e-6, 0.02 * float(moved)), err_msg=k)
+
+
+def test_topk_tensor_core_kernel_failure_falls_back_to_exact(monkeypatch):
+    """If the nomination kernel cannot run (shared-memory window not 1 KB aligned; forced here with the
+    debug bit) the re-scoring pass flags every row and the exact kernel ranks them: same lists, no trap."""
+    rng = np.random.default_rng(3)
+    ue = rng.standard_normal((200, 64)).astype(np.float32)
+    ie = rng.standard_normal((3000, 64)).astype(np.float32)
+    eu = np.arange(200)
+    want = g.full_rank_topk(torch.from_numpy(ue).to(DEV), torch.from_numpy(ie).to(DEV), eu, None, None, 20,
+                            tensor_cores=False)
+    monkeypatch.setenv("GR_TC_DEBUG", "4")
+    stats = {}
+    got = g.full_rank_topk(torch.from_numpy(ue).to(DEV), torch.from_numpy(ie).to(DEV), eu, None, None, 20,
+                           tensor_cores=True, stats=stats)
+    assert stats["rows_reranked_exactly"] == 200 and torch.equal(got, want)
