@@ -455,3 +455,40 @@ def test_topk_tensor_core_kernel_failure_falls_back_to_exact(monkeypatch):
     got = g.full_rank_topk(torch.from_numpy(ue).to(DEV), torch.from_numpy(ie).to(DEV), eu, None, None, 20,
                            tensor_cores=True, stats=stats)
     assert stats["rows_reranked_exactly"] == 200 and torch.equal(got, want)
+
+
+def test_trainer_full_loop_vs_reference(tiny, tmp_path):
+    """`Trainer.train()` (trainer.py:469-579): 2-epoch linear warm-up, cosine schedule, validation every
+    epoch, early-stopping bookkeeping — 4 epochs of LightGCN from the same seeds as the reference run
+    (tests/golden/make_golden_trainloop.py)."""
+    import os
+    z = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "trainloop.npz")))
+    ds = dataset_from(tiny)
+    cfg = {"learning_rate": 5e-3, "weight_decay": 1e-4, "batch_size": 512, "epochs": 4, "eval_every": 1,
+           "use_scheduler": True, "warmup_epochs": 2, "max_grad_norm": 1.0, "negative_samples": 1,
+           "validation_metrics": ["recall@10", "ndcg@10", "recall@20"], "early_stopping_metric": "recall@10",
+           "early_stopping": {"patience": 3, "min_delta": 0.0001}, "model_name": "lightgcn_golden",
+           "checkpoint_dir": str(tmp_path / "ckpt")}
+    torch.manual_seed(42)
+    m = g.LightGCN(int(tiny["n_users"]), int(tiny["n_items"]), embedding_dim=64, n_layers=3, init_scale=0.1)
+    tr = g.Trainer(m, ds, cfg, device=torch.device(DEV))
+    lrs, orig = [], tr.train_epoch
+
+    def spy():
+        lrs.append(tr.optimizer.param_groups[0]["lr"])
+        return orig()
+
+    tr.train_epoch = spy
+    torch.manual_seed(123)
+    res = tr.train()
+    np.testing.assert_allclose(lrs, z["lrs"], rtol=1e-12)
+    np.testing.assert_allclose(res["train_losses"], z["train_losses"], rtol=2e-5)
+    np.testing.assert_allclose(m.user_embedding.weight.detach().cpu().numpy(), z["user_w"], rtol=2e-3, atol=2e-5)
+    np.testing.assert_allclose(m.item_embedding.weight.detach().cpu().numpy(), z["item_w"], rtol=2e-3, atol=2e-5)
+    assert len(res["valid_metrics"]) == 4
+    n_eval = len(np.unique(tiny["valid_u"]))
+    for ep, vm in enumerate(res["valid_metrics"]):
+        for k, v in vm.items():                     # weights agree to ~1e-5, so at most a near-tie may flip
+            assert abs(v - float(z[f"valid/{ep}/{k}"])) <= 2.0 / n_eval, (ep, k, v)
+    assert abs(res["best_metric"] - float(z["best_metric"])) <= 2.0 / n_eval
+    assert (tmp_path / "ckpt").exists() and any((tmp_path / "ckpt").iterdir())
