@@ -492,3 +492,40 @@ def test_trainer_full_loop_vs_reference(tiny, tmp_path):
             assert abs(v - float(z[f"valid/{ep}/{k}"])) <= 2.0 / n_eval, (ep, k, v)
     assert abs(res["best_metric"] - float(z["best_metric"])) <= 2.0 / n_eval
     assert (tmp_path / "ckpt").exists() and any((tmp_path / "ckpt").iterdir())
+
+
+def test_export_embeddings_and_warm_start_round_trip(tiny, tmp_path):
+    """trainer.py:362-468: the exported payload holds the PROPAGATED embeddings (not the raw tables) under
+    the reference's keys, and warm-start copies them into user/item_embedding.weight; `apply_to` filters
+    by model name; a shape mismatch raises."""
+    ds = dataset_from(tiny)
+    nu, ni = int(tiny["n_users"]), int(tiny["n_items"])
+    path = tmp_path / "emb" / "lightgcn_tiny.pt"
+    cfg = dict(CFG, epochs=1, checkpoint_dir=str(tmp_path / "ckpt"), model_name="lightgcn", dataset_name="tiny",
+               export_embeddings={"enabled": True, "apply_to": "lightgcn", "path": str(path)})
+    torch.manual_seed(42)
+    m = g.LightGCN(nu, ni, embedding_dim=64, n_layers=3, init_scale=0.1)
+    tr = g.Trainer(m, ds, cfg, device=torch.device(DEV))
+    torch.manual_seed(123)
+    tr.train()
+    payload = torch.load(path)
+    assert set(payload) == {"user_embedding", "item_embedding", "source_model", "dataset", "embedding_dim", "n_users", "n_items"}
+    assert (payload["source_model"], payload["dataset"], payload["embedding_dim"], payload["n_users"], payload["n_items"]) == \
+        ("lightgcn", "tiny", 64, nu, ni)
+    with torch.no_grad():
+        ue, ie = m.get_all_embeddings(ds.get_torch_adjacency())
+    assert torch.equal(payload["user_embedding"], ue.cpu()) and torch.equal(payload["item_embedding"], ie.cpu())
+    assert not torch.equal(payload["user_embedding"], m.user_embedding.weight.detach().cpu())
+    # warm start into another model family
+    ws = {"enabled": True, "apply_to": "orthogonal_bundle", "embeddings_path": str(path)}
+    m2 = g.OrthogonalBundleGNN(nu, ni, embedding_dim=64)
+    g.Trainer(m2, ds, dict(CFG, checkpoint_dir=str(tmp_path / "c2"), model_name="orthogonal_bundle", warm_start=ws),
+              device=torch.device(DEV))
+    assert torch.equal(m2.user_embedding.weight.detach().cpu(), payload["user_embedding"])
+    m3 = g.NGCF(nu, ni, embedding_dim=64)
+    before = m3.user_embedding.weight.detach().clone()
+    g.Trainer(m3, ds, dict(CFG, checkpoint_dir=str(tmp_path / "c3"), model_name="ngcf", warm_start=ws), device=torch.device(DEV))
+    assert torch.equal(m3.user_embedding.weight.detach().cpu(), before)          # apply_to filtered it out
+    with pytest.raises(ValueError):
+        g.Trainer(g.LightGCN(nu, ni, embedding_dim=32), ds,
+                  dict(CFG, checkpoint_dir=str(tmp_path / "c4"), warm_start=dict(ws, apply_to=None)), device=torch.device(DEV))
