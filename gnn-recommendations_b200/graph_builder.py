@@ -20,7 +20,7 @@ import torch
 from . import _lib
 from ._lib import check, lib, ptr, stream_ptr
 
-LONG_ROW_THRESHOLD = int(os.environ.get("GR_LONG_ROW_THRESHOLD", "1024"))
+LONG_ROW_THRESHOLD = int(os.environ.get("GR_LONG_ROW_THRESHOLD", "0"))   # 0 = choose by graph size
 GROUP_NNZ = int(os.environ.get("GR_GROUP_NNZ", "0"))      # 0 = choose by graph size
 # Rows above SPLIT_ROW_THRESHOLD entries are cut into SPLIT_ROW_SEGMENT-entry segments processed by
 # different CTAs (partials added in segment order).  No dataset shape of the reference has such a
@@ -59,7 +59,12 @@ class NormAdjCSR:
         self._part_buf = {}
         self.timings = None      # set to a list to collect (start, end) CUDA events per SpMM launch
         self.launches = 0        # kernels launched by spmm() so far
-        self.long_threshold = LONG_ROW_THRESHOLD if long_threshold is None else int(long_threshold)
+        if long_threshold is not None:
+            self.long_threshold = int(long_threshold)
+        elif LONG_ROW_THRESHOLD > 0:
+            self.long_threshold = LONG_ROW_THRESHOLD
+        else:   # measured (B200): ML-1M shape 768 > 1024 by 9 %; Amazon-Book shape and larger: 1024
+            self.long_threshold = 768 if self.nnz < (1 << 22) else 1024
         self._schedule()
 
     # ---- reference-API conveniences -----------------------------------------------------
