@@ -154,12 +154,25 @@ def run_reference(args):
         "impl": "reference", "metric": "lightgcn_propagation_edges_per_s", "value": value, "unit": "edges/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.workload, args.gpus),
+        "config": reference_config(args.workload, sample, args.gpus),
         "cpu_baseline": {"value": value, "unit": "edges/s", "cores": torch.get_num_threads(), "kind": "port",
                          "sample": desc},
         "e2e": {"value": value, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+def reference_config(name, sample, n_gpus):
+    """The reference arm runs a bounded SAMPLE of the b200 arm's workload on the host cores: say so in
+    config.workload itself (edges/s is size-normalised)."""
+    cfg = workload_config(sample, 1)
+    if sample != name:
+        nu, ni, e, d, L = WORKLOADS[name]
+        cfg["workload"] = (f"{cfg['workload']} — the bounded 1/{e // WORKLOADS[sample][2]}-scale CPU sample of the "
+                           f"b200 arm's workload {name} ({nu} users x {ni} items, {e} edges, d={d}, L={L})")
+    cfg["partition"] = "host cores (CPU port of the reference's LightGCN.forward), rank 0 only"
+    cfg["b200_arm_workload"] = workload_config(name, n_gpus)["workload"]
+    return cfg
 
 
 def workload_config(name, n_gpus):
@@ -315,101 +328,132 @@ def run_b200(args):
                 "avg_launch_ms": avg_kernel_ms, "launches_timed": len(kernel_ms),
                 "kernel_share_of_step": sum(kernel_ms) / (ms_step * args.steps)}
 
-    # ---- e2e: evaluator.py:76-80 as a user runs it — adjacency arrives as the reference's torch
-    # COO in pinned host memory, is uploaded, converted and propagated; embeddings return to host
+    # ---- e2e: the propagation as a user with a HOST-resident graph runs it — every step uploads the
+    # adjacency (32-bit CSR in pinned host memory: 8 B per entry; what NormAdjCSR.to_host() / a scipy CSR
+    # holds), builds the row schedule, propagates and returns the embeddings to pinned host memory.
+    # Same schedule at every N (each rank moves its own row block and its own output rows).
     e2e = None
     if not args.no_e2e:
-        rows_h = csr.row_ids().to(torch.int64)
-        cols_h = csr.indices.to(torch.int64)
-        idx_host = torch.empty((2, csr.nnz), dtype=torch.int64, pin_memory=True)
-        idx_host[0].copy_(rows_h)
-        idx_host[1].copy_(cols_h)
-        del rows_h, cols_h
-        val_host = torch.empty(csr.nnz, dtype=torch.float32, pin_memory=True)
-        val_host.copy_(csr.vals)
+        ip_h, ix_h, vl_h = csr.to_host(pin=True)
         out_host = torch.empty((n_rows_local, d), dtype=torch.float32, pin_memory=True)
-        shape = (csr.n_rows, csr.n_cols)
+        n_cols, thr = csr.n_cols, csr.long_threshold
+        h2d_bytes = int(ip_h.numel() * 4 + ix_h.numel() * 4 + vl_h.numel() * 4)
         torch.cuda.empty_cache()
 
-        def e2e_step():
-            idx_d = idx_host.to(dev, non_blocking=True)
-            val_d = val_host.to(dev, non_blocking=True)
-            adj = torch.sparse_coo_tensor(idx_d, val_d, shape, check_invariants=False)
-            loc = g.NormAdjCSR.from_torch_coo(adj)        # what as_csr() does on a cache miss
+        def propagate_on(loc):
             if world == 1:
                 with torch.no_grad():
-                    ue, ie = model.get_all_embeddings(loc)
-                out_host[:nu].copy_(ue, non_blocking=True)
-                out_host[nu:].copy_(ie, non_blocking=True)
-            else:
-                out = (lightgcn_propagate_fused(loc, exchange, x0_local, L) if exchange is not None
-                       else lightgcn_propagate_sharded(loc, part, rank, x0_local, L))
-                out_host.copy_(out, non_blocking=True)
+                    return model.propagate(loc)
+            return (lightgcn_propagate_fused(loc, exchange, x0_local, L) if exchange is not None
+                    else lightgcn_propagate_sharded(loc, part, rank, x0_local, L))
+
+        def e2e_step():
+            loc = g.NormAdjCSR(ip_h.to(dev, non_blocking=True), ix_h.to(dev, non_blocking=True),
+                               vl_h.to(dev, non_blocking=True), n_rows_local, n_cols, symmetric=True,
+                               long_threshold=thr)
+            with torch.no_grad():
+                out = propagate_on(loc)
+            out_host.copy_(out, non_blocking=True)
             torch.cuda.current_stream().synchronize()
             return float(out_host[0, 0])
 
         ms_serial = timed(e2e_step, args.steps, min(args.warmup, 3))
-        ms_e2e, mode = ms_serial, "one step at a time"
 
-        if world == 1:
-            # The same steps software-pipelined, as a serving loop runs them: the upload of step i+1
-            # (copy stream) and the download of step i-1 (second copy stream) overlap the propagation
-            # of step i.  Every step still uploads its own COO and downloads its own embeddings; one
-            # device COO buffer is enough because the CSR conversion has consumed it (host-synchronous)
-            # before the next upload is enqueued.
-            s_h2d, s_d2h = torch.cuda.Stream(), torch.cuda.Stream()
-            cur = torch.cuda.current_stream()
-            idx_d = torch.empty(idx_host.shape, dtype=torch.int64, device=dev)
-            val_d = torch.empty(val_host.shape, dtype=torch.float32, device=dev)
+        # The same steps software-pipelined, as a serving loop runs them: the upload of step i+1 (copy
+        # stream) and the download of step i-1 (second copy stream) overlap the propagation of step i.
+        # Every step still uploads its own graph and downloads its own embeddings; two device graph
+        # buffers alternate so that an upload never overwrites the graph a propagation is reading.
+        s_h2d, s_d2h = torch.cuda.Stream(), torch.cuda.Stream()
+        cur = torch.cuda.current_stream()
+        bufs = [(torch.empty_like(csr.indptr), torch.empty_like(csr.indices), torch.empty_like(csr.vals))
+                for _ in range(2)]
+        free_ev = [None, None]
+        state = {"i": 0}
 
-            def pipelined_step():
-                with torch.cuda.stream(s_h2d):
-                    idx_d.copy_(idx_host, non_blocking=True)
-                    val_d.copy_(val_host, non_blocking=True)
-                    up = torch.cuda.Event()
-                    up.record(s_h2d)
-                cur.wait_event(up)
-                adj = torch.sparse_coo_tensor(idx_d, val_d, shape, check_invariants=False)
-                loc = g.NormAdjCSR.from_torch_coo(adj)      # synchronises: idx_d / val_d are free again
-                with torch.no_grad():
-                    ue, ie = model.get_all_embeddings(loc)
-                done = torch.cuda.Event()
-                done.record(cur)
-                with torch.cuda.stream(s_d2h):
-                    s_d2h.wait_event(done)
-                    out_host[:nu].copy_(ue, non_blocking=True)
-                    out_host[nu:].copy_(ie, non_blocking=True)
-                ue.record_stream(s_d2h)
-                ie.record_stream(s_d2h)
+        def pipelined_step():
+            k = state["i"] & 1
+            state["i"] += 1
+            ip_d, ix_d, vl_d = bufs[k]
+            with torch.cuda.stream(s_h2d):
+                if free_ev[k] is not None:
+                    s_h2d.wait_event(free_ev[k])          # the propagation that read this buffer has finished
+                ip_d.copy_(ip_h, non_blocking=True)
+                ix_d.copy_(ix_h, non_blocking=True)
+                vl_d.copy_(vl_h, non_blocking=True)
+                up = torch.cuda.Event()
+                up.record(s_h2d)
+            cur.wait_event(up)
+            loc = g.NormAdjCSR(ip_d, ix_d, vl_d, n_rows_local, n_cols, symmetric=True, long_threshold=thr)
+            with torch.no_grad():
+                out = propagate_on(loc)
+            done = torch.cuda.Event()
+            done.record(cur)
+            free_ev[k] = done
+            with torch.cuda.stream(s_d2h):
+                s_d2h.wait_event(done)
+                out_host.copy_(out, non_blocking=True)
+            out.record_stream(s_d2h)
 
-            def drain():
-                cur.wait_stream(s_d2h)
-                cur.wait_stream(s_h2d)
+        def drain():
+            cur.wait_stream(s_d2h)
+            cur.wait_stream(s_h2d)
 
-            for _ in range(min(args.warmup, 3)):
-                pipelined_step()
-            drain()
-            barrier()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(args.steps):
-                pipelined_step()
-            drain()
-            e1.record()
-            barrier()
-            ms_e2e = e0.elapsed_time(e1) / args.steps
-            mode = ("software-pipelined: upload of step i+1 and download of step i-1 on copy streams overlap the "
-                    "propagation of step i; timed over all steps incl. pipeline fill and drain")
-            assert float(out_host[0, 0]) == float(out_host[0, 0])
-            del idx_d, val_d
+        for _ in range(min(args.warmup, 3)):
+            pipelined_step()
+        drain()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            pipelined_step()
+        drain()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1) / args.steps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e = float(t.item())
+        assert float(out_host[0, 0]) == float(out_host[0, 0])
+        del bufs
         e2e = {"value": L * nnz / (ms_e2e * 1e-3), "unit": "edges/s", "ms_per_step": ms_e2e,
-               "h2d_bytes_per_step": int(idx_host.numel() * 8 + val_host.numel() * 4),
-               "d2h_bytes_per_step": int(out_host.numel() * 4),
-               "schedule": mode,
+               "h2d_bytes_per_step": h2d_bytes * world, "d2h_bytes_per_step": int(out_host.numel() * 4) * world,
+               "bytes_are": "summed over all ranks (each rank uploads its row block, downloads its output rows)",
+               "schedule": "software-pipelined at every N: upload of step i+1 and download of step i-1 on copy streams "
+                           "overlap the propagation of step i; timed over all steps incl. pipeline fill and drain",
                "serial_ms_per_step": ms_serial, "serial_value": L * nnz / (ms_serial * 1e-3),
-               "path": "torch COO (int64 indices, f32 values) in pinned host memory -> .to(device) -> "
-                       "model.get_all_embeddings(adj) -> embeddings copied to pinned host memory"}
-        del idx_host, val_host, out_host
+               "path": "32-bit CSR (int32 indptr/indices, f32 values: NormAdjCSR.to_host layout, 8 B per entry) in pinned "
+                       "host memory -> device -> row schedule -> model.propagate(adj) -> embeddings copied to pinned "
+                       "host memory"}
+        del ip_h, ix_h, vl_h
+        # the reference's own delivery format, for comparison (N=1): torch sparse COO with int64 indices
+        # (20 B per entry, graph_builder.py:163-172) -> .to(device) -> as_csr -> propagate -> host
+        if world == 1:
+            rows_h = csr.row_ids().to(torch.int64)
+            idx_host = torch.empty((2, csr.nnz), dtype=torch.int64, pin_memory=True)
+            idx_host[0].copy_(rows_h)
+            idx_host[1].copy_(csr.indices)
+            del rows_h
+            val_host = torch.empty(csr.nnz, dtype=torch.float32, pin_memory=True)
+            val_host.copy_(csr.vals)
+            shape = (csr.n_rows, csr.n_cols)
+
+            def coo_step():
+                adj = torch.sparse_coo_tensor(idx_host.to(dev, non_blocking=True), val_host.to(dev, non_blocking=True),
+                                              shape, check_invariants=False)
+                loc = g.NormAdjCSR.from_torch_coo(adj)        # what as_csr() does on a cache miss
+                del adj
+                with torch.no_grad():
+                    out = model.propagate(loc)
+                out_host.copy_(out, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+
+            ms_coo = timed(coo_step, max(2, args.steps // 3), 1)
+            e2e["torch_coo_int64"] = {"serial_ms_per_step": ms_coo, "serial_value": L * nnz / (ms_coo * 1e-3),
+                                      "h2d_bytes_per_step": int(idx_host.numel() * 8 + val_host.numel() * 4),
+                                      "what": "the reference's delivery format (int64 COO, 20 B per entry), one step at a time"}
+            del idx_host, val_host
+        del out_host
+        torch.cuda.empty_cache()
 
     # ---- CPU baseline beside it (rank 0, N=1 only) ---------------------------------------------
     cpu = None
@@ -425,12 +469,22 @@ def run_b200(args):
                          f"3 full forwards after 1 warm-up, torch CPU torch.sparse.mm (oracle port of "
                          f"lightgcn.py:62-104)"}
 
-    # ---- the rest of the path, small configs (not the headline; N=1 only) -------------------------
+    # ---- the rest of the path (not the headline) ----------------------------------------------------
     extras = None
-    if rank == 0 and world == 1 and not args.no_extras:
+    if world == 1 and not args.no_extras:
+        torch_main = None
+        try:        # stock torch.sparse.mm (cuSPARSE) on the same resident graph and table
+            x0 = torch.cat([model.user_embedding.weight, model.item_embedding.weight]).detach()
+            torch_main = run_torch_gpu_baseline(csr, x0, L, dev)
+            del x0
+        except Exception as err:
+            torch_main = {"error": f"{type(err).__name__}: {str(err)[:200]}"}
         model = csr = full = None
         torch.cuda.empty_cache()
-        extras = run_extras(g, dev)
+        extras = run_extras(g, dev, hbm_peak)
+        extras["torch_gpu"][f"spmm_{args.workload.lower().replace('/', '_')}"] = torch_main
+    elif world > 1 and not args.no_extras:
+        extras = run_extras_multi(g, dev, rank, world, csr, part, exchange, x0_local, nu, ni, L, d, ms_step, kernel_ms)
 
     if rank == 0:
         line = {
@@ -449,14 +503,272 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
-def run_extras(g, dev):
-    """Secondary measurements of the other path stages at the small dataset shapes: full-ranking
-    top-20 evaluation (C4, Amazon-Book shape) and one full training epoch with the reference's
-    semantics — a complete propagation forward + backward per 512-triple step — (C1, ML-1M shape)."""
+def _ev_time(fn, iters, warm=2, flush=None):
+    """Mean ms of fn() over ``iters`` runs (CUDA events on the current stream; optional L2 flush between runs)."""
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    evs = []
+    for _ in range(iters):
+        if flush is not None:
+            flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        evs.append((e0, e1))
+    torch.cuda.synchronize()
+    return float(np.mean([a.elapsed_time(b) for a, b in evs]))
+
+
+def _traffic(key):
+    tpath = os.path.join(REPO, "profiles", "roofline_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            return json.load(f).get(key)
+    return None
+
+
+MODEL_CASES = {
+    # extras key: (shape, model factory name, BASELINE.json config index)
+    "gs_c2": ("C2", "gs", 1),
+    "ngcf_c3": ("C3", "ngcf", 2),
+    "gat_c3": ("C3", "gat", 2),
+}
+
+
+def _model_forward_bytes(name, nnz, n, d=64, L=3, heads=4):
+    """SURVEY.md §8d algorithmic bytes of one eval-mode forward.  SpMM: per edge 8 + 4d, per row 4 + 4d.
+    NGCF / Group-and-Shuffle epilogue (rowmap): 2 rows read + 1 row written per node.  GAT layer: head
+    projection (row in, heads*dh out), node scores (row in, 2*heads out), aggregation per edge 4 (col) +
+    4 (t_j of the head group) * heads + 4 * heads*dh (gathered H row), per row 4 + 4*heads + 4*width_out."""
+    if name in ("ngcf", "gs"):
+        return L * (nnz * (8 + 4 * d) + n * (4 + 4 * d) + 3 * n * 4 * d)
+    total = 0
+    for l in range(L):
+        width = d if l < L - 1 else heads * d           # heads * dh: 4 x 16, last layer 4 x 64
+        w_out = d
+        total += n * 4 * (d + width)                     # projection
+        total += n * 4 * (width + 2 * heads)             # node scores
+        total += nnz * (4 + 4 * heads + 4 * width) + n * (4 + 4 * heads + 4 * w_out)
+    return total
+
+
+def run_model_extras(g, dev, hbm_peak):
+    """BASELINE.json configs[1] (Group-and-Shuffle at the Gowalla shape) and configs[2] (NGCF and GAT at the
+    Yelp2018 shape): eval-mode forward (edges/s, algorithmic-bytes fraction of the HBM peak), one training step
+    (sampler + forward + fused BPR + backward kernels + fused clip/Adam) and the oracle port's CPU forward."""
+    from gnn_recommendations_b200.synthetic import synth_split
+    from oracle import pyoracle as po
+    sys.path.insert(0, os.path.join(REPO, "tests"))
+    out = {}
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    splits = {}
+    for key, (shape, name, cfg_idx) in MODEL_CASES.items():
+        if shape not in splits:
+            splits[shape] = synth_split(shape, 42)
+        sp = splits[shape]
+        nu, ni = sp["n_users"], sp["n_items"]
+        tu, ti = sp["train"]
+        torch.manual_seed(42)
+        model = {"gs": lambda: g.OrthogonalBundleGNN(nu, ni, 64, 3, 8, 0.1, 0.0, 0.01),
+                 "ngcf": lambda: g.NGCF(nu, ni, 64, [64, 64, 64], 0.1, 0.1),
+                 "gat": lambda: g.GAT(nu, ni, 64, 3, 4, 0.1, 0.2, 0.1)}[name]()
+        cpu_params = {k: v.detach().clone() for k, v in model.state_dict().items()}
+        ds = g.InteractionDataset(sp["train"], sp["valid"], sp["test"], nu, ni, device=dev, name=shape)
+        cfg = {"batch_size": 512, "learning_rate": 1e-3, "weight_decay": 1e-4, "use_scheduler": False,
+               "checkpoint_dir": "/tmp/gr_bench_ckpt"}
+        tr = g.Trainer(model, ds, cfg, device=dev)
+        csr = ds.get_torch_adjacency(normalized=True)
+        nnz, n = csr.nnz, nu + ni
+        model.eval()
+
+        def fwd():
+            with torch.no_grad():
+                return model.get_all_embeddings(csr)
+        ms_fwd = _ev_time(fwd, 10, 2, flush)
+        b_alg = _model_forward_bytes(name, nnz, n)
+        model.train()
+        n_steps = 100
+        tr.train_steps(5)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        loss = tr.train_steps(n_steps)
+        torch.cuda.synchronize()
+        ms_step = (time.perf_counter() - t0) / n_steps * 1e3
+        steps_epoch = len(tu) // 512 + 1
+        # CPU: the oracle port's eval forward on the host cores (1 run; GAT through the CSR edge-softmax
+        # restatement — the dense reference needs 19 GB per temporary at this shape)
+        import test_gpu_models as T
+        ref = po.build_norm_adj(tu, ti, nu, ni)
+        adj = po.to_torch_coo(ref)
+        model.eval()
+        with torch.no_grad():
+            t0 = time.perf_counter()
+            T._oracle_forward(name, adj, ref, cpu_params, model)
+            cpu_s = time.perf_counter() - t0
+        out[key] = {
+            "config": f"BASELINE.json configs[{cfg_idx}]: {type(model).__name__} 3-layer d=64 at the {shape} shape "
+                      f"({nu} x {ni}, nnz(A_hat)={nnz})",
+            "forward_ms": ms_fwd, "forward_edges_per_s": 3 * nnz / (ms_fwd * 1e-3),
+            "roofline": {"bound": "hbm", "algorithmic_bytes_per_forward": b_alg,
+                         "achieved": b_alg / (ms_fwd * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": b_alg / (ms_fwd * 1e-3) / 1e9 / hbm_peak,
+                         "note": "whole forward incl. launch gaps; tables (18 MB) are L2-resident, L2 flushed between runs"},
+            "train_step_ms": ms_step, "train_steps_timed": n_steps, "loss": loss,
+            "epoch_s_extrapolated": ms_step * steps_epoch * 1e-3, "steps_per_epoch": steps_epoch,
+            "cpu_forward_s": cpu_s, "cpu_forward_edges_per_s": 3 * nnz / cpu_s, "cpu_cores": torch.get_num_threads(),
+            "what": "eval forward through model.get_all_embeddings; training step = Trainer.train_steps body (host "
+                    "sampler, propagation, fused BPR, backward kernels gr_rowmap_bwd / gr_gat_bwd / gr_gs_compose_bwd + "
+                    "SpMM on A^T, fused clip+Adam); CPU = oracle port, one forward"}
+        del tr, model, ds, csr
+        torch.cuda.empty_cache()
+    return out
+
+
+def run_prop_extra(g, dev, workload, hbm_peak):
+    """north_star target: LightGCN 3-layer propagation at the dataset shapes, fraction of the HBM peak."""
+    from gnn_recommendations_b200.synthetic import synth_pairs_device
+    nu, ni, e, d, L = WORKLOADS[workload]
+    u, i = synth_pairs_device(nu, ni, e, 42, dev)
+    csr = g.NormAdjCSR.from_pairs(u, i, nu, ni, device=dev)
+    with torch.device(dev):
+        model = g.LightGCN(nu, ni, embedding_dim=d, n_layers=L, init_scale=0.1)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def fwd():
+        with torch.no_grad():
+            return model.propagate(csr)
+    ms = _ev_time(fwd, 30, 5, flush)
+    b_alg = L * alg_bytes_per_layer(csr.nnz, nu + ni, d)
+    b_comp = L * (csr.nnz * 8 + (nu + ni) * (4 + 8 * d))
+    tr = _traffic(f"{workload}@1")
+    return {"edges_per_s": L * csr.nnz / (ms * 1e-3), "ms": ms, "layers": L, "nnz": csr.nnz, "long_rows": int(csr.n_long),
+            "algorithmic_bytes": b_alg, "frac_of_hbm_peak_algorithmic": b_alg / (ms * 1e-3) / 1e9 / hbm_peak,
+            "compulsory_bytes": b_comp, "frac_of_hbm_peak_compulsory": b_comp / (ms * 1e-3) / 1e9 / hbm_peak,
+            "ncu_bytes_per_layer": tr,
+            "what": f"LightGCN {L}-layer propagation at the {workload} shape, L2 flushed between iterations; the table "
+                    f"({(nu + ni) * d * 4 / 1e6:.1f} MB) is L2-resident so the algorithmic fraction can exceed the DRAM "
+                    "fraction; ncu_bytes_per_layer = dram / lts bytes of one layer from profiles/"}
+
+
+def run_torch_gpu_baseline(csr, x, L, dev):
+    """Stock torch on the same GPU: torch.sparse.mm over a CSR tensor (cuSPARSE) for the propagation
+    (lightgcn.py:88 as the reference would run it on CUDA)."""
+    a = torch.sparse_csr_tensor(csr.indptr, csr.indices, csr.vals, size=(csr.n_rows, csr.n_cols))
+
+    def fwd():
+        with torch.no_grad():
+            y = x
+            acc = x
+            for _ in range(L):
+                y = torch.sparse.mm(a, y)
+                acc = acc + y
+            return acc / (L + 1)
+    ms = _ev_time(fwd, 3, 1)
+    return {"ms": ms, "edges_per_s": L * csr.nnz / (ms * 1e-3),
+            "what": f"torch {torch.__version__} torch.sparse.mm (CSR, CUDA) x {L} layers + layer mean, same graph and table"}
+
+
+def run_extras_multi(g, dev, rank, world, csr, part, exchange, x0_local, nu, ni, L, d, ms_step, kernel_ms):
+    """N > 1: (1) NVLink bytes and rate of one layer exchange; (2) BASELINE.metric's epoch time through the
+    row-partitioned training step (ShardedLightGCN: two propagations + replicated BPR batch + local clip/Adam),
+    timed over a few steps and extrapolated to the E/B + 1 steps of an epoch; (3) BASELINE configs[3]: full-ranking
+    top-20 at the Amazon-Book shape with the item catalogue sharded over the ranks and the per-shard lists merged."""
+    import torch.distributed as dist
+
+    from gnn_recommendations_b200.dist import ShardedLightGCN, full_rank_topk_sharded, item_shard
+    from gnn_recommendations_b200.evaluator import seen_csr
+    from gnn_recommendations_b200.synthetic import synth_pairs_device
+
+    out = {}
+    n_loc = csr.n_rows
+    egress = n_loc * d * 4 * (world - 1)
+    layer_ms = float(np.mean(kernel_ms)) if kernel_ms else None
+    out["exchange"] = {"egress_bytes_per_layer_per_rank": egress, "layer_kernel_ms": layer_ms,
+                       "nvlink_egress_gb_per_s": (egress / (layer_ms * 1e-3) / 1e9) if layer_ms else None,
+                       "nvlink_peak_gb_per_s": 900.0,
+                       "what": "rows this rank stores into the other ranks' layer buffers from the SpMM epilogue (fused "
+                               "all-gather) per layer, over the CUDA-event time of that layer's launch"}
+    # ---- epoch time at this workload, row-partitioned training step
+    e_total = csr.nnz  # local entries; global edges = nnz_global / 2
+    nnz_t = torch.tensor([csr.nnz], dtype=torch.int64, device=dev)
+    dist.all_reduce(nnz_t)
+    n_edges = int(nnz_t.item()) // 2
+    csr.full_symmetric = True
+    sm = ShardedLightGCN(csr, part, rank, x0_local, nu, L, exchange=exchange)
+    gen = torch.Generator(device=dev).manual_seed(7)          # same batch on every rank
+    B = 512
+
+    def one_step():
+        users = torch.randint(0, nu, (B,), device=dev, generator=gen)
+        pos = torch.randint(0, ni, (B,), device=dev, generator=gen)
+        neg = torch.randint(0, ni, (B,), device=dev, generator=gen)
+        return sm.train_step(users, pos, neg)
+    one_step()
+    dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    n_steps = 3
+    for _ in range(n_steps):
+        loss = one_step()
+    dist.barrier()
+    torch.cuda.synchronize()
+    sec = torch.tensor([(time.perf_counter() - t0) / n_steps], dtype=torch.float64, device=dev)
+    dist.all_reduce(sec, op=dist.ReduceOp.MAX)
+    steps_epoch = n_edges // B + 1
+    out["epoch"] = {"train_step_ms": float(sec.item()) * 1e3, "steps_timed": n_steps, "steps_per_epoch": steps_epoch,
+                    "epoch_s_extrapolated": float(sec.item()) * steps_epoch, "loss": loss,
+                    "what": "ShardedLightGCN.train_step (forward propagation, replicated B=512 batch with one [3B,d] "
+                            "all-reduce, fused B x B BPR, backward = the same propagation on the gradient, global-norm "
+                            "clip, local fused Adam); epoch = E // B + 1 such steps (trainer.py:237), extrapolated"}
+    del sm
+    torch.cuda.empty_cache()
+    # ---- eval at C4, item-sharded (every rank scores ALL users against its item range, then merge)
+    cu, ci, ce, cd, cL = WORKLOADS["C4"]
+    u, i = synth_pairs_device(cu, ci, ce, 42, dev)
+    c4 = g.NormAdjCSR.from_pairs(u, i, cu, ci, device=dev)
+    torch.manual_seed(42)
+    with torch.device(dev):
+        model = g.LightGCN(cu, ci, embedding_dim=cd, n_layers=cL, init_scale=0.1)
+    with torch.no_grad():
+        ue, ie = model.get_all_embeddings(c4)
+    eval_users = np.arange(cu)
+    ip, it = seen_csr(eval_users, cu, (u.cpu().numpy(), i.cpu().numpy()))
+    ip_d, it_d = torch.from_numpy(ip).to(dev), torch.from_numpy(it).to(dev)
+    eu_d = torch.from_numpy(eval_users).to(dev)
+    lo, hi = item_shard(ci, world, rank)
+    ie_loc = ie[lo:hi].contiguous()
+
+    def ev():
+        return full_rank_topk_sharded(ue, ie_loc, lo, hi, eu_d, ip_d, it_d, 20, world)
+    ev()
+    dist.barrier()
+    ms = _ev_time(ev, 3, 1)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    got = ev()
+    same = None
+    if rank == 0:
+        from gnn_recommendations_b200.evaluator import full_rank_topk
+        same = bool(torch.equal(got, full_rank_topk(ue, ie, eu_d, ip_d, it_d, 20, tensor_cores=False)))
+    out["eval_c4"] = {"ms": float(t.item()), "users_per_s": cu / (float(t.item()) * 1e-3), "users": cu, "items": ci, "k": 20,
+                      "identical_to_single_gpu_lists": same,
+                      "what": f"BASELINE configs[3]: item catalogue split into {world} id ranges, every rank ranks all users "
+                              "against its range, per-rank top-20 (score, id) lists all-gathered and merged (score desc, id asc)"}
+    return out
+
+
+def run_extras(g, dev, hbm_peak):
+    """Secondary measurements of the other path stages at the dataset shapes: LightGCN propagation at C1 / C4
+    (the north_star target), full-ranking top-20 evaluation (C4), one training epoch (C1), the other model
+    families at BASELINE.json configs[1] / [2], and stock-torch GPU baselines."""
     from gnn_recommendations_b200.evaluator import full_rank_topk, seen_csr
     from gnn_recommendations_b200.synthetic import synth_pairs_device
 
     out = {}
+    out["prop_c1"] = run_prop_extra(g, dev, "C1", hbm_peak)
+    out["prop_c4"] = run_prop_extra(g, dev, "C4", hbm_peak)
     # --- eval users/s at C4: scores + seen-mask + top-20 for every user, catalogue 91 599 items
     nu, ni, e, d, L = WORKLOADS["C4"]
     u, i = synth_pairs_device(nu, ni, e, 42, dev)
@@ -465,6 +777,8 @@ def run_extras(g, dev):
         model = g.LightGCN(nu, ni, embedding_dim=d, n_layers=L, init_scale=0.1)
     with torch.no_grad():
         ue, ie = model.get_all_embeddings(csr)
+    x0 = torch.cat([model.user_embedding.weight, model.item_embedding.weight]).detach()
+    out["torch_gpu"] = {"spmm_c4": run_torch_gpu_baseline(csr, x0, L, dev)}
     eval_users = np.arange(nu)
     ip, it = seen_csr(eval_users, nu, (u.cpu().numpy(), i.cpu().numpy()))
     ip_d, it_d = torch.from_numpy(ip).to(dev), torch.from_numpy(it).to(dev)
@@ -484,8 +798,8 @@ def run_extras(g, dev):
 
     ms_exact, _ = time_topk(False)
     ms, st = time_topk(None)
-    same = bool(torch.equal(full_rank_topk(ue, ie, eu_d, ip_d, it_d, 20, tensor_cores=False),
-                            full_rank_topk(ue, ie, eu_d, ip_d, it_d, 20, tensor_cores=None)))
+    ours = full_rank_topk(ue, ie, eu_d, ip_d, it_d, 20, tensor_cores=None)
+    same = bool(torch.equal(full_rank_topk(ue, ie, eu_d, ip_d, it_d, 20, tensor_cores=False), ours))
     out["eval_c4"] = {"users_per_s": nu / (ms * 1e-3), "ms": ms, "users": nu, "items": ni, "k": 20, "d": d,
                       "tensor_cores": bool(st.get("tensor_cores")), "rows_reranked_exactly": st.get("rows_reranked_exactly"),
                       "tf32_tflop_per_s": 2.0 * nu * ni * d / (ms * 1e-3) / 1e12,
@@ -494,7 +808,28 @@ def run_extras(g, dev):
                       "lists_identical_to_exact_kernel": same,
                       "what": "full-ranking top-20 for all users: tcgen05 TF32 nomination (K'=32, two CTAs per SM) + exact fp32 "
                               "re-scoring + exact re-rank of unproven rows; exact_only = FFMA kernel alone"}
-    del csr, model, ue, ie
+
+    # stock torch on the GPU: the reference's loop (evaluator.py:96-108) — batches of 2048 users, U_b @ I^T,
+    # seen items to -inf, torch.topk
+    rows_seen = torch.repeat_interleave(torch.arange(nu, device=dev), (ip_d[1:] - ip_d[:-1]))
+    cols_seen = it_d.long()
+
+    def torch_eval():
+        outs = []
+        for s0 in range(0, nu, 2048):
+            sc = ue[s0:s0 + 2048] @ ie.T
+            lo, hi = int(ip[s0]), int(ip[min(s0 + 2048, nu)])
+            sc[rows_seen[lo:hi] - s0, cols_seen[lo:hi]] = float("-inf")
+            outs.append(torch.topk(sc, 20, dim=1).indices)
+        return torch.cat(outs)
+    ms_t = _ev_time(torch_eval, 2, 1)
+    tk = torch_eval()
+    agree = float((tk == ours).float().mean())
+    out["torch_gpu"]["eval_c4"] = {"ms": ms_t, "users_per_s": nu / (ms_t * 1e-3), "positions_equal_to_ours": agree,
+                                   "what": "torch.mm (cuBLAS, TF32 off) + index mask + torch.topk in 2048-user batches "
+                                           "(evaluator.py:96-108 on CUDA); tie order of torch.topk is arbitrary"}
+    del csr, model, ue, ie, x0
+    torch.cuda.empty_cache()
     # --- epoch time at C1: 1 954 steps of sample + propagate + fused BPR + backward + clip + Adam
     nu, ni, e, d, L = WORKLOADS["C1"]
     u, i = synth_pairs_device(nu, ni, e, 42, dev)
@@ -516,6 +851,9 @@ def run_extras(g, dev):
                        "edge_traversals_per_s": steps * 2 * L * 2 * e / sec,
                        "what": "Trainer.train_epoch at the ML-1M shape (B=512, full propagation fwd+bwd per step, "
                                "host sampler included); reference CPU: 1410.6 s (BASELINE.md)"}
+    del tr, model, ds
+    torch.cuda.empty_cache()
+    out.update(run_model_extras(g, dev, hbm_peak))
     return out
 
 

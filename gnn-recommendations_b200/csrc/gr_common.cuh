@@ -77,6 +77,22 @@ __device__ __forceinline__ float apply_scale(float v, float scale, int mode) {
     return v;
 }
 
+// --- counter-based dropout bits ------------------------------------------------------------------
+// splitmix64 stream element `idx` of `seed`: four independent 16-bit uniforms per call.  Forward and
+// backward kernels derive the same mask from (seed, element index); nothing is stored.
+__host__ __device__ __forceinline__ unsigned long long drop_bits(unsigned long long seed, unsigned long long idx) {
+    unsigned long long x = seed + (idx + 1ULL) * 0x9E3779B97F4A7C15ULL;
+    x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ULL;
+    x ^= x >> 27; x *= 0x94D049BB133111EBULL;
+    x ^= x >> 31;
+    return x;
+}
+__host__ __device__ __forceinline__ bool drop_keep(unsigned long long bits, int lane4, unsigned thr) {
+    return ((unsigned)(bits >> (16 * lane4)) & 0xFFFFu) >= thr;
+}
+inline unsigned drop_threshold(float p) { return p > 0.f ? (unsigned)(p * 65536.f + 0.5f) : 0u; }
+inline float drop_scale_of(unsigned thr) { return 65536.f / (float)(65536u - thr); }
+
 // --- cp.async (LDGSTS) -----------------------------------------------------------------------
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src, uint64_t pol) {
     unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));

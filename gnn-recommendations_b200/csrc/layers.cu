@@ -30,6 +30,9 @@ struct RowMapArgs {
     int n_rows, d_in, d_out;
     float alpha, beta, slope;
     int act;  // 0 none, 1 LeakyReLU(slope), 2 ELU
+    unsigned drop_thr;        // 0 = no dropout; else element dropped when its 16-bit uniform < drop_thr
+    float drop_scale;         // 65536 / (65536 - drop_thr)
+    unsigned long long drop_seed;
 };
 
 constexpr int RM_ROWS = 64;
@@ -141,6 +144,12 @@ __global__ void __launch_bounds__(256) rowmap_kernel(const RowMapArgs a) {
                 const float4 rv = __ldg(reinterpret_cast<const float4 *>(a.resid + (long long)r * a.ldr) + cg);
                 o[0] += a.beta * rv.x; o[1] += a.beta * rv.y; o[2] += a.beta * rv.z; o[3] += a.beta * rv.w;
             }
+            if (a.drop_thr) {   // nn.Dropout on the layer output (ngcf.py:86, model.py:198-199): keep/(1-p)
+                const unsigned long long bits = drop_bits(a.drop_seed, (unsigned long long)r * nc4 + cg);
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    o[c] = drop_keep(bits, c, a.drop_thr) ? o[c] * a.drop_scale : 0.f;
+            }
             *reinterpret_cast<float4 *>(a.out + (long long)r * a.ldo + cg * 4) = make_float4(o[0], o[1], o[2], o[3]);
         }
     }
@@ -187,6 +196,12 @@ struct GatArgs {
     float *out;
     long long ldo;
     float *m_out, *z_out;  // [n_rows, heads] softmax statistics for the backward pass (may be NULL)
+    float *raw_out;        // [n_rows, heads*dh] per-head aggregate before head-mean / ELU (may be NULL)
+    long long ldraw;
+    long long n_cols;
+    unsigned drop_thr;     // attention dropout (gat.py:138): weight kept with prob 1-p, scaled by 1/(1-p)
+    float drop_scale;
+    unsigned long long drop_seed;
 };
 
 // One warp per row, online softmax (running max / running sum, rescaled accumulator), one pass over
@@ -200,6 +215,7 @@ __global__ void __launch_bounds__(256) gat_aggregate_kernel(const GatArgs a) {
     const int dh4 = a.dh / 4;
     int head[SLOTS];
     bool on[SLOTS];
+    const int hgroups = (a.heads + 3) >> 2;
     float si[SLOTS], m[SLOTS], z[SLOTS];
     float4 acc[SLOTS];
 #pragma unroll
@@ -219,9 +235,11 @@ __global__ void __launch_bounds__(256) gat_aggregate_kernel(const GatArgs a) {
         for (int k = 0; k < cnt; k += 4) {
             float4 hv[4][SLOTS];
             float tv[4][SLOTS];
+            int jj[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int j = __shfl_sync(0xffffffffu, mycol, (k + u) & 31);
+                jj[u] = j;
                 if (k + u < cnt) {
 #pragma unroll
                     for (int q = 0; q < SLOTS; ++q)
@@ -241,8 +259,13 @@ __global__ void __launch_bounds__(256) gat_aggregate_kernel(const GatArgs a) {
                             e = e > 0.f ? e : e * a.slope;
                             const float mn = fmaxf(m[q], e);
                             const float sc = expf(m[q] - mn);   // exp(-inf) = 0 on the first neighbour
-                            const float w = expf(e - mn);
+                            float w = expf(e - mn);
                             z[q] = z[q] * sc + w;
+                            if (a.drop_thr) {   // the softmax normaliser keeps every edge; only the weight is dropped
+                                const unsigned long long bits = drop_bits(
+                                    a.drop_seed, ((unsigned long long)i * a.n_cols + jj[u]) * hgroups + (head[q] >> 2));
+                                w = drop_keep(bits, head[q] & 3, a.drop_thr) ? w * a.drop_scale : 0.f;
+                            }
                             acc[q].x = acc[q].x * sc + w * hv[u][q].x;
                             acc[q].y = acc[q].y * sc + w * hv[u][q].y;
                             acc[q].z = acc[q].z * sc + w * hv[u][q].z;
@@ -263,6 +286,7 @@ __global__ void __launch_bounds__(256) gat_aggregate_kernel(const GatArgs a) {
                 a.m_out[(long long)i * a.heads + head[q]] = m[q];
                 a.z_out[(long long)i * a.heads + head[q]] = z[q];
             }
+            if (a.raw_out) *reinterpret_cast<float4 *>(a.raw_out + (long long)i * a.ldraw + slot * 4) = acc[q];
         }
     if (!a.mean_heads) {
 #pragma unroll
@@ -302,8 +326,10 @@ using namespace gr;
 extern "C" int gr_rowmap_f32(const float *x1, int64_t ld1, const float *wa, const float *bias_a, const float *x2,
                              int64_t ld2, const float *x3, int64_t ld3, const float *wb, const float *bias_b,
                              const float *resid, int64_t ldr, float alpha, float beta, int32_t act, float slope,
-                             int64_t n_rows, int32_t d_in, int32_t d_out, float *out, int64_t ldo, void *stream) {
+                             int64_t n_rows, int32_t d_in, int32_t d_out, float drop_p, uint64_t drop_seed,
+                             float *out, int64_t ldo, void *stream) {
     if (!x1 || !wa || !out || n_rows < 0) return GR_ERR_INVALID;
+    if (!(drop_p >= 0.f) || drop_p >= 1.f) return GR_ERR_INVALID;
     if (wb && (!x2 || !x3)) return GR_ERR_INVALID;
     if (n_rows == 0) return GR_OK;
     if (d_in <= 0 || d_out <= 0 || (d_in & 3) || (d_out & 3) || d_in > 256 || d_out > 256) return GR_ERR_UNSUPPORTED;
@@ -319,6 +345,7 @@ extern "C" int gr_rowmap_f32(const float *x1, int64_t ld1, const float *wa, cons
     a.ld1 = ld1; a.ld2 = ld2; a.ld3 = ld3; a.ldr = ldr; a.ldo = ldo;
     a.out = out; a.n_rows = (int)n_rows; a.d_in = d_in; a.d_out = d_out;
     a.alpha = alpha; a.beta = beta; a.slope = slope; a.act = act;
+    a.drop_thr = drop_threshold(drop_p); a.drop_scale = drop_scale_of(a.drop_thr); a.drop_seed = drop_seed;
     const size_t smem = ((size_t)d_in * d_out + (size_t)d_in * RM_ROWS) * 4 * (wb ? 2 : 1);
     if (smem > 227 * 1024) return GR_ERR_UNSUPPORTED;
     GR_CUDA_CHECK(cudaFuncSetAttribute(rowmap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -341,9 +368,12 @@ extern "C" int gr_gat_node_scores(const float *h, int64_t ldh, const float *a_se
 
 extern "C" int gr_gat_aggregate(const int32_t *indptr, const int32_t *indices, int64_t n_rows, const float *h,
                                 int64_t ldh, const float *s, const float *t, int32_t heads, int32_t dh,
-                                float slope, int32_t mean_heads, int32_t elu, float *out, int64_t ldo, float *m_out,
-                                float *z_out, void *stream) {
+                                float slope, int32_t mean_heads, int32_t elu, float drop_p, uint64_t drop_seed,
+                                int64_t n_cols, float *out, int64_t ldo, float *m_out, float *z_out, float *raw_out,
+                                int64_t ldraw, void *stream) {
     if (!indptr || !indices || !h || !s || !t || !out || n_rows < 0 || heads <= 0 || dh <= 0) return GR_ERR_INVALID;
+    if (!(drop_p >= 0.f) || drop_p >= 1.f || n_cols < 0) return GR_ERR_INVALID;
+    if (raw_out && ((ldraw & 3) || ldraw < (int64_t)heads * dh || !aligned16(raw_out))) return GR_ERR_INVALID;
     if ((m_out == nullptr) != (z_out == nullptr)) return GR_ERR_INVALID;
     if (n_rows == 0) return GR_OK;
     const int width = heads * dh;
@@ -354,7 +384,9 @@ extern "C" int gr_gat_aggregate(const int32_t *indptr, const int32_t *indices, i
     GatArgs a;
     a.indptr = indptr; a.indices = indices; a.h = h; a.ldh = ldh; a.s = s; a.t = t;
     a.n_rows = (int)n_rows; a.heads = heads; a.dh = dh; a.slope = slope; a.mean_heads = mean_heads; a.elu = elu;
-    a.out = out; a.ldo = ldo; a.m_out = m_out; a.z_out = z_out;
+    a.out = out; a.ldo = ldo; a.m_out = m_out; a.z_out = z_out; a.raw_out = raw_out; a.ldraw = ldraw;
+    a.n_cols = n_cols;
+    a.drop_thr = drop_threshold(drop_p); a.drop_scale = drop_scale_of(a.drop_thr); a.drop_seed = drop_seed;
     const unsigned grid = (unsigned)((n_rows + 7) / 8);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (width / 4 <= 32) gat_aggregate_kernel<1><<<grid, 256, 0, st>>>(a);

@@ -74,8 +74,12 @@ class RowPartition:
         src = torch.repeat_interleave(starts - indptr[:-1], counts) + torch.arange(total, device=rows.device)
         indices = self.to_padded(full.indices[src]).to(torch.int32).contiguous()
         vals = full.vals[src].contiguous()
-        return NormAdjCSR(indptr.to(torch.int32), indices, vals, int(rows.numel()), self.padded_rows,
-                          long_threshold=full.long_threshold)
+        local = NormAdjCSR(indptr.to(torch.int32), indices, vals, int(rows.numel()), self.padded_rows,
+                           long_threshold=full.long_threshold)
+        # whether the FULL matrix equals its transpose (True for the reference's 'symmetric' normalisation);
+        # None = unknown.  ShardedLightGCN's backward needs it.
+        local.full_symmetric = full._symmetric
+        return local
 
 
 def build_local_csr(part: RowPartition, rank: int, user, item, n_users: int, n_items: int,
@@ -134,7 +138,9 @@ def build_local_csr(part: RowPartition, rank: int, user, item, n_users: int, n_i
         if int(status.item()) & 4:
             raise _lib.GrError("degree exceeds the look-up table")
     kw = {} if long_threshold is None else {"long_threshold": long_threshold}
-    return NormAdjCSR(indptr, indices, vals, n_local, part.padded_rows, **kw)
+    local = NormAdjCSR(indptr, indices, vals, n_local, part.padded_rows, **kw)
+    local.full_symmetric = (mode != 1)      # 'row' normalisation D^-1 A is not symmetric
+    return local
 
 
 class PeerExchange:
@@ -285,14 +291,32 @@ def gather_rows(part: RowPartition, rank: int, x_local: torch.Tensor, group=None
     return out
 
 
+def merge_topk_partials(ps: torch.Tensor, pi: torch.Tensor, k: int) -> torch.Tensor:
+    """K-way merge of per-shard top-k lists [segments, n_eval, k] under (score desc, id asc) (gr_topk_merge)."""
+    from ._lib import check, lib, ptr, stream_ptr
+
+    n_eval, dev = int(ps.shape[1]), ps.device
+    ps, pi = ps.contiguous(), pi.contiguous()
+    ids = torch.empty((n_eval, k), dtype=torch.int64, device=dev)
+    sc = torch.empty((n_eval, k), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib().gr_topk_merge(ptr(ps), ptr(pi), int(ps.shape[0]), n_eval, k, ptr(ids), ptr(sc), stream_ptr()),
+              "gr_topk_merge")
+    return ids
+
+
 def full_rank_topk_sharded(user_emb: torch.Tensor, item_emb_local: torch.Tensor, item_lo: int, item_hi: int,
                            eval_users, seen_indptr, seen_items, k: int, world_size: int, group=None,
                            n_splits: int = 1, partial_fn: Optional[Callable] = None,
-                           merge_fn: Optional[Callable] = None) -> torch.Tensor:
+                           merge_fn: Optional[Callable] = None, tensor_cores: Optional[bool] = None,
+                           return_partial: bool = False):
     """Each rank ranks its own item id range [item_lo, item_hi) for ALL eval users
     (gr_score_topk_partial), the per-rank top-k (score, id) lists are all-gathered
     (k * 8 bytes per user per rank) and merged under (score desc, id asc) (gr_topk_merge).
     Scores are per-(user,item) independent, so the result is bit-identical to the 1-GPU list.
+    ``tensor_cores`` (None = automatic): the rank's partial list comes from the tcgen05 nomination + exact
+    re-scoring path of ``full_rank_topk`` run on the rank's item shard (seen-item CSR cut to the shard's id
+    range and shifted), which yields the same bits as the exact partial kernel.
     ``partial_fn`` / ``merge_fn`` are injectable for the CPU (gloo) tests of the exchange logic."""
     import torch.distributed as dist
 
@@ -301,8 +325,9 @@ def full_rank_topk_sharded(user_emb: torch.Tensor, item_emb_local: torch.Tensor,
     n_eval = int(eval_users.numel())
     if partial_fn is None:
         from ._lib import check, lib, ptr, stream_ptr
+        from .evaluator import TC_MIN_ITEMS, full_rank_topk, tc_kprime
 
-        def partial_fn(ue, ie, lo, hi, eu, sip, sit, kk, ns):
+        def exact_partial(ue, ie, lo, hi, eu, sip, sit, kk, ns):
             ps = torch.empty((ns, n_eval, kk), dtype=torch.float32, device=dev)
             pi = torch.empty((ns, n_eval, kk), dtype=torch.int32, device=dev)
             with torch.cuda.device(dev):
@@ -311,13 +336,31 @@ def full_rank_topk_sharded(user_emb: torch.Tensor, item_emb_local: torch.Tensor,
                                                   ptr(pi), stream_ptr()), "gr_score_topk_partial")
             return ps, pi
 
-        def merge_fn(ps, pi, kk):
-            ids = torch.empty((n_eval, kk), dtype=torch.int64, device=dev)
-            sc = torch.empty((n_eval, kk), dtype=torch.float32, device=dev)
-            with torch.cuda.device(dev):
-                check(lib().gr_topk_merge(ptr(ps), ptr(pi), int(ps.shape[0]), n_eval, kk, ptr(ids), ptr(sc),
-                                          stream_ptr()), "gr_topk_merge")
-            return ids
+        def tc_partial(ue, ie, lo, hi, eu, sip, sit, kk, ns):
+            # seen items of each row restricted to [lo, hi) and shifted to shard-local ids (rows stay sorted)
+            lip = lit = None
+            if sip is not None:
+                inside = (sit >= lo) & (sit < hi)
+                csum = torch.zeros(sit.numel() + 1, dtype=torch.int64, device=dev)
+                torch.cumsum(inside, 0, out=csum[1:])
+                lip = csum[sip.clamp(max=sit.numel())]
+                lit = (sit[inside] - lo).to(torch.int32)
+            ids, sc = full_rank_topk(ue, ie, eu, lip, lit, kk, return_scores=True, tensor_cores=True)
+            ids = torch.where(ids >= 0, ids + lo, ids)
+            return sc.unsqueeze(0).contiguous(), ids.to(torch.int32).unsqueeze(0).contiguous()
+
+        def partial_fn(ue, ie, lo, hi, eu, sip, sit, kk, ns):
+            d_, n_loc = int(ue.shape[1]), int(hi - lo)
+            kp = tc_kprime(kk)
+            can = bool(lib().gr_topk_tc_supported(d_, kp)) and kk + 8 <= kp and n_loc >= max(kp, TC_MIN_ITEMS)
+            if tensor_cores is True and not can:
+                raise ValueError(f"tensor-core top-K path does not support d={d_}, k={kk}, shard of {n_loc} items")
+            if can and tensor_cores is not False and ns == 1:
+                return tc_partial(ue, ie, lo, hi, eu, sip, sit, kk, ns)
+            return exact_partial(ue, ie, lo, hi, eu, sip, sit, kk, ns)
+
+    if merge_fn is None:
+        merge_fn = merge_topk_partials
 
     if seen_indptr is not None:
         seen_indptr = torch.as_tensor(seen_indptr, dtype=torch.int64).to(dev).contiguous()
@@ -326,6 +369,8 @@ def full_rank_topk_sharded(user_emb: torch.Tensor, item_emb_local: torch.Tensor,
             seen_items = torch.zeros(1, dtype=torch.int32, device=dev)
     ps, pi = partial_fn(user_emb.contiguous(), item_emb_local.contiguous(), int(item_lo), int(item_hi), eval_users,
                         seen_indptr, seen_items, k, n_splits)
+    if return_partial:          # (scores, ids) [segments, n_eval, k] of this rank, before the exchange
+        return ps, pi
     if world_size > 1 and dist.is_initialized():
         all_ps = torch.empty((world_size * ps.shape[0], n_eval, k), dtype=ps.dtype, device=dev)
         all_pi = torch.empty((world_size * pi.shape[0], n_eval, k), dtype=pi.dtype, device=dev)
@@ -358,6 +403,13 @@ class ShardedLightGCN:
                  n_layers: int, lr: float = 1e-3, weight_decay: float = 1e-4, max_grad_norm: float = 1.0,
                  exchange: Optional["PeerExchange"] = None, group=None, propagate: Optional[Callable] = None,
                  bpr: Optional[Callable] = None, fused_optimizer: bool = True):
+        # The backward pass applies the FORWARD row blocks to the gradient (mean_l Â^l g), which is dL/dE0 only
+        # when Â = Â^T.  A row-normalised graph (normalization='row': D^-1 A) would silently get wrong
+        # gradients, so it is refused (the single-GPU path handles it through csr.transpose()).
+        if getattr(local, "full_symmetric", None) is False:
+            raise ValueError("ShardedLightGCN needs a symmetric adjacency (normalization='symmetric' or 'none'): "
+                             "its backward pass reuses the forward row blocks; train 'row'-normalised graphs on "
+                             "one GPU")
         self.local, self.part, self.rank, self.group = local, part, rank, group
         self.n_users, self.n_layers = int(n_users), int(n_layers)
         self.max_grad_norm = float(max_grad_norm)

@@ -4,20 +4,21 @@ The reference materialises dense N x N attention matrices (19 GB per temporary a
 shape); here each layer is a CSR edge-softmax over the adjacency PATTERN: h = x W^T for all heads
 (one rowmap kernel), per-node scores, then one pass over each row's neighbours with an online
 softmax and the weighted aggregation (gr_gat_aggregate), heads concatenated or averaged, ELU
-fused.  Attention dropout is applied by the reference to the dense weights; with dropout > 0 in
-train() mode it is applied here to the layer output instead (the RNG streams cannot match across
-devices anyway: parity is checked in eval() mode)."""
+fused.  In train() mode the reference's dropout on the softmaxed attention weights (gat.py:138) is
+applied at the same place, per edge and head, inside the aggregation kernel (mask = counter-based hash
+of a seed drawn from torch's CPU generator; the backward kernel re-derives it).  The RNG stream itself
+cannot match the reference's dense N x N draw, so element-wise parity is checked in eval() mode and
+the train-mode path statistically and against a same-mask torch restatement."""
 from __future__ import annotations
 
 from typing import Optional, Tuple
 
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 from .base import BaseRecommender
 from .graph_builder import as_csr
-from .layer_ops import gat_layer
+from .layer_ops import gat_layer, new_dropout_seed
 
 
 class GATLayer(nn.Module):
@@ -33,9 +34,9 @@ class GATLayer(nn.Module):
         self.dropout_layer = nn.Dropout(dropout)
 
     def forward(self, x: torch.Tensor, adj_matrix, elu: bool = False) -> torch.Tensor:
-        out = gat_layer(as_csr(adj_matrix), x, [w.weight for w in self.W], list(self.a_self), list(self.a_neigh),
-                        self.alpha, self.concat_heads, elu)
-        return out
+        p = self.dropout if (self.training and self.dropout > 0) else 0.0
+        return gat_layer(as_csr(adj_matrix), x, [w.weight for w in self.W], list(self.a_self), list(self.a_neigh),
+                         self.alpha, self.concat_heads, elu, drop_p=p, drop_seed=new_dropout_seed() if p else 0)
 
 
 class GAT(BaseRecommender):
@@ -72,8 +73,6 @@ class GAT(BaseRecommender):
         outs = [x]
         for layer in self.layers:
             x = layer(x, csr, elu=True)                       # ELU of gat.py:283 fused into the kernel
-            if self.training and self.dropout > 0:
-                x = F.dropout(x, self.dropout, True)
             outs.append(x)
         return torch.mean(torch.stack(outs, dim=0), dim=0)
 

@@ -246,6 +246,36 @@ class NormAdjCSR:
                 raise _lib.GrError("degree exceeds the look-up table")
         return cls(indptr, indices, vals, n, n, deg=deg, symmetric=(mode != 1))
 
+    @classmethod
+    def from_host_csr(cls, indptr, indices, vals, n_cols: Optional[int] = None, device="cuda",
+                      symmetric: Optional[bool] = None, non_blocking: bool = True) -> "NormAdjCSR":
+        """32-bit CSR arrays in HOST memory (numpy or torch CPU tensors, ideally pinned; what ``to_host`` returns
+        or ``scipy.sparse.csr_matrix`` holds: indptr/indices int32, data f32 — 8 B per entry instead of the 20 B
+        of the int64 torch COO) -> device.  The upload is the only data movement; the row schedule is built on
+        the device."""
+        device = _require_cuda(device)
+
+        def up(a, dt):
+            t = torch.as_tensor(a)
+            if t.dtype != dt:
+                t = t.to(dt)
+            return t.to(device, non_blocking=non_blocking).contiguous()
+
+        ip, ix, vl = up(indptr, torch.int32), up(indices, torch.int32), up(vals, torch.float32)
+        n_rows = int(ip.numel()) - 1
+        if ix.numel() != vl.numel():
+            raise ValueError("indices and vals must have the same length")
+        return cls(ip, ix, vl, n_rows, n_rows if n_cols is None else int(n_cols), symmetric=symmetric)
+
+    def to_host(self, pin: bool = True):
+        """(indptr, indices, vals) as int32 / int32 / f32 CPU tensors (pinned by default)."""
+        out = []
+        for t in (self.indptr, self.indices, self.vals):
+            h = torch.empty(t.shape, dtype=t.dtype, pin_memory=pin)
+            h.copy_(t)
+            out.append(h)
+        return tuple(out)
+
     # ---- views --------------------------------------------------------------------------------
     def row_ids(self) -> torch.Tensor:
         counts = (self.indptr[1:] - self.indptr[:-1]).long()
@@ -338,8 +368,26 @@ def degree_lut(max_deg: int, power: float) -> np.ndarray:
 # (trainer.py:233, 293; evaluator.py:76) and passes the same object to the model for every
 # step in between.
 # --------------------------------------------------------------------------------------------
-_CACHE: "OrderedDict[tuple, tuple]" = OrderedDict()
+_CACHE: "OrderedDict[tuple, NormAdjCSR]" = OrderedDict()
 _CACHE_SIZE = 4
+
+
+def _content_key(adj_matrix: torch.Tensor) -> tuple:
+    """Key of a torch sparse COO adjacency by CONTENT (the reference hands a freshly built
+    tensor object to every epoch / validate / evaluate call): shape, nnz and device-side checksums of the row
+    ids, column ids and value bits (wrapping int64 sums, plus position-weighted sums over a strided sample).
+    Three small reductions + one host read; the COO tensor itself is NOT kept alive."""
+    idx, val = adj_matrix._indices(), adj_matrix._values()
+    nnz = int(val.numel())
+    if nnz == 0:
+        return (tuple(adj_matrix.shape), 0, str(adj_matrix.device))
+    stride = max(1, nnz // (1 << 20))
+    samp = idx[:, ::stride]
+    w = torch.arange(1, samp.shape[1] + 1, device=idx.device, dtype=torch.int64)
+    vbits = val.view(torch.int32) if val.dtype == torch.float32 else val.float().view(torch.int32)
+    sums = torch.stack([idx[0].sum(), idx[1].sum(), vbits.sum(dtype=torch.int64), (samp[0] * w).sum(),
+                        (samp[1] * w).sum(), (vbits[::stride].long() * w).sum()])
+    return (tuple(adj_matrix.shape), nnz, str(adj_matrix.device), str(val.dtype)) + tuple(sums.tolist())
 
 
 def as_csr(adj_matrix) -> NormAdjCSR:
@@ -354,16 +402,24 @@ def as_csr(adj_matrix) -> NormAdjCSR:
     if adj_matrix.device.type != "cuda":
         raise _lib.GrError("adjacency must live on a CUDA device (call .to(device) first, as the reference "
                            "Trainer does)")
-    idx, val = adj_matrix._indices(), adj_matrix._values()
-    key = (idx.data_ptr(), val.data_ptr(), int(val.numel()), tuple(adj_matrix.shape), str(adj_matrix.device))
-    hit = _CACHE.get(key)
-    if hit is not None:
+    # fast path: the very same tensor object as last time (every step of an epoch passes it again)
+    ident = (id(adj_matrix), adj_matrix._indices().data_ptr(), adj_matrix._values().data_ptr(),
+             int(adj_matrix._values().numel()))
+    last = getattr(as_csr, "_last", None)
+    if last is not None and last[0] == ident and last[1]() is adj_matrix:
+        return last[2]
+    key = _content_key(adj_matrix)
+    csr = _CACHE.get(key)
+    if csr is not None:
         _CACHE.move_to_end(key)
-        return hit[0]
-    csr = NormAdjCSR.from_torch_coo(adj_matrix)
-    _CACHE[key] = (csr, adj_matrix)          # keep the tensor alive so its pointers stay unique
-    while len(_CACHE) > _CACHE_SIZE:
-        _CACHE.popitem(last=False)
+    else:
+        csr = NormAdjCSR.from_torch_coo(adj_matrix)
+        _CACHE[key] = csr
+        while len(_CACHE) > _CACHE_SIZE:
+            _CACHE.popitem(last=False)
+    import weakref
+
+    as_csr._last = (ident, weakref.ref(adj_matrix), csr)      # weak: the COO tensor is not kept alive
     return csr
 
 

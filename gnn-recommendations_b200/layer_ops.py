@@ -1,23 +1,28 @@
 """Autograd wrappers of the propagation kernels shared by the model classes.
 
-Forward passes run the hand-written kernels of libgr_b200.so.  Backward of the sparse product is
-the same SpMM kernel on Â^T.  Backward of the small dense epilogues and of the GAT edge-softmax
-re-evaluates the layer with stock torch ops under autograd (checkpoint style): these are
-[N,64]x[64,64]-sized library GEMMs / index ops off the bandwidth-critical path; fused backward
-kernels are listed as next work in DESIGN.md.
+Forward AND backward passes run the hand-written kernels of libgr_b200.so: the backward of the sparse
+product is the same SpMM kernel on Â^T, the backward of the dense per-row epilogues is gr_rowmap_bwd
+(input gradients + deterministic weight-gradient reduction) and the backward of the GAT edge-softmax is
+gr_gat_bwd (softmax weights recomputed per row from the stored max / normaliser).  No stock torch GEMM /
+index kernel is left on the training step (what autograd would run under trainer.py:270).
 """
 from __future__ import annotations
 
 from typing import Optional, Sequence
 
 import torch
-import torch.nn.functional as F
 
 from . import _lib
 from ._lib import check, lib, ptr, stream_ptr
 from .graph_builder import NormAdjCSR
 
 ACT_NONE, ACT_LEAKY, ACT_ELU = 0, 1, 2
+
+
+def new_dropout_seed() -> int:
+    """A 63-bit seed drawn from torch's global CPU generator (the stream the reference's nn.Dropout
+    consumes), so torch.manual_seed makes train-mode runs reproducible."""
+    return int(torch.empty((), dtype=torch.int64).random_().item())
 
 
 class _Spmm(torch.autograd.Function):
@@ -38,131 +43,219 @@ def spmm(csr: NormAdjCSR, x: torch.Tensor) -> torch.Tensor:
     return _Spmm.apply(x, csr)
 
 
-def _rowmap_raw(x1, wa, ba, x2, x3, wb, bb, resid, alpha, beta, act, slope):
+def _rows(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    """Row-major with unit inner stride (any row stride: column slices of a wider matrix are fine)."""
+    if t is None:
+        return None
+    if t.dim() == 2 and t.stride(1) == 1 and t.stride(0) % 4 == 0 and t.data_ptr() % 16 == 0:
+        return t
+    return t.contiguous()
+
+
+def _ld(t: Optional[torch.Tensor]) -> int:
+    return 0 if t is None else t.stride(0)
+
+
+def _rowmap_raw(x1, wa, ba, x2, x3, wb, bb, resid, alpha, beta, act, slope, drop_p=0.0, drop_seed=0, out=None):
     n, d_in = x1.shape
     d_out = wa.shape[1]
-    out = torch.empty((n, d_out), dtype=torch.float32, device=x1.device)
+    if out is None:
+        out = torch.empty((n, d_out), dtype=torch.float32, device=x1.device)
     with torch.cuda.device(x1.device):
         check(lib().gr_rowmap_f32(
-            ptr(x1), x1.stride(0), ptr(wa), ptr(ba),
-            ptr(x2), x2.stride(0) if x2 is not None else 0, ptr(x3), x3.stride(0) if x3 is not None else 0,
-            ptr(wb), ptr(bb), ptr(resid), resid.stride(0) if resid is not None else 0,
-            float(alpha), float(beta), int(act), float(slope), n, d_in, d_out, ptr(out), out.stride(0),
-            stream_ptr()), "gr_rowmap_f32")
+            ptr(x1), _ld(x1), ptr(wa), ptr(ba), ptr(x2), _ld(x2), ptr(x3), _ld(x3), ptr(wb), ptr(bb), ptr(resid),
+            _ld(resid), float(alpha), float(beta), int(act), float(slope), n, d_in, d_out, float(drop_p),
+            int(drop_seed), ptr(out), out.stride(0), stream_ptr()), "gr_rowmap_f32")
     return out
 
 
-def _rowmap_torch(x1, wa, ba, x2, x3, wb, bb, resid, alpha, beta, act, slope):
-    z = x1 @ wa
-    if ba is not None:
-        z = z + ba
-    if wb is not None:
-        zb = (x2 * x3) @ wb
-        if bb is not None:
-            zb = zb + bb
-        z = z + zb
-    if act == ACT_LEAKY:
-        z = F.leaky_relu(z, negative_slope=slope)
-    elif act == ACT_ELU:
-        z = F.elu(z)
-    z = alpha * z
-    if resid is not None:
-        z = z + beta * resid
-    return z
+def _rowmap_bwd_raw(g, out, x1, wa, x2, x3, wb, resid, alpha, beta, act, slope, drop_p, drop_seed, need_dx, need_dx2,
+                    need_dx3, need_dresid, need_dw):
+    """-> (dx1, dx2, dx3, dresid, dw) — dw is the flat [nw*d_in*d_out + d_out] buffer of gr_rowmap_bwd."""
+    n, d_in = x1.shape
+    d_out = wa.shape[1]
+    dev = x1.device
+    has_b = wb is not None
+    l = lib()
+    dx1 = torch.empty((n, d_in), dtype=torch.float32, device=dev) if need_dx else None
+    dx2 = torch.empty((n, d_in), dtype=torch.float32, device=dev) if (need_dx2 and has_b) else None
+    dx3 = torch.empty((n, d_in), dtype=torch.float32, device=dev) if (need_dx3 and has_b) else None
+    dres = torch.empty((n, d_out), dtype=torch.float32, device=dev) if need_dresid else None
+    total = (2 if has_b else 1) * d_in * d_out + d_out
+    dw = torch.empty(total, dtype=torch.float32, device=dev) if need_dw else None
+    ws_bytes = l.gr_rowmap_bwd_workspace_bytes(n, d_in, d_out, int(has_b))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        check(l.gr_rowmap_bwd(
+            ptr(g), _ld(g), ptr(out), _ld(out), ptr(x1), _ld(x1), ptr(wa), ptr(x2), _ld(x2), ptr(x3), _ld(x3), ptr(wb),
+            ptr(resid), _ld(resid), float(alpha), float(beta), int(act), float(slope), n, d_in, d_out, float(drop_p),
+            int(drop_seed), ptr(dx1), _ld(dx1), ptr(dx2), _ld(dx2), ptr(dx3), _ld(dx3), ptr(dres), _ld(dres), ptr(dw),
+            ptr(ws), ws_bytes, stream_ptr()), "gr_rowmap_bwd")
+    return dx1, dx2, dx3, dres, dw
 
 
 class _RowMap(torch.autograd.Function):
+    """tensors = (x1, wa, ba, x2, x3, wb, bb, resid); ``x3_is_x1``: the bi-interaction's second factor is x1
+    itself (NGCF: both are Â x) — its gradient is folded into x1's inside the kernel."""
+
     @staticmethod
-    def forward(ctx, alpha, beta, act, slope, *tensors):
-        ctx.cfg = (alpha, beta, act, slope)
-        ctx.present = [t is not None for t in tensors]
-        ctx.save_for_backward(*[t for t in tensors if t is not None])
-        cont = [None if t is None else t.contiguous() for t in tensors]
-        return _rowmap_raw(*cont, alpha, beta, act, slope)
+    def forward(ctx, alpha, beta, act, slope, drop_p, drop_seed, x3_is_x1, x1, wa, ba, x2, x3, wb, bb, resid):
+        x1, x2, x3, resid = _rows(x1), _rows(x2), _rows(x3), _rows(resid)
+        wa = wa.contiguous()
+        wb = None if wb is None else wb.contiguous()
+        ba = None if ba is None else ba.contiguous()
+        bb = None if bb is None else bb.contiguous()
+        x3k = x1 if x3_is_x1 else x3
+        out = _rowmap_raw(x1, wa, ba, x2, x3k, wb, bb, resid, alpha, beta, act, slope, drop_p, drop_seed)
+        ctx.cfg = (alpha, beta, act, slope, drop_p, drop_seed, x3_is_x1)
+        ctx.has = (ba is not None, x2 is not None, x3 is not None, wb is not None, bb is not None, resid is not None)
+        keep_out = out if act != ACT_NONE else None
+        keep_res = resid if (act != ACT_NONE and resid is not None) else None
+        ctx.save_for_backward(x1, wa, x2, x3, wb, keep_res, keep_out)
+        return out
 
     @staticmethod
     def backward(ctx, g):
-        saved = list(ctx.saved_tensors)
-        tensors = [saved.pop(0) if p else None for p in ctx.present]
-        needs = ctx.needs_input_grad[4:]
-        with torch.enable_grad():
-            leaves = [None if t is None else t.detach().requires_grad_(nd) for t, nd in zip(tensors, needs)]
-            y = _rowmap_torch(*leaves, *ctx.cfg)
-            want = [l for l in leaves if l is not None and l.requires_grad]
-            grads = torch.autograd.grad(y, want, g, allow_unused=True) if want else []
-        it = iter(grads)
-        out = [next(it) if (l is not None and l.requires_grad) else None for l in leaves]
-        return (None, None, None, None, *out)
+        x1, wa, x2, x3, wb, resid, out = ctx.saved_tensors
+        alpha, beta, act, slope, drop_p, drop_seed, x3_is_x1 = ctx.cfg
+        has_ba, has_x2, has_x3, has_wb, has_bb, has_res = ctx.has
+        need = ctx.needs_input_grad[7:]     # x1, wa, ba, x2, x3, wb, bb, resid
+        g = _rows(g)
+        x3k = x1 if x3_is_x1 else x3
+        need_dx = need[0] or (has_wb and (need[3] or need[4]))
+        need_dw = need[1] or need[2] or need[5] or need[6]
+        dx1, dx2, dx3, dres, dw = _rowmap_bwd_raw(
+            g, out, x1, wa, x2, x3k, wb, resid, alpha, beta, act, slope, drop_p, drop_seed, need_dx,
+            has_wb and need[3], has_wb and need[4] and not x3_is_x1, has_res and need[7], need_dw)
+        d_in, d_out = wa.shape
+        dwa = dwb = db = None
+        if dw is not None:
+            dwa = dw[:d_in * d_out].view(d_in, d_out)
+            if has_wb:
+                dwb = dw[d_in * d_out:2 * d_in * d_out].view(d_in, d_out)
+            db = dw[-d_out:]
+        return (None,) * 7 + (dx1 if need[0] else None, dwa if need[1] else None, db if (has_ba and need[2]) else None,
+                              dx2, dx3, dwb if need[5] else None, db if (has_bb and need[6]) else None, dres)
 
 
 def rowmap(x1, wa, bias_a=None, x2=None, x3=None, wb=None, bias_b=None, resid=None, alpha: float = 1.0,
-           beta: float = 0.0, act: int = ACT_NONE, slope: float = 0.0) -> torch.Tensor:
-    """out = alpha * act(x1 @ wa + bias_a + (x2 * x3) @ wb + bias_b) + beta * resid  (gr_rowmap_f32)."""
-    return _RowMap.apply(float(alpha), float(beta), int(act), float(slope), x1, wa, bias_a, x2, x3, wb, bias_b, resid)
+           beta: float = 0.0, act: int = ACT_NONE, slope: float = 0.0, drop_p: float = 0.0,
+           drop_seed: int = 0) -> torch.Tensor:
+    """out = D * (alpha * act(x1 @ wa + bias_a + (x2 * x3) @ wb + bias_b) + beta * resid)  (gr_rowmap_f32);
+    D = 1 unless drop_p > 0 (layer-output dropout, mask = hash(drop_seed, element))."""
+    x3_is_x1 = x3 is not None and x3 is x1
+    return _RowMap.apply(float(alpha), float(beta), int(act), float(slope), float(drop_p), int(drop_seed), x3_is_x1,
+                         x1, wa, bias_a, x2, None if x3_is_x1 else x3, wb, bias_b, resid)
+
+
+# ------------------------------------------------------------------------------------------------
+# Group-and-Shuffle: the composed per-layer map M_l = W_conn,l W_orth,l[:, perm]
+# ------------------------------------------------------------------------------------------------
+class _GsCompose(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, skew, perm_c, perm_g):
+        skew = skew.contiguous()
+        n_layers, n_sets, nb, bs, _ = skew.shape
+        d = nb * bs
+        blocks = torch.empty_like(skew)
+        m = torch.empty((n_layers, d, d), dtype=torch.float32, device=skew.device)
+        with torch.cuda.device(skew.device):
+            check(lib().gr_gs_compose(ptr(skew), ptr(perm_c), ptr(perm_g), n_layers, n_sets, d, bs, ptr(blocks),
+                                      ptr(m), stream_ptr()), "gr_gs_compose")
+        ctx.save_for_backward(skew, blocks, perm_c, perm_g)
+        return m
+
+    @staticmethod
+    def backward(ctx, dm):
+        skew, blocks, perm_c, perm_g = ctx.saved_tensors
+        n_layers, n_sets, nb, bs, _ = skew.shape
+        dm = dm.contiguous()
+        dblocks = torch.empty_like(skew)
+        dskew = torch.empty_like(skew)
+        with torch.cuda.device(skew.device):
+            check(lib().gr_gs_compose_bwd(ptr(skew), ptr(blocks), ptr(perm_c), ptr(perm_g), n_layers, n_sets, nb * bs,
+                                          bs, ptr(dm), ptr(dblocks), ptr(dskew), stream_ptr()), "gr_gs_compose_bwd")
+        return dskew, None, None
+
+
+def gs_compose(skew: torch.Tensor, perm_c: Optional[torch.Tensor], perm_g: torch.Tensor) -> torch.Tensor:
+    """skew [L, S, nb, bs, bs] (S = 2: connection then local blocks; S = 1: local only), perm_c / perm_g [L, d]
+    int64 -> M [L, d, d] with M_l = blockdiag(exp(P - P^T))[:, perm_c] @ blockdiag(exp(Q - Q^T))[:, perm_g]
+    (bundle_layer.py:59-73, group_shuffle_layer.py:88-129, model.py:176); differentiable w.r.t. skew."""
+    return _GsCompose.apply(skew, None if perm_c is None else perm_c.contiguous(), perm_g.contiguous())
 
 
 # ------------------------------------------------------------------------------------------------
 # GAT layer
 # ------------------------------------------------------------------------------------------------
-def _gat_forward_kernels(csr, x, wcat, a_self, a_neigh, heads, dh, slope, mean_heads, elu):
+def _gat_forward_kernels(csr, x, wcat, a_self, a_neigh, heads, dh, slope, mean_heads, elu, drop_p=0.0, drop_seed=0,
+                         keep=False):
     n = x.shape[0]
     dev = x.device
     h = _rowmap_raw(x, wcat, None, None, None, None, None, None, 1.0, 0.0, ACT_NONE, 0.0)     # [N, heads*dh]
     s = torch.empty((n, heads), dtype=torch.float32, device=dev)
     t = torch.empty((n, heads), dtype=torch.float32, device=dev)
     out = torch.empty((n, dh if mean_heads else heads * dh), dtype=torch.float32, device=dev)
+    m = z = raw = None
+    if keep:
+        m, z = torch.empty_like(s), torch.empty_like(s)
     l = lib()
     with torch.cuda.device(dev):
         check(l.gr_gat_node_scores(ptr(h), h.stride(0), ptr(a_self), ptr(a_neigh), n, heads, dh, ptr(s), ptr(t),
                                    stream_ptr()), "gr_gat_node_scores")
         check(l.gr_gat_aggregate(ptr(csr.indptr), ptr(csr.indices), n, ptr(h), h.stride(0), ptr(s), ptr(t), heads,
-                                 dh, float(slope), int(mean_heads), int(elu), ptr(out), out.stride(0), None, None,
-                                 stream_ptr()), "gr_gat_aggregate")
-    return out
-
-
-def _gat_forward_torch(row, col, n, x, wcat, a_self, a_neigh, heads, dh, slope, mean_heads, elu):
-    """Edge-list restatement with stock torch ops (used for the backward pass only)."""
-    h = (x @ wcat).view(n, heads, dh)
-    s = (h * a_self.view(1, heads, dh)).sum(-1)
-    t = (h * a_neigh.view(1, heads, dh)).sum(-1)
-    e = F.leaky_relu(s[row] + t[col], negative_slope=slope)                       # [E, heads]
-    m = torch.full((n, heads), float("-inf"), device=x.device).scatter_reduce(
-        0, row.view(-1, 1).expand(-1, heads), e, reduce="amax", include_self=True)
-    p = torch.exp(e - m[row])
-    z = torch.zeros((n, heads), device=x.device).index_add_(0, row, p)
-    w = p / z[row]
-    out = torch.zeros((n, heads, dh), device=x.device).index_add_(0, row, w.unsqueeze(-1) * h[col])
-    out = out.mean(dim=1) if mean_heads else out.reshape(n, heads * dh)
-    return F.elu(out) if elu else out
+                                 dh, float(slope), int(mean_heads), int(elu), float(drop_p), int(drop_seed),
+                                 csr.n_cols, ptr(out), out.stride(0), ptr(m), ptr(z), ptr(raw),
+                                 raw.stride(0) if raw is not None else 0, stream_ptr()), "gr_gat_aggregate")
+    return out, (h, s, t, m, z, raw)
 
 
 class _GatLayer(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, wcat, a_self, a_neigh, csr, heads, dh, slope, mean_heads, elu):
-        ctx.csr, ctx.cfg = csr, (heads, dh, slope, mean_heads, elu)
-        ctx.save_for_backward(x, wcat, a_self, a_neigh)
-        return _gat_forward_kernels(csr, x.contiguous(), wcat.contiguous(), a_self.contiguous(),
-                                    a_neigh.contiguous(), heads, dh, slope, mean_heads, elu)
+    def forward(ctx, x, wcat, a_self, a_neigh, csr, heads, dh, slope, mean_heads, elu, drop_p, drop_seed):
+        x, wcat, a_self, a_neigh = _rows(x), wcat.contiguous(), a_self.contiguous(), a_neigh.contiguous()
+        keep = any(ctx.needs_input_grad[:4])
+        out, (h, s, t, m, z, raw) = _gat_forward_kernels(csr, x, wcat, a_self, a_neigh, heads, dh, slope, mean_heads,
+                                                         elu, drop_p, drop_seed, keep)
+        ctx.csr, ctx.cfg = csr, (heads, dh, slope, mean_heads, elu, drop_p, drop_seed)
+        if keep:
+            ctx.save_for_backward(x, wcat, a_self, a_neigh, h, s, t, m, z, out)
+        return out
 
     @staticmethod
     def backward(ctx, g):
-        x, wcat, a_self, a_neigh = ctx.saved_tensors
+        x, wcat, a_self, a_neigh, h, s, t, m, z, out = ctx.saved_tensors
+        heads, dh, slope, mean_heads, elu, drop_p, drop_seed = ctx.cfg
         csr = ctx.csr
-        row, col = csr.row_ids(), csr.indices.long()
-        with torch.enable_grad():
-            leaves = [t.detach().requires_grad_(True) for t in (x, wcat, a_self, a_neigh)]
-            y = _gat_forward_torch(row, col, x.shape[0], *leaves, *ctx.cfg)
-            grads = torch.autograd.grad(y, leaves, g)
-        return (*grads, None, None, None, None, None, None)
+        csr_t = csr.transpose()          # the pattern of Âᵀ (Â itself for the symmetric bipartite graph)
+        g = _rows(g)
+        n, width, dev = x.shape[0], heads * dh, x.device
+        l = lib()
+        dH = torch.empty((n, width), dtype=torch.float32, device=dev)
+        da = torch.empty(2 * width, dtype=torch.float32, device=dev)
+        ws_bytes = l.gr_gat_bwd_workspace_bytes(n, heads, dh)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            check(l.gr_gat_bwd(ptr(csr.indptr), ptr(csr.indices), ptr(csr_t.indptr), ptr(csr_t.indices), n, csr.n_cols,
+                               ptr(h), h.stride(0), ptr(s), ptr(t), ptr(m), ptr(z), ptr(out), out.stride(0), ptr(g), g.stride(0), ptr(a_self), ptr(a_neigh), heads, dh,
+                               float(slope), int(mean_heads), int(elu), float(drop_p), int(drop_seed), ptr(dH), ptr(da),
+                               ptr(ws), ws_bytes, stream_ptr()), "gr_gat_bwd")
+        need = ctx.needs_input_grad
+        dx, _, _, _, dw = _rowmap_bwd_raw(dH, None, x, wcat, None, None, None, None, 1.0, 0.0, ACT_NONE, 0.0, 0.0, 0,
+                                          need[0], False, False, False, need[1])
+        dwcat = dw[:wcat.numel()].view_as(wcat) if dw is not None else None
+        return (dx, dwcat, da[:width] if need[2] else None, da[width:] if need[3] else None) + (None,) * 8
 
 
 def gat_layer(csr: NormAdjCSR, x, weights: Sequence[torch.Tensor], a_self: Sequence[torch.Tensor],
-              a_neigh: Sequence[torch.Tensor], slope: float, concat_heads: bool, elu: bool) -> torch.Tensor:
+              a_neigh: Sequence[torch.Tensor], slope: float, concat_heads: bool, elu: bool, drop_p: float = 0.0,
+              drop_seed: int = 0) -> torch.Tensor:
     """One GATLayer.forward (gat.py:76-151) + the ELU GAT.forward applies after it (gat.py:283).
-    ``weights[h]``: nn.Linear.weight [dh, d_in]; ``a_self[h]`` / ``a_neigh[h]``: [dh, 1]."""
+    ``weights[h]``: nn.Linear.weight [dh, d_in]; ``a_self[h]`` / ``a_neigh[h]``: [dh, 1].
+    ``drop_p`` > 0: dropout on the softmaxed attention weights (gat.py:138)."""
     heads, dh = len(weights), weights[0].shape[0]
     wcat = torch.cat([w.t() for w in weights], dim=1)                       # [d_in, heads*dh]
     a_s = torch.cat([a.reshape(-1) for a in a_self])
     a_n = torch.cat([a.reshape(-1) for a in a_neigh])
-    return _GatLayer.apply(x, wcat, a_s, a_n, csr, heads, dh, float(slope), not concat_heads, elu)
+    return _GatLayer.apply(x, wcat, a_s, a_n, csr, heads, dh, float(slope), not concat_heads, elu, float(drop_p),
+                           int(drop_seed))

@@ -1,7 +1,8 @@
 """NGCF — drop-in for src/models/baselines/ngcf.py (NGCFLayer :16-86, NGCF :89-242).
 
 Per layer: n = Â x (SpMM kernel), out = LeakyReLU_0.2(W1 n + b1 + W2 (x * n) + b2) (one rowmap
-kernel: both 64x64 maps, the bi-interaction product, biases and the activation fused), dropout;
+kernel: both 64x64 maps, the bi-interaction product, biases, the activation and the train-mode
+dropout fused; backward = gr_rowmap_bwd + the SpMM on Â^T);
 the L+1 layer outputs are concatenated (final width 64 * (L+1))."""
 from __future__ import annotations
 
@@ -12,7 +13,7 @@ import torch.nn as nn
 
 from .base import BaseRecommender
 from .graph_builder import as_csr
-from .layer_ops import ACT_LEAKY, rowmap, spmm
+from .layer_ops import ACT_LEAKY, new_dropout_seed, rowmap, spmm
 
 
 class NGCFLayer(nn.Module):
@@ -26,9 +27,9 @@ class NGCFLayer(nn.Module):
     def forward(self, x: torch.Tensor, adj_matrix) -> torch.Tensor:
         csr = as_csr(adj_matrix)
         n = spmm(csr, x)
-        out = rowmap(n, self.W1.weight.t(), self.W1.bias, x, n, self.W2.weight.t(), self.W2.bias,
-                     act=ACT_LEAKY, slope=0.2)
-        return self.dropout(out)
+        p = self.dropout.p if (self.training and self.dropout.p > 0) else 0.0      # ngcf.py:86, fused
+        return rowmap(n, self.W1.weight.t(), self.W1.bias, x, n, self.W2.weight.t(), self.W2.bias,
+                      act=ACT_LEAKY, slope=0.2, drop_p=p, drop_seed=new_dropout_seed() if p else 0)
 
 
 class NGCF(BaseRecommender):

@@ -3,8 +3,10 @@ src/models/orthogonal_bundle/{model.py:29, group_shuffle_layer.py:12, bundle_lay
 
 Per layer the reference computes  c = Â x ; t = c @ W_conn ; g = (t @ W_orth)[:, perm] ;
 x = (1-a) g + a x0.  The two 64x64 maps and the column permutation compose into one matrix
-M = W_conn (W_orth[:, perm]) built with stock torch ops (48 tiny matrix_exp calls, autograd kept),
-so a layer is one SpMM kernel plus one rowmap kernel (dense map + residual fused); the layer
+M = W_conn (W_orth[:, perm]) built on the device by gr_gs_compose (block matrix exponentials +
+composition in two launches for all layers; backward gr_gs_compose_bwd through the adjoint Frechet
+derivative of exp — the reference runs 48 matrix_exp calls per forward), so a layer is one SpMM
+kernel plus one rowmap kernel (dense map + residual fused; backward gr_rowmap_bwd); the layer
 outputs are combined with softmax(layer_weights).  State-dict keys, constructor signature and
 RNG order match the reference.  The edge-list mode (use_edge_index=True, off by default,
 model.py:64) is not part of the hot path and raises NotImplementedError."""
@@ -18,7 +20,7 @@ import torch.nn.functional as F
 
 from .base import BaseRecommender
 from .graph_builder import as_csr
-from .layer_ops import rowmap, spmm
+from .layer_ops import gs_compose, new_dropout_seed, rowmap, spmm
 
 
 def _block_orthogonal(skew_params) -> torch.Tensor:
@@ -107,11 +109,20 @@ class OrthogonalBundleGNN(BaseRecommender):
         self.dropout_layer = nn.Dropout(dropout) if dropout > 0 else None
         self.layer_weights = nn.Parameter(torch.ones(n_layers + 1))
 
-    def _layer_matrix(self, l: int) -> torch.Tensor:
-        m = self.local_transform_layers[l].matrix()
+    def _layer_matrices(self) -> torch.Tensor:
+        """[L, d, d]: M_l = W_conn,l @ W_orth,l[:, perm_l] for every layer in two launches (gr_gs_compose: block
+        matrix exponentials + composition; differentiable w.r.t. all skew parameters)."""
+        sets = []
         if self.use_parallel_transport:
-            m = self.connection_layers[l]() @ m
-        return m
+            sets.append([p for layer in self.connection_layers for p in layer.skew_params])
+        sets.append([p for layer in self.local_transform_layers for p in layer.skew_params])
+        nb = self.embedding_dim // self.block_size
+        skew = torch.stack([p for group in sets for p in group]).view(
+            len(sets), self.n_layers, nb, self.block_size, self.block_size).transpose(0, 1)
+        perm_c = (torch.stack([layer.shuffle_perm for layer in self.connection_layers])
+                  if self.use_parallel_transport else None)
+        perm_g = torch.stack([layer.perm for layer in self.local_transform_layers])
+        return gs_compose(skew, perm_c, perm_g)
 
     def _layers(self, adj_matrix, residual: bool) -> List[torch.Tensor]:
         if self.use_edge_index:
@@ -123,14 +134,15 @@ class OrthogonalBundleGNN(BaseRecommender):
         x0 = torch.cat([self.user_embedding.weight, self.item_embedding.weight], dim=0)
         x, outs = x0, [x0]
         a = self.residual_alpha
+        ms = self._layer_matrices()
         for l in range(self.n_layers):
             c = spmm(csr, x)
             if residual:
-                x = rowmap(c, self._layer_matrix(l), resid=x0, alpha=1.0 - a, beta=a)
-                if self.dropout_layer is not None:
-                    x = self.dropout_layer(x)
+                p = self.dropout if (self.training and self.dropout_layer is not None) else 0.0   # model.py:198-199
+                x = rowmap(c, ms[l], resid=x0, alpha=1.0 - a, beta=a, drop_p=p,
+                           drop_seed=new_dropout_seed() if p else 0)
             else:
-                x = rowmap(c, self._layer_matrix(l))
+                x = rowmap(c, ms[l])
             outs.append(x)
         return outs
 

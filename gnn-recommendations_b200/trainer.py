@@ -104,13 +104,17 @@ class Trainer:
         return torch.cat([user_emb, item_emb], dim=0)
 
     def train_epoch(self) -> float:
-        self.model.train()
         sampler = self._get_sampler()
+        return self.train_steps(len(sampler) // self.batch_size + 1)          # trainer.py:237
+
+    def train_steps(self, n_steps: int) -> float:
+        """``n_steps`` bodies of the reference's epoch loop (trainer.py:237-279); ``train_epoch`` runs
+        ``len(train) // batch_size + 1`` of them.  Returns the mean loss."""
+        self.model.train()
         adj = self.dataset.get_torch_adjacency(normalized=True).to(self.device)
-        n_batches_total = len(sampler) // self.batch_size + 1          # trainer.py:237
         total = torch.zeros((), dtype=torch.float64, device=self.device)
         n_batches = 0
-        for _ in range(n_batches_total):
+        for _ in range(int(n_steps)):
             users, pos, neg = self._sample_batch()
             if users.numel() == 0:
                 continue

@@ -161,7 +161,44 @@ int gr_peer_scatter_rows(const float *src, int64_t lds, int64_t n_rows, int32_t 
 int gr_rowmap_f32(const float *x1, int64_t ld1, const float *wa, const float *bias_a, const float *x2, int64_t ld2,
                   const float *x3, int64_t ld3, const float *wb, const float *bias_b, const float *resid,
                   int64_t ldr, float alpha, float beta, int32_t act, float slope, int64_t n_rows, int32_t d_in,
-                  int32_t d_out, float *out, int64_t ldo, void *stream);
+                  int32_t d_out, float drop_p, uint64_t drop_seed, float *out, int64_t ldo, void *stream);
+
+/* Backward of gr_rowmap_f32 — replaces what autograd runs under loss.backward() (src/training/trainer.py:270)
+ * for NGCFLayer.forward (ngcf.py:69-84), the Group-and-Shuffle maps (model.py:176-195) and the GAT head
+ * projections (gat.py:99).  With drop_p > 0 the forward output is  D * (alpha*act(z) + beta*R),  D = keep/(1-p)
+ * re-derived from drop_seed (the layer-output nn.Dropout of ngcf.py:86 / model.py:198-199 fused).
+ * Given g = dL/dout [n, d_out]:
+ *     dz = alpha * D*g * act'(z)   (act' recovered from `out`, required when act != 0)
+ *     dx1 = dz Wa^T;  dP = dz Wb^T;  dx2 = dP*X3;  dx3 = dP*X2;  dresid = beta * D*g
+ *     dw  = [ X1^T dz  |  (X2*X3)^T dz (if wb)  |  column sums of dz ]   (floats: nw*d_in*d_out + d_out)
+ * Any of dx1/dx2/dx3/dresid/dw may be NULL (skipped; dx2/dx3 need dx1).  dx3 == NULL with wb != NULL means
+ * "X3 is X1" (NGCF: both are A x): dx3 is added into dx1.  Deterministic: per-CTA partial sums reduced in a
+ * fixed order.  workspace: gr_rowmap_bwd_workspace_bytes(n_rows, d_in, d_out, wb != NULL). */
+size_t gr_rowmap_bwd_workspace_bytes(int64_t n_rows, int32_t d_in, int32_t d_out, int32_t has_b);
+int gr_rowmap_bwd(const float *g, int64_t ldg, const float *out, int64_t ldo, const float *x1, int64_t ld1,
+                  const float *wa, const float *x2, int64_t ld2, const float *x3, int64_t ld3, const float *wb,
+                  const float *resid, int64_t ldr, float alpha, float beta, int32_t act, float slope,
+                  int64_t n_rows, int32_t d_in, int32_t d_out, float drop_p, uint64_t drop_seed, float *dx1,
+                  int64_t ldd1, float *dx2, int64_t ldd2, float *dx3, int64_t ldd3, float *dresid, int64_t lddr,
+                  float *dw, void *workspace, size_t workspace_bytes, void *stream);
+
+/* Group-and-Shuffle orthogonal maps of OrthogonalBundleGNN, composed per layer on the device:
+ *     M_l = blockdiag(exp(P_k - P_k^T))[:, perm_conn_l]  @  blockdiag(exp(Q_k - Q_k^T))[:, perm_local_l]
+ * replacing BundleConnectionLayer.forward (src/models/orthogonal_bundle/bundle_layer.py:56-73),
+ * GroupShuffleLayer._build_orthogonal_matrix / forward (group_shuffle_layer.py:88-129) and the two matmuls of
+ * model.py:176 — 16 torch.matrix_exp calls, 2 block_diag, 2 index ops and a 64x64 GEMM per layer there.
+ *   skew   [n_layers, n_sets, d/bs, bs, bs] f32: the skew_params; n_sets = 2 (set 0 connection P, set 1 local Q)
+ *          or 1 (use_parallel_transport = False: M_l = blockdiag(exp(Q))[:, perm_local_l]; perm_conn = NULL)
+ *   perm_* [n_layers, d] int64 (the torch.randperm buffers);  bs <= 16, d % bs == 0
+ *   blocks [same shape as skew] out: the block exponentials (kept for the backward pass);  m_out [n_layers, d, d]
+ * Matrix exponentials: scaling-and-squaring, degree-12 Taylor in double (then rounded to f32).
+ * gr_gs_compose_bwd: dm = dL/dM [n_layers, d, d] -> dskew (same shape as skew) through the adjoint Frechet
+ * derivative of exp; dblocks_ws: scratch of the same size as skew. */
+int gr_gs_compose(const float *skew, const int64_t *perm_conn, const int64_t *perm_local, int32_t n_layers,
+                  int32_t n_sets, int32_t d, int32_t bs, float *blocks, float *m_out, void *stream);
+int gr_gs_compose_bwd(const float *skew, const float *blocks, const int64_t *perm_conn, const int64_t *perm_local,
+                      int32_t n_layers, int32_t n_sets, int32_t d, int32_t bs, const float *dm, float *dblocks_ws,
+                      float *dskew, void *stream);
 
 /* GAT (src/models/baselines/gat.py:76-151) over the CSR PATTERN of the adjacency (its values are
  * ignored, gat.py:120-127) instead of the reference's dense N x N temporaries.
@@ -176,7 +213,27 @@ int gr_gat_node_scores(const float *h, int64_t ldh, const float *a_self, const f
                        int32_t heads, int32_t dh, float *s, float *t, void *stream);
 int gr_gat_aggregate(const int32_t *indptr, const int32_t *indices, int64_t n_rows, const float *h, int64_t ldh,
                      const float *s, const float *t, int32_t heads, int32_t dh, float slope, int32_t mean_heads,
-                     int32_t elu, float *out, int64_t ldo, float *m_out, float *z_out, void *stream);
+                     int32_t elu, float drop_p, uint64_t drop_seed, int64_t n_cols, float *out, int64_t ldo,
+                     float *m_out, float *z_out, float *raw_out, int64_t ldraw, void *stream);
+/*   drop_p > 0: the reference's dropout on the softmaxed attention weights (gat.py:138) — every edge weight is
+ *       kept with probability 1-p and scaled by 1/(1-p) (the normaliser still sums all edges); the mask is a
+ *       counter-based hash of (drop_seed, row, column, head), so the backward pass re-derives it.
+ *   raw_out (optional, [n_rows, heads*dh]): per-head aggregates before head-mean / ELU, for the backward pass.
+ *
+ * gr_gat_bwd: backward of node scores + aggregation (autograd under trainer.py:270 through gat.py:97-149).
+ *   Inputs: what the forward produced (h, s, t, m, z, out) and dout = dL/dout.  (t_indptr, t_indices) is the
+ *   CSR of the TRANSPOSED pattern (the same arrays as (indptr, indices) for the symmetric bipartite adjacency).
+ *   Outputs: dH [n, heads*dh] (complete gradient w.r.t. H = x Wcat, incl. the a_self / a_neigh paths) and
+ *   da [2, heads*dh] = (d a_self | d a_neigh).  One warp per row recomputes the softmax weights from (m, z);
+ *   the softmax-backward centring term D_i = sum_k alpha_ik <dO_i, H_k> is re-formed from the same weights
+ *   (not from the forward output) so that the differences x_ik - D_i of over-smoothed deep layers survive in
+ *   fp32.  No atomics, no edge-sized temporaries, deterministic.  dh/4 must be a power of two. */
+size_t gr_gat_bwd_workspace_bytes(int64_t n_rows, int32_t heads, int32_t dh);
+int gr_gat_bwd(const int32_t *indptr, const int32_t *indices, const int32_t *t_indptr, const int32_t *t_indices,
+               int64_t n_rows, int64_t n_cols, const float *h, int64_t ldh, const float *s, const float *t,
+               const float *m, const float *z, const float *out, int64_t ldo, const float *dout, int64_t lddo, const float *a_self, const float *a_neigh, int32_t heads,
+               int32_t dh, float slope, int32_t mean_heads, int32_t elu, float drop_p, uint64_t drop_seed,
+               float *dH, float *da, void *workspace, size_t workspace_bytes, void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * BPR step

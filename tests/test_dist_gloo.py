@@ -190,3 +190,20 @@ def test_item_shard_covers_range():
         spans = [item_shard(n, w, r) for r in range(w)]
         assert spans[0][0] == 0 and spans[-1][1] == n
         assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+
+
+def test_sharded_training_refuses_row_normalised_graphs():
+    """ShardedLightGCN's backward applies the forward row blocks to the gradient, which is the
+    gradient only for a symmetric adjacency; a 'row'-normalised (D^-1 A) partition must be refused, not
+    silently mis-trained."""
+    sp = synth_split("tiny", 42)
+    nu, ni = sp["n_users"], sp["n_items"]
+    adj = po.build_norm_adj(*sp["train"], nu, ni, normalization="row")
+    part = RowPartition(torch.from_numpy(adj["indptr"]), 2)
+    local = _cpu_local_csr(part, adj, 0)
+    local.full_symmetric = False            # what RowPartition.local_csr / build_local_csr record for 'row'
+    x0 = torch.zeros(part.n_local(0), 8)
+    with pytest.raises(ValueError, match="symmetric"):
+        ShardedLightGCN(local, part, 0, x0, nu, 2, propagate=lambda x: x, bpr=lambda *a: None, fused_optimizer=False)
+    local.full_symmetric = True
+    ShardedLightGCN(local, part, 0, x0, nu, 2, propagate=lambda x: x, bpr=lambda *a: None, fused_optimizer=False)

@@ -76,7 +76,29 @@ def test_build_random_graphs_vs_oracle(seed):
 def test_coo_to_csr_paths(tiny_ref):
     coo = po.to_torch_coo(tiny_ref).to(DEV)
     assert_csr_equal(g.NormAdjCSR.from_torch_coo(coo), tiny_ref)
-    assert g.as_csr(coo) is g.as_csr(coo)                          # cached by content pointers
+    first = g.as_csr(coo)
+    assert g.as_csr(coo) is first                                  # same tensor object: identity fast path
+    # the reference rebuilds the adjacency tensor every epoch / validate: a NEW tensor with the
+    # same content must hit the cache (keyed by content, the COO tensor is not retained) ...
+    import gc, weakref
+    fresh = po.to_torch_coo(tiny_ref).to(DEV)
+    assert fresh._indices().data_ptr() != coo._indices().data_ptr()
+    assert g.as_csr(fresh) is first
+    wr = weakref.ref(fresh)
+    del fresh
+    gc.collect()
+    assert wr() is None                                            # ... and is not pinned in HBM by the cache
+    # ... while different content (one value changed) must not
+    other = po.to_torch_coo(tiny_ref).to(DEV)
+    other._values()[7] *= 2.0
+    assert g.as_csr(other) is not first
+    # host CSR round trip (8 B per entry instead of the int64 COO's 20 B)
+    ip, ix, vl = first.to_host()
+    assert ip.is_pinned() and ip.dtype == torch.int32 and ix.dtype == torch.int32
+    again = g.NormAdjCSR.from_host_csr(ip, ix, vl, device=DEV)
+    assert_csr_equal(again, tiny_ref)
+    xx = torch.randn(first.n_cols, 64, generator=torch.Generator().manual_seed(0)).to(DEV)
+    assert torch.equal(again.spmm(xx)[0], first.spmm(xx)[0])
     # unsorted rows: storage order inside a row must be preserved
     perm = torch.randperm(coo._values().numel(), generator=torch.Generator().manual_seed(1)).to(DEV)
     shuffled = torch.sparse_coo_tensor(coo._indices()[:, perm], coo._values()[perm], coo.shape)

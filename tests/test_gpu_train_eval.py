@@ -438,7 +438,7 @@ def test_trainer_epoch_other_models_vs_reference(name, tiny, tmp_path):
             assert np.array_equal(v.cpu().numpy(), want), k
             continue
         moved = np.abs(want - z[f"{name}/init/{k}"]).max()
-        np.testing.assert_allclose(v.detach().cpu().numpy(), want, rtol=2e-3, atol=max(5e-6, 0.02 * float(moved)), err_msg=k)
+        np.testing.assert_allclose(v.detach().cpu().numpy(), want, rtol=1e-4, atol=max(2e-6, 1e-3 * float(moved)), err_msg=k)
 
 
 def test_topk_tensor_core_kernel_failure_falls_back_to_exact(monkeypatch):
@@ -529,3 +529,38 @@ def test_export_embeddings_and_warm_start_round_trip(tiny, tmp_path):
     with pytest.raises(ValueError):
         g.Trainer(g.LightGCN(nu, ni, embedding_dim=32), ds,
                   dict(CFG, checkpoint_dir=str(tmp_path / "c4"), warm_start=dict(ws, apply_to=None)), device=torch.device(DEV))
+
+
+# ----------------------------------------------------------------------------- item-sharded evaluation, ranks emulated
+@pytest.mark.parametrize("world,tc", [(2, False), (4, True), (8, True), (3, None)])
+def test_item_sharded_topk_partials_merge_to_the_single_gpu_lists(world, tc):
+    """SURVEY §8e / BASELINE configs[3]: every rank ranks ALL users against its item id range, the per-rank
+    top-k (score, id) lists are merged under (score desc, id asc).  The ranks are emulated on one GPU (the
+    all-gather is a concatenation); exact partial kernel and the tcgen05 nomination path on each shard (seen CSR
+    cut to the shard) must both merge to the bit-identical single-GPU lists, incl. users whose seen items empty
+    a shard."""
+    from gnn_recommendations_b200.dist import full_rank_topk_sharded, item_shard, merge_topk_partials
+    rng = np.random.default_rng(world)
+    nu, ni, d, k = 700, 20000, 64, 20
+    ue = torch.from_numpy(rng.standard_normal((nu, d)).astype(np.float32)).to(DEV)
+    ie = torch.from_numpy(rng.standard_normal((ni, d)).astype(np.float32)).to(DEV)
+    ie[100:140] = ie[100]                                              # exact ties across a shard boundary or inside
+    eu = np.arange(0, nu, 2)
+    seen_u = rng.integers(0, nu, 30000)
+    seen_i = rng.integers(0, ni, 30000)
+    lo0, hi0 = item_shard(ni, world, 0)                                # user 0 has seen ALL of shard 0
+    seen_u = np.concatenate([seen_u, np.zeros(hi0 - lo0, np.int64)])
+    seen_i = np.concatenate([seen_i, np.arange(lo0, hi0)])
+    from gnn_recommendations_b200.evaluator import seen_csr
+    ip, it = seen_csr(eu, nu, (seen_u, seen_i))
+    want = g.full_rank_topk(ue, ie, eu, ip, it, k, tensor_cores=False)
+    parts_s, parts_i = [], []
+    for r in range(world):
+        lo, hi = item_shard(ni, world, r)
+        ps, pi = full_rank_topk_sharded(ue, ie[lo:hi].contiguous(), lo, hi, eu, ip, it, k, world, tensor_cores=tc,
+                                        return_partial=True)
+        assert ps.shape[1:] == (len(eu), k) and pi.dtype == torch.int32
+        parts_s.append(ps)
+        parts_i.append(pi)
+    got = merge_topk_partials(torch.cat(parts_s), torch.cat(parts_i), k)
+    assert torch.equal(got, want)
