@@ -32,7 +32,7 @@ SIGNATURES = {
     "gr_csr_normalize": (C.c_int, [_p, _p, _p, _p, _p, _i64, _i64, _i64, _i32, _p, _p, _p]),
     "gr_row_groups": (C.c_int, [_p, _i64, _i32, _i32, _p, _p]),
     "gr_spmm_csr_f32": (C.c_int, [_p, _p, _p, _p, _i32, _p, _i32, _p, _i32, _p, _p, _i32, _i32, _i64, _i32,
-                                  _p, _i64, _p, _i64, _p, _i64, _p, _i64, _f32, _i32, _p, _i32, _i32, _i64, _p]),
+                                  _p, _i64, _p, _i64, _p, _i64, _p, _i64, _f32, _i32, _p, _i32, _i32, _i64, _p, _p]),
     "gr_peer_scatter_rows": (C.c_int, [_p, _i64, _i64, _i32, _p, _i32, _i32, _i64, _i64, _p]),
     "gr_rowmap_f32": (C.c_int, [_p, _i64, _p, _p, _p, _i64, _p, _i64, _p, _p, _p, _i64, _f32, _f32, _i32, _f32,
                                 _i64, _i32, _i32, _f32, _u64, _p, _i64, _p]),
@@ -43,11 +43,12 @@ SIGNATURES = {
     "gr_gs_compose": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _i32, _p, _p, _p]),
     "gr_gs_compose_bwd": (C.c_int, [_p, _p, _p, _p, _i32, _i32, _i32, _i32, _p, _p, _p, _p]),
     "gr_gat_node_scores": (C.c_int, [_p, _i64, _p, _p, _i64, _i32, _i32, _p, _p, _p]),
+    "gr_gat_aggregate_workspace_bytes": (_sz, [_i32, _i32, _i32]),
     "gr_gat_aggregate": (C.c_int, [_p, _p, _i64, _p, _i64, _p, _p, _i32, _i32, _f32, _i32, _i32, _f32, _u64, _i64,
-                                   _p, _i64, _p, _p, _p, _i64, _p]),
-    "gr_gat_bwd_workspace_bytes": (_sz, [_i64, _i32, _i32]),
+                                   _p, _p, _i64, _p, _p, _p, _sz, _p]),
+    "gr_gat_bwd_workspace_bytes": (_sz, [_i64, _i32, _i32, _i32, _i32, _i32]),
     "gr_gat_bwd": (C.c_int, [_p, _p, _p, _p, _i64, _i64, _p, _i64, _p, _p, _p, _p, _p, _i64, _p, _i64,
-                             _p, _p, _i32, _i32, _f32, _i32, _i32, _f32, _u64, _p, _p, _p, _sz, _p]),
+                             _p, _p, _i32, _i32, _f32, _i32, _i32, _f32, _u64, _p, _p, _p, _p, _p, _sz, _p]),
     "gr_sample_bpr_batch": (_i64, [_p, _p, _p, _p, _p, _i64, _i64, _i64, _p, _p, _p, _p, _p]),
     "gr_bpr_workspace_bytes": (_sz, [_i64]),
     "gr_bpr_fused": (C.c_int, [_p, _i64, _i64, _i64, _p, _p, _p, _i64, _i32, _f32, _p, _i64, _p, _p, _sz, _p]),
@@ -64,7 +65,7 @@ SIGNATURES = {
     "gr_temporal_split_workspace_bytes": (_sz, [_i64]),
     "gr_temporal_split": (C.c_int, [_p, _p, _p, _i64, _i64, _i64, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "gr_clip_adam_workspace_bytes": (_sz, [_p, _i32]),
-    "gr_clip_adam_fused": (C.c_int, [_p, _p, _p, _p, _p, _i32] + [C.c_double] * 7 + [_p, _p, _sz, _p]),
+    "gr_clip_adam_fused": (C.c_int, [_p, _p, _p, _p, _p, _i32] + [C.c_double] * 7 + [_p, _p, _p, _sz, _p]),
     "gr_topk_metrics_workspace_bytes": (_sz, [_i64, _i64, _i32]),
     "gr_topk_metrics": (C.c_int, [_p, _i64, _i32, _p, _p, _i64, _p, _i32, _p, _p, _p, _p, _p, _sz, _p]),
     "gr_topk_tc_supported": (C.c_int, [_i32, _i32]),
@@ -72,6 +73,12 @@ SIGNATURES = {
     "gr_score_topk_tc": (C.c_int, [_p, _i64, _p, _i64, _i32, _p, _i64, _i64, _p, _p, _i32, _i32, _p, _p, _p, _p,
                                    _p, _sz, _p]),
 }
+
+
+class GatSegments(C.Structure):
+    """include/gr_b200.h: gr_gat_segments (host struct of device arrays)."""
+    _fields_ = [("seg_len", _i32), ("n_seg", _i32), ("n_long", _i32), ("seg_row", _p), ("seg_begin", _p),
+                ("seg_end", _p), ("long_rows", _p), ("long_seg_ptr", _p)]
 
 
 class GrError(RuntimeError):

@@ -120,6 +120,11 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// --- shared launch helpers (layers_bwd.cu) --------------------------------------------------------
+int persistent_grid(int work_items, int per_sm);      // min(work_items, SMs * per_sm), >= 1
+// out[e] = sum_p partial[p][e] (p ascending, double accumulator); returns non-zero on launch failure
+int launch_reduce_partials(const float *partial, int n_part, long long total, float *out, cudaStream_t st);
+
 // --- device radix sort (graph.cu) -------------------------------------------------------------
 // LSD radix sort of 64-bit keys (optionally carrying a 32-bit payload), 8 bits per pass,
 // stable.  Sorted data ends in keys_a/payload_a when `*in_a_out` is true, else in *_b.

@@ -155,170 +155,6 @@ __global__ void __launch_bounds__(256) rowmap_kernel(const RowMapArgs a) {
     }
 }
 
-// =============================================================================================
-// GAT
-// =============================================================================================
-// s[i,h] = <H[i, h*dh : (h+1)*dh], a_self[h]>,  t likewise with a_neigh.  One warp per node.
-__global__ void __launch_bounds__(256) gat_node_scores_kernel(const float *h, long long ldh, const float *a_self,
-                                                              const float *a_neigh, int n, int heads, int dh,
-                                                              float *s, float *t) {
-    const int lane = threadIdx.x & 31;
-    const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (i >= n) return;
-    for (int hd = 0; hd < heads; ++hd) {
-        float ps = 0.f, pt = 0.f;
-        for (int f = lane; f < dh; f += 32) {
-            const float v = __ldg(h + (long long)i * ldh + hd * dh + f);
-            ps = __fmaf_rn(v, __ldg(a_self + hd * dh + f), ps);
-            pt = __fmaf_rn(v, __ldg(a_neigh + hd * dh + f), pt);
-        }
-#pragma unroll
-        for (int o = 16; o; o >>= 1) {
-            ps += __shfl_xor_sync(0xffffffffu, ps, o);
-            pt += __shfl_xor_sync(0xffffffffu, pt, o);
-        }
-        if (lane == 0) {
-            s[(long long)i * heads + hd] = ps;
-            t[(long long)i * heads + hd] = pt;
-        }
-    }
-}
-
-struct GatArgs {
-    const int *indptr, *indices;
-    const float *h;
-    long long ldh;
-    const float *s, *t;
-    int n_rows, heads, dh;
-    float slope;
-    int mean_heads;  // 0: concat heads -> width heads*dh; 1: average heads -> width dh
-    int elu;
-    float *out;
-    long long ldo;
-    float *m_out, *z_out;  // [n_rows, heads] softmax statistics for the backward pass (may be NULL)
-    float *raw_out;        // [n_rows, heads*dh] per-head aggregate before head-mean / ELU (may be NULL)
-    long long ldraw;
-    long long n_cols;
-    unsigned drop_thr;     // attention dropout (gat.py:138): weight kept with prob 1-p, scaled by 1/(1-p)
-    float drop_scale;
-    unsigned long long drop_seed;
-};
-
-// One warp per row, online softmax (running max / running sum, rescaled accumulator), one pass over
-// the neighbours; lane owns float4 slots lane, lane+32 of the heads*dh wide row.  SLOTS = 1 or 2.
-template <int SLOTS>
-__global__ void __launch_bounds__(256) gat_aggregate_kernel(const GatArgs a) {
-    const int lane = threadIdx.x & 31;
-    const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (i >= a.n_rows) return;
-    const int width4 = a.heads * a.dh / 4;
-    const int dh4 = a.dh / 4;
-    int head[SLOTS];
-    bool on[SLOTS];
-    const int hgroups = (a.heads + 3) >> 2;
-    float si[SLOTS], m[SLOTS], z[SLOTS];
-    float4 acc[SLOTS];
-#pragma unroll
-    for (int q = 0; q < SLOTS; ++q) {
-        const int slot = lane + 32 * q;
-        on[q] = slot < width4;
-        head[q] = on[q] ? slot / dh4 : 0;
-        si[q] = __ldg(a.s + (long long)i * a.heads + head[q]);
-        m[q] = -CUDART_INF_F;
-        z[q] = 0.f;
-        acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    const int start = a.indptr[i], end = a.indptr[i + 1];
-    for (int base = start; base < end; base += 32) {
-        const int mycol = (base + lane < end) ? __ldg(a.indices + base + lane) : 0;
-        const int cnt = min(32, end - base);
-        for (int k = 0; k < cnt; k += 4) {
-            float4 hv[4][SLOTS];
-            float tv[4][SLOTS];
-            int jj[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int j = __shfl_sync(0xffffffffu, mycol, (k + u) & 31);
-                jj[u] = j;
-                if (k + u < cnt) {
-#pragma unroll
-                    for (int q = 0; q < SLOTS; ++q)
-                        if (on[q]) {
-                            hv[u][q] = __ldg(reinterpret_cast<const float4 *>(a.h + (long long)j * a.ldh) + lane + 32 * q);
-                            tv[u][q] = __ldg(a.t + (long long)j * a.heads + head[q]);
-                        }
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (k + u < cnt) {
-#pragma unroll
-                    for (int q = 0; q < SLOTS; ++q)
-                        if (on[q]) {
-                            float e = si[q] + tv[u][q];
-                            e = e > 0.f ? e : e * a.slope;
-                            const float mn = fmaxf(m[q], e);
-                            const float sc = expf(m[q] - mn);   // exp(-inf) = 0 on the first neighbour
-                            float w = expf(e - mn);
-                            z[q] = z[q] * sc + w;
-                            if (a.drop_thr) {   // the softmax normaliser keeps every edge; only the weight is dropped
-                                const unsigned long long bits = drop_bits(
-                                    a.drop_seed, ((unsigned long long)i * a.n_cols + jj[u]) * hgroups + (head[q] >> 2));
-                                w = drop_keep(bits, head[q] & 3, a.drop_thr) ? w * a.drop_scale : 0.f;
-                            }
-                            acc[q].x = acc[q].x * sc + w * hv[u][q].x;
-                            acc[q].y = acc[q].y * sc + w * hv[u][q].y;
-                            acc[q].z = acc[q].z * sc + w * hv[u][q].z;
-                            acc[q].w = acc[q].w * sc + w * hv[u][q].w;
-                            m[q] = mn;
-                        }
-                }
-            }
-        }
-    }
-    // out = acc / z   (a row without neighbours gives 0/0 = NaN, like the reference's softmax of -inf)
-#pragma unroll
-    for (int q = 0; q < SLOTS; ++q)
-        if (on[q]) {
-            acc[q].x /= z[q]; acc[q].y /= z[q]; acc[q].z /= z[q]; acc[q].w /= z[q];
-            const int slot = lane + 32 * q;
-            if (a.m_out && (slot % dh4) == 0) {
-                a.m_out[(long long)i * a.heads + head[q]] = m[q];
-                a.z_out[(long long)i * a.heads + head[q]] = z[q];
-            }
-            if (a.raw_out) *reinterpret_cast<float4 *>(a.raw_out + (long long)i * a.ldraw + slot * 4) = acc[q];
-        }
-    if (!a.mean_heads) {
-#pragma unroll
-        for (int q = 0; q < SLOTS; ++q)
-            if (on[q]) {
-                float4 o = acc[q];
-                if (a.elu) { o.x = act_apply(o.x, 2, 0.f); o.y = act_apply(o.y, 2, 0.f); o.z = act_apply(o.z, 2, 0.f); o.w = act_apply(o.w, 2, 0.f); }
-                *reinterpret_cast<float4 *>(a.out + (long long)i * a.ldo + (lane + 32 * q) * 4) = o;
-            }
-    } else {
-        // average over heads (torch.stack(heads).mean(0): left-to-right sum / heads): slot (head, f4)
-        // -> output slot f4.  Heads of one f4 live in lanes f4 + dh4*head (mod 32) across the SLOTS.
-        __shared__ float4 stage[8][64];
-        float4 *st = stage[threadIdx.x >> 5];
-#pragma unroll
-        for (int q = 0; q < SLOTS; ++q)
-            if (on[q]) st[lane + 32 * q] = acc[q];
-        __syncwarp();
-        for (int f = lane; f < dh4; f += 32) {
-            float4 sum = st[f];
-            for (int hd = 1; hd < a.heads; ++hd) {
-                const float4 v = st[hd * dh4 + f];
-                sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
-            }
-            const float hh = (float)a.heads;
-            float4 o = make_float4(sum.x / hh, sum.y / hh, sum.z / hh, sum.w / hh);
-            if (a.elu) { o.x = act_apply(o.x, 2, 0.f); o.y = act_apply(o.y, 2, 0.f); o.z = act_apply(o.z, 2, 0.f); o.w = act_apply(o.w, 2, 0.f); }
-            *reinterpret_cast<float4 *>(a.out + (long long)i * a.ldo + f * 4) = o;
-        }
-    }
-}
-
 }  // namespace gr
 
 using namespace gr;
@@ -354,43 +190,3 @@ extern "C" int gr_rowmap_f32(const float *x1, int64_t ld1, const float *wa, cons
     return GR_OK;
 }
 
-extern "C" int gr_gat_node_scores(const float *h, int64_t ldh, const float *a_self, const float *a_neigh,
-                                  int64_t n_rows, int32_t heads, int32_t dh, float *s, float *t, void *stream) {
-    if (!h || !a_self || !a_neigh || !s || !t || n_rows < 0 || heads <= 0 || dh <= 0 || ldh < (int64_t)heads * dh)
-        return GR_ERR_INVALID;
-    if (n_rows == 0) return GR_OK;
-    if (n_rows > 0x7fffffffLL) return GR_ERR_OVERFLOW;
-    gat_node_scores_kernel<<<(unsigned)((n_rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        h, ldh, a_self, a_neigh, (int)n_rows, heads, dh, s, t);
-    GR_LAUNCH_CHECK();
-    return GR_OK;
-}
-
-extern "C" int gr_gat_aggregate(const int32_t *indptr, const int32_t *indices, int64_t n_rows, const float *h,
-                                int64_t ldh, const float *s, const float *t, int32_t heads, int32_t dh,
-                                float slope, int32_t mean_heads, int32_t elu, float drop_p, uint64_t drop_seed,
-                                int64_t n_cols, float *out, int64_t ldo, float *m_out, float *z_out, float *raw_out,
-                                int64_t ldraw, void *stream) {
-    if (!indptr || !indices || !h || !s || !t || !out || n_rows < 0 || heads <= 0 || dh <= 0) return GR_ERR_INVALID;
-    if (!(drop_p >= 0.f) || drop_p >= 1.f || n_cols < 0) return GR_ERR_INVALID;
-    if (raw_out && ((ldraw & 3) || ldraw < (int64_t)heads * dh || !aligned16(raw_out))) return GR_ERR_INVALID;
-    if ((m_out == nullptr) != (z_out == nullptr)) return GR_ERR_INVALID;
-    if (n_rows == 0) return GR_OK;
-    const int width = heads * dh;
-    if ((dh & 3) || width > 256 || (ldh & 3) || (ldo & 3) || ldh < width) return GR_ERR_UNSUPPORTED;
-    if (ldo < (mean_heads ? dh : width)) return GR_ERR_INVALID;
-    if (!aligned16(h) || !aligned16(out)) return GR_ERR_INVALID;
-    if (n_rows > 0x7fffffffLL) return GR_ERR_OVERFLOW;
-    GatArgs a;
-    a.indptr = indptr; a.indices = indices; a.h = h; a.ldh = ldh; a.s = s; a.t = t;
-    a.n_rows = (int)n_rows; a.heads = heads; a.dh = dh; a.slope = slope; a.mean_heads = mean_heads; a.elu = elu;
-    a.out = out; a.ldo = ldo; a.m_out = m_out; a.z_out = z_out; a.raw_out = raw_out; a.ldraw = ldraw;
-    a.n_cols = n_cols;
-    a.drop_thr = drop_threshold(drop_p); a.drop_scale = drop_scale_of(a.drop_thr); a.drop_seed = drop_seed;
-    const unsigned grid = (unsigned)((n_rows + 7) / 8);
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (width / 4 <= 32) gat_aggregate_kernel<1><<<grid, 256, 0, st>>>(a);
-    else gat_aggregate_kernel<2><<<grid, 256, 0, st>>>(a);
-    GR_LAUNCH_CHECK();
-    return GR_OK;
-}

@@ -281,286 +281,14 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const float *parti
     out[e] = (float)s;
 }
 
-// =============================================================================================
-// GAT backward
-// =============================================================================================
-struct GatPrepArgs {
-    const float *dout, *out, *s, *m, *z;
-    long long lddo, ldo;
-    float *dO;      // [n, heads*dh] gradient w.r.t. the per-head aggregates
-    float4 *stat;   // [n, heads] (s, m, 1/z, D); D is filled by the row-role kernel
-    int n_rows, heads, dh, mean_heads, elu;
-};
-
-// One warp per row: undo ELU / head-mean on the incoming gradient; pack the softmax statistics.
-template <int SLOTS>
-__global__ void __launch_bounds__(256) gat_bwd_prep_kernel(const GatPrepArgs a) {
-    const int lane = threadIdx.x & 31;
-    const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (i >= a.n_rows) return;
-    const int width4 = a.heads * a.dh / 4, dh4 = a.dh / 4;
-    const float inv_heads = 1.f / (float)a.heads;
-#pragma unroll
-    for (int q = 0; q < SLOTS; ++q) {
-        const int slot = lane + 32 * q;
-        if (slot >= width4) continue;
-        const int head = slot / dh4;
-        const int oslot = a.mean_heads ? slot % dh4 : slot;
-        float4 d = __ldg(reinterpret_cast<const float4 *>(a.dout + (long long)i * a.lddo) + oslot);
-        if (a.elu) {
-            const float4 o = __ldg(reinterpret_cast<const float4 *>(a.out + (long long)i * a.ldo) + oslot);
-            d.x *= act_grad_from_output(o.x, 2, 0.f); d.y *= act_grad_from_output(o.y, 2, 0.f);
-            d.z *= act_grad_from_output(o.z, 2, 0.f); d.w *= act_grad_from_output(o.w, 2, 0.f);
-        }
-        if (a.mean_heads) { d.x *= inv_heads; d.y *= inv_heads; d.z *= inv_heads; d.w *= inv_heads; }
-        *reinterpret_cast<float4 *>(a.dO + (long long)i * a.heads * a.dh + slot * 4) = d;
-        if ((slot % dh4) == 0) {
-            const long long ih = (long long)i * a.heads + head;
-            a.stat[ih] = make_float4(__ldg(a.s + ih), __ldg(a.m + ih), 1.f / __ldg(a.z + ih), 0.f);
-        }
-    }
-}
-
-struct GatBwdArgs {
-    const int *indptr, *indices;        // row pattern:    j attends to k in row j
-    const int *t_indptr, *t_indices;    // column pattern: rows i that attend to j (== row pattern when symmetric)
-    const float *h, *dO, *t, *a_self, *a_neigh;
-    float4 *stat;         // [n, heads] (s, m, 1/z, D)
-    float *ds;            // [n, heads]
-    long long ldh;
-    float *dH;            // [n, heads*dh]
-    float *partial;       // [n_ctas][2 * heads*dh]: per-CTA sums of ds*H and dt*H (-> da_self, da_neigh)
-    long long n_cols;
-    int n_rows, heads, dh;
-    float slope;
-    unsigned drop_thr;
-    float drop_scale;
-    unsigned long long drop_seed;
-};
-
-__device__ __forceinline__ float seg_sum(float v, int dh4) {
-    for (int o = dh4 >> 1; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-// <dO_i,h , H_k,h> restricted to this lane's float4; fixed operation order so the row-role and the
-// column-role kernels produce the SAME bits for the same edge (their difference x - D must cancel).
-__device__ __forceinline__ float dot4_fixed(const float4 &dO, const float4 &hv) {
-    return __fmaf_rn(dO.w, hv.w, __fmaf_rn(dO.z, hv.z, __fmaf_rn(dO.y, hv.y, __fmul_rn(dO.x, hv.x))));
-}
-// alpha_ik = exp(LeakyReLU(s_i + t_k) - m_i) / z_i, same expression in both kernels
-__device__ __forceinline__ float gat_alpha(float pre, float slope, float m, float zinv) {
-    const float e = pre > 0.f ? pre : pre * slope;
-    return __fmul_rn(expf(e - m), zinv);
-}
-
-// Row role: for row j, one pass over its neighbours k (gathering H_k): the softmax-consistent
-//   D_j = sum_k alpha_jk c_jk x_jk / sum_k alpha_jk      (x_jk = <dO_j, H_k>)
-//   ds_j = sum_k alpha_jk l'_jk (c_jk x_jk - D_j)  =  S1 - D_j S2
-// D is formed from the SAME alpha / x the terms use (not from the forward output), so that rows whose
-// neighbours carry nearly equal features (x_jk ~ D_j: deep layers) keep their small differences.
-template <int SLOTS>
-__global__ void __launch_bounds__(256) gat_bwd_row_kernel(const GatBwdArgs a) {
-    const int lane = threadIdx.x & 31;
-    const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (j >= a.n_rows) return;
-    const int width4 = a.heads * a.dh / 4, dh4 = a.dh / 4;
-    const int hgroups = (a.heads + 3) >> 2;
-    int head[SLOTS];
-    bool on[SLOTS];
-    float4 doj[SLOTS];
-    float sj[SLOTS], mj[SLOTS], zinv[SLOTS], S0[SLOTS], S1[SLOTS], S2[SLOTS], S3[SLOTS];
-#pragma unroll
-    for (int q = 0; q < SLOTS; ++q) {
-        const int slot = lane + 32 * q;
-        on[q] = slot < width4;
-        head[q] = on[q] ? slot / dh4 : 0;
-        doj[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-        sj[q] = mj[q] = 0.f; zinv[q] = 1.f;
-        S0[q] = S1[q] = S2[q] = S3[q] = 0.f;
-        if (on[q]) {
-            doj[q] = __ldg(reinterpret_cast<const float4 *>(a.dO + (long long)j * a.heads * a.dh) + slot);
-            const float4 st = a.stat[(long long)j * a.heads + head[q]];
-            sj[q] = st.x; mj[q] = st.y; zinv[q] = st.z;
-        }
-    }
-    const int start = a.indptr[j], end = a.indptr[j + 1];
-    for (int base = start; base < end; base += 32) {
-        const int mycol = (base + lane < end) ? __ldg(a.indices + base + lane) : 0;
-        const int cnt = min(32, end - base);
-        for (int kk = 0; kk < cnt; kk += 4) {
-            float4 hv[4][SLOTS];
-            float tv[4][SLOTS];
-            int kid[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                kid[u] = __shfl_sync(0xffffffffu, mycol, (kk + u) & 31);
-                if (kk + u < cnt) {
-#pragma unroll
-                    for (int q = 0; q < SLOTS; ++q)
-                        if (on[q]) {
-                            hv[u][q] = __ldg(reinterpret_cast<const float4 *>(a.h + (long long)kid[u] * a.ldh) + lane + 32 * q);
-                            tv[u][q] = __ldg(a.t + (long long)kid[u] * a.heads + head[q]);
-                        }
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (kk + u < cnt) {
-#pragma unroll
-                    for (int q = 0; q < SLOTS; ++q) {
-                        float dot = on[q] ? dot4_fixed(doj[q], hv[u][q]) : 0.f;
-                        dot = seg_sum(dot, dh4);
-                        if (on[q]) {
-                            const float pre = sj[q] + tv[u][q];
-                            const float alpha = gat_alpha(pre, a.slope, mj[q], zinv[q]);
-                            float c = 1.f;
-                            if (a.drop_thr) {
-                                const unsigned long long bits = drop_bits(
-                                    a.drop_seed, ((unsigned long long)j * a.n_cols + kid[u]) * hgroups + (head[q] >> 2));
-                                c = drop_keep(bits, head[q] & 3, a.drop_thr) ? a.drop_scale : 0.f;
-                            }
-                            const float lp = pre > 0.f ? 1.f : a.slope;
-                            const float ax = alpha * (c * dot);
-                            S0[q] += alpha;
-                            S1[q] += ax * lp;
-                            S2[q] += alpha * lp;
-                            S3[q] += ax;
-                        }
-                    }
-                }
-            }
-        }
-    }
-#pragma unroll
-    for (int q = 0; q < SLOTS; ++q) {
-        const int slot = lane + 32 * q;
-        if (on[q] && (slot % dh4) == 0) {
-            const long long jh = (long long)j * a.heads + head[q];
-            const float D = S3[q] / S0[q];
-            a.stat[jh].w = D;
-            a.ds[jh] = S1[q] - D * S2[q];
-        }
-    }
-}
-
-// Column role: for node j, one pass over the rows i that attend to it (gathering dO_i and row i's
-// statistics): dt_j = sum_i alpha_ij l'_ij (c_ij x_ij - D_i),  dH_j = sum_i alpha_ij c_ij dO_i, then the
-// s = <H, a_self>, t = <H, a_neigh> paths: dH_j += ds_j a_self + dt_j a_neigh; per-CTA partials of
-// da_self = sum_j ds_j H_j and da_neigh = sum_j dt_j H_j.
-template <int SLOTS>
-__global__ void __launch_bounds__(256) gat_bwd_col_kernel(const GatBwdArgs a) {
-    __shared__ float4 red[8][2][32 * SLOTS];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int width4 = a.heads * a.dh / 4, dh4 = a.dh / 4;
-    const int hgroups = (a.heads + 3) >> 2;
-    int head[SLOTS];
-    bool on[SLOTS];
-    float4 as[SLOTS], an[SLOTS], gs[SLOTS], gn[SLOTS];
-#pragma unroll
-    for (int q = 0; q < SLOTS; ++q) {
-        const int slot = lane + 32 * q;
-        on[q] = slot < width4;
-        head[q] = on[q] ? slot / dh4 : 0;
-        as[q] = an[q] = gs[q] = gn[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (on[q]) {
-            as[q] = __ldg(reinterpret_cast<const float4 *>(a.a_self) + slot);
-            an[q] = __ldg(reinterpret_cast<const float4 *>(a.a_neigh) + slot);
-        }
-    }
-    const int total_warps = gridDim.x * 8;
-    for (int j = blockIdx.x * 8 + warp; j < a.n_rows; j += total_warps) {
-        float4 hj[SLOTS], dh_acc[SLOTS];
-        float tj[SLOTS], ds_j[SLOTS], dt_acc[SLOTS];
-#pragma unroll
-        for (int q = 0; q < SLOTS; ++q) {
-            const int slot = lane + 32 * q;
-            hj[q] = dh_acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-            tj[q] = ds_j[q] = dt_acc[q] = 0.f;
-            if (on[q]) {
-                hj[q] = __ldg(reinterpret_cast<const float4 *>(a.h + (long long)j * a.ldh) + slot);
-                tj[q] = __ldg(a.t + (long long)j * a.heads + head[q]);
-                ds_j[q] = __ldg(a.ds + (long long)j * a.heads + head[q]);
-            }
-        }
-        const int start = a.t_indptr[j], end = a.t_indptr[j + 1];
-        for (int base = start; base < end; base += 32) {
-            const int myrow = (base + lane < end) ? __ldg(a.t_indices + base + lane) : 0;
-            const int cnt = min(32, end - base);
-            for (int kk = 0; kk < cnt; kk += 4) {
-                float4 dv[4][SLOTS];
-                float4 sv[4][SLOTS];
-                int iid[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    iid[u] = __shfl_sync(0xffffffffu, myrow, (kk + u) & 31);
-                    if (kk + u < cnt) {
-#pragma unroll
-                        for (int q = 0; q < SLOTS; ++q)
-                            if (on[q]) {
-                                dv[u][q] = __ldg(reinterpret_cast<const float4 *>(a.dO + (long long)iid[u] * a.heads * a.dh) + lane + 32 * q);
-                                sv[u][q] = __ldg(a.stat + (long long)iid[u] * a.heads + head[q]);
-                            }
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    if (kk + u < cnt) {
-#pragma unroll
-                        for (int q = 0; q < SLOTS; ++q) {
-                            float dot = on[q] ? dot4_fixed(dv[u][q], hj[q]) : 0.f;
-                            dot = seg_sum(dot, dh4);
-                            if (on[q]) {
-                                const float pre = sv[u][q].x + tj[q];
-                                const float alpha = gat_alpha(pre, a.slope, sv[u][q].y, sv[u][q].z);
-                                float c = 1.f;
-                                if (a.drop_thr) {
-                                    const unsigned long long bits = drop_bits(
-                                        a.drop_seed, ((unsigned long long)iid[u] * a.n_cols + j) * hgroups + (head[q] >> 2));
-                                    c = drop_keep(bits, head[q] & 3, a.drop_thr) ? a.drop_scale : 0.f;
-                                }
-                                dt_acc[q] += alpha * (c * dot - sv[u][q].w) * (pre > 0.f ? 1.f : a.slope);
-                                const float w = alpha * c;
-                                dh_acc[q].x += w * dv[u][q].x; dh_acc[q].y += w * dv[u][q].y;
-                                dh_acc[q].z += w * dv[u][q].z; dh_acc[q].w += w * dv[u][q].w;
-                            }
-                        }
-                    }
-                }
-            }
-        }
-#pragma unroll
-        for (int q = 0; q < SLOTS; ++q)
-            if (on[q]) {
-                float4 o = dh_acc[q];
-                o.x += ds_j[q] * as[q].x + dt_acc[q] * an[q].x; o.y += ds_j[q] * as[q].y + dt_acc[q] * an[q].y;
-                o.z += ds_j[q] * as[q].z + dt_acc[q] * an[q].z; o.w += ds_j[q] * as[q].w + dt_acc[q] * an[q].w;
-                *reinterpret_cast<float4 *>(a.dH + (long long)j * a.heads * a.dh + (lane + 32 * q) * 4) = o;
-                gs[q].x += ds_j[q] * hj[q].x; gs[q].y += ds_j[q] * hj[q].y; gs[q].z += ds_j[q] * hj[q].z; gs[q].w += ds_j[q] * hj[q].w;
-                gn[q].x += dt_acc[q] * hj[q].x; gn[q].y += dt_acc[q] * hj[q].y; gn[q].z += dt_acc[q] * hj[q].z; gn[q].w += dt_acc[q] * hj[q].w;
-            }
-    }
-    // per-CTA partial of the attention-vector gradients (warps added in index order)
-#pragma unroll
-    for (int q = 0; q < SLOTS; ++q) {
-        red[warp][0][lane + 32 * q] = gs[q];
-        red[warp][1][lane + 32 * q] = gn[q];
-    }
-    __syncthreads();
-    for (int e = threadIdx.x; e < 2 * 32 * SLOTS; e += 256) {
-        const int which = e / (32 * SLOTS), slot = e % (32 * SLOTS);
-        if (slot >= width4) continue;
-        float4 s = red[0][which][slot];
-        for (int w = 1; w < 8; ++w) {
-            const float4 v = red[w][which][slot];
-            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-        }
-        *reinterpret_cast<float4 *>(a.partial + ((long long)blockIdx.x * 2 + which) * width4 * 4 + slot * 4) = s;
-    }
-}
-
-static int persistent_grid(int work_items, int per_sm) {
+int persistent_grid(int work_items, int per_sm) {
     const int cap = sm_count() * per_sm;
     return work_items < cap ? (work_items > 0 ? work_items : 1) : cap;
+}
+
+int launch_reduce_partials(const float *partial, int n_part, long long total, float *out, cudaStream_t st) {
+    reduce_partials_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(partial, n_part, total, out);
+    return cudaPeekAtLastError() == cudaSuccess ? 0 : 1;
 }
 
 }  // namespace gr
@@ -659,79 +387,3 @@ extern "C" int gr_rowmap_bwd(const float *g, int64_t ldg, const float *out, int6
     return GR_OK;
 }
 
-static int gat_bwd_ctas(int64_t n_rows) { return persistent_grid((int)((n_rows + 7) / 8), 8); }
-
-extern "C" size_t gr_gat_bwd_workspace_bytes(int64_t n_rows, int32_t heads, int32_t dh) {
-    if (n_rows <= 0 || heads <= 0 || dh <= 0) return 256;
-    const size_t width = (size_t)heads * dh;
-    const size_t dO = ((size_t)n_rows * width * 4 + 255) & ~(size_t)255;
-    const size_t stat = ((size_t)n_rows * heads * 16 + 255) & ~(size_t)255;
-    const size_t ds = ((size_t)n_rows * heads * 4 + 255) & ~(size_t)255;
-    return dO + stat + ds + (size_t)gat_bwd_ctas(n_rows) * 2 * width * 4 + 256;
-}
-
-extern "C" int gr_gat_bwd(const int32_t *indptr, const int32_t *indices, const int32_t *t_indptr,
-                          const int32_t *t_indices, int64_t n_rows, int64_t n_cols, const float *h, int64_t ldh,
-                          const float *s, const float *t, const float *m, const float *z, const float *out,
-                          int64_t ldo, const float *dout, int64_t lddo,
-                          const float *a_self, const float *a_neigh, int32_t heads, int32_t dh, float slope,
-                          int32_t mean_heads, int32_t elu, float drop_p, uint64_t drop_seed, float *dH,
-                          float *da, void *workspace, size_t workspace_bytes, void *stream) {
-    if (!indptr || !indices || !t_indptr || !t_indices || !h || !s || !t || !m || !z || !dout || !a_self ||
-        !a_neigh || !dH || !da || n_rows < 0 || n_cols < 0 || heads <= 0 || dh <= 0)
-        return GR_ERR_INVALID;
-    if (elu && !out) return GR_ERR_INVALID;
-    if (!(drop_p >= 0.f) || drop_p >= 1.f) return GR_ERR_INVALID;
-    if (n_rows != n_cols) return GR_ERR_UNSUPPORTED;     // the column role indexes the same node set
-    const int width = heads * dh;
-    const int dh4 = dh / 4;
-    if ((dh & 3) || width > 256 || (dh4 & (dh4 - 1)) || dh4 > 32) return GR_ERR_UNSUPPORTED;
-    const int wout = mean_heads ? dh : width;
-    if ((ldh & 3) || ldh < width || (lddo & 3) || lddo < wout) return GR_ERR_INVALID;
-    if (elu && ((ldo & 3) || ldo < wout)) return GR_ERR_INVALID;
-    if (!aligned16(h) || !aligned16(out) || !aligned16(dout) || !aligned16(a_self) ||
-        !aligned16(a_neigh) || !aligned16(dH) || !aligned16(da) || !aligned16(workspace))
-        return GR_ERR_INVALID;
-    if (n_rows > 0x7fffffffLL) return GR_ERR_OVERFLOW;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (n_rows == 0) {
-        GR_CUDA_CHECK(cudaMemsetAsync(da, 0, (size_t)2 * width * 4, st));
-        return GR_OK;
-    }
-    if (workspace_bytes < gr_gat_bwd_workspace_bytes(n_rows, heads, dh)) return GR_ERR_WORKSPACE;
-    char *ws = static_cast<char *>(workspace);
-    float *dO = reinterpret_cast<float *>(ws);
-    ws += ((size_t)n_rows * width * 4 + 255) & ~(size_t)255;
-    float4 *stat = reinterpret_cast<float4 *>(ws);
-    ws += ((size_t)n_rows * heads * 16 + 255) & ~(size_t)255;
-    float *ds = reinterpret_cast<float *>(ws);
-    ws += ((size_t)n_rows * heads * 4 + 255) & ~(size_t)255;
-    float *partial = reinterpret_cast<float *>(ws);
-
-    GatPrepArgs p;
-    p.dout = dout; p.out = out; p.s = s; p.m = m; p.z = z;
-    p.lddo = lddo; p.ldo = ldo; p.dO = dO; p.stat = stat;
-    p.n_rows = (int)n_rows; p.heads = heads; p.dh = dh; p.mean_heads = mean_heads; p.elu = elu;
-    const unsigned rows_grid = (unsigned)((n_rows + 7) / 8);
-    if (width / 4 <= 32) gat_bwd_prep_kernel<1><<<rows_grid, 256, 0, st>>>(p);
-    else gat_bwd_prep_kernel<2><<<rows_grid, 256, 0, st>>>(p);
-    GR_LAUNCH_CHECK();
-
-    GatBwdArgs a;
-    a.indptr = indptr; a.indices = indices; a.t_indptr = t_indptr; a.t_indices = t_indices;
-    a.h = h; a.dO = dO; a.t = t; a.a_self = a_self; a.a_neigh = a_neigh; a.stat = stat; a.ds = ds; a.ldh = ldh;
-    a.dH = dH; a.partial = partial; a.n_cols = n_cols; a.n_rows = (int)n_rows; a.heads = heads; a.dh = dh;
-    a.slope = slope;
-    a.drop_thr = drop_threshold(drop_p); a.drop_scale = drop_scale_of(a.drop_thr); a.drop_seed = drop_seed;
-    if (width / 4 <= 32) gat_bwd_row_kernel<1><<<rows_grid, 256, 0, st>>>(a);
-    else gat_bwd_row_kernel<2><<<rows_grid, 256, 0, st>>>(a);
-    GR_LAUNCH_CHECK();
-    const int ctas = gat_bwd_ctas(n_rows);
-    if (width / 4 <= 32) gat_bwd_col_kernel<1><<<ctas, 256, 0, st>>>(a);
-    else gat_bwd_col_kernel<2><<<ctas, 256, 0, st>>>(a);
-    GR_LAUNCH_CHECK();
-    const long long total = 2LL * width;
-    reduce_partials_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(partial, ctas, total, da);
-    GR_LAUNCH_CHECK();
-    return GR_OK;
-}

@@ -88,6 +88,8 @@ __global__ void __launch_bounds__(1024) opt_finalize_kernel(const double *partia
 
 struct AdamScalars {   // each rounded once from the caller's doubles, as torch rounds its python scalars
     float step_size, one_minus_beta1, beta2, one_minus_beta2, eps, weight_decay, bc2_sqrt;
+    const float *step_dev;   // optional device [2] = (step_size, bc2_sqrt): the step-dependent scalars read at
+                             // run time, so that a CUDA graph captured once stays valid for every later step
 };
 
 __device__ __forceinline__ void adam_one(float &p, float g, float &m, float &v, float coef, const AdamScalars &s) {
@@ -99,7 +101,11 @@ __device__ __forceinline__ void adam_one(float &p, float g, float &m, float &v, 
     p = __fmaf_rn(-s.step_size, m / denom, p);
 }
 
-__global__ void __launch_bounds__(OPT_THREADS) opt_adam_kernel(const OptTable t, const float *clip, const AdamScalars s) {
+__global__ void __launch_bounds__(OPT_THREADS) opt_adam_kernel(const OptTable t, const float *clip, AdamScalars s) {
+    if (s.step_dev) {
+        s.step_size = __ldg(s.step_dev);
+        s.bc2_sqrt = __ldg(s.step_dev + 1);
+    }
     const int ti = opt_find_tensor(t, blockIdx.x);
     float *p = t.p[ti], *m = t.m[ti], *v = t.v[ti];
     const float *g = t.g[ti];
@@ -145,8 +151,8 @@ extern "C" size_t gr_clip_adam_workspace_bytes(const int64_t *numel_host, int32_
 extern "C" int gr_clip_adam_fused(void *const *params_host, const void *const *grads_host, void *const *exp_avg_host,
                                   void *const *exp_avg_sq_host, const int64_t *numel_host, int32_t n_tensors,
                                   double max_norm, double step_size, double beta1, double beta2, double eps,
-                                  double weight_decay, double bias_correction2_sqrt, float *norm_out, void *workspace,
-                                  size_t workspace_bytes, void *stream) {
+                                  double weight_decay, double bias_correction2_sqrt, const float *step_scalars_dev,
+                                  float *norm_out, void *workspace, size_t workspace_bytes, void *stream) {
     if (!params_host || !grads_host || !exp_avg_host || !exp_avg_sq_host || !numel_host || n_tensors <= 0 || !workspace)
         return GR_ERR_INVALID;
     if (workspace_bytes < gr_clip_adam_workspace_bytes(numel_host, n_tensors)) return GR_ERR_WORKSPACE;
@@ -163,14 +169,16 @@ extern "C" int gr_clip_adam_fused(void *const *params_host, const void *const *g
     double *partial = reinterpret_cast<double *>(static_cast<char *>(workspace) + 256);
     const bool do_clip = max_norm > 0.0;
 
-    // both passes walk the list in chunks of OPT_MAX_TENSORS
+    // both passes walk the list in chunks of at most OPT_MAX_TENSORS non-empty tensors; `i` is the next input
+    // index, so a chunk that skipped empty tensors does not overlap the following one
     for (int pass = do_clip ? 0 : 1; pass < 2; ++pass) {
         long long part_base = 0;
-        for (int c0 = 0; c0 < n_tensors; c0 += OPT_MAX_TENSORS) {
+        int i = 0;
+        while (i < n_tensors) {
             OptTable t;
             t.n = 0;
             long long blocks = 0;
-            for (int i = c0; i < n_tensors && t.n < OPT_MAX_TENSORS; ++i) {
+            for (; i < n_tensors && t.n < OPT_MAX_TENSORS; ++i) {
                 if (numel_host[i] == 0) continue;
                 t.p[t.n] = static_cast<float *>(params_host[i]);
                 t.g[t.n] = static_cast<const float *>(grads_host[i]);
@@ -188,7 +196,7 @@ extern "C" int gr_clip_adam_fused(void *const *params_host, const void *const *g
                 opt_sumsq_kernel<<<(unsigned)blocks, OPT_THREADS, 0, s>>>(t, partial, part_base);
             } else {
                 AdamScalars sc{(float)step_size, (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), (float)eps,
-                               (float)weight_decay, (float)bias_correction2_sqrt};
+                               (float)weight_decay, (float)bias_correction2_sqrt, step_scalars_dev};
                 opt_adam_kernel<<<(unsigned)blocks, OPT_THREADS, 0, s>>>(t, do_clip ? clip : nullptr, sc);
             }
             GR_LAUNCH_CHECK();

@@ -19,7 +19,9 @@
 // ranks (NVLink P2P stores or one NVSwitch multicast store): the all-gather of the row-partitioned
 // propagation is fused into the SpMM.
 #include <cstdlib>
+#include <map>
 #include <mutex>
+#include <utility>
 
 #include "gr_common.cuh"
 
@@ -61,6 +63,10 @@ struct SpmmArgs {
     int n_peers;
     int peer_multicast;     // peer_y[0] is a multicast address
     long long peer_row_off;
+    // long-row scheduler state in CALLER memory: [0] ticket counter, [1] finished-CTA counter.  Zero on
+    // entry; the last CTA of a launch zeroes both again.  (No library-global device state: two
+    // propagations in flight on different streams use different words.)
+    unsigned int *sched;
 };
 
 // kernel template parameter PEERS: how the finished row also leaves the GPU
@@ -391,7 +397,6 @@ struct LongCfg {
 
 // ticket / exit counters of the persistent long-row kernel, re-armed by the last CTA of each launch
 // (one gr_spmm_csr_f32 in flight per device at a time)
-__device__ unsigned int g_long_ticket = 0, g_long_done = 0;
 
 __device__ __forceinline__ unsigned lr_smem(const void *p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void lr_mbar_init(uint64_t *bar, unsigned count) {
@@ -451,7 +456,7 @@ __global__ void __launch_bounds__(LongCfg<D>::THREADS, 1) spmm_long_rows(const S
     // persistent CTAs: rows are handed out in row_order (longest first) through a ticket counter,
     // so the hottest row starts first and no CTA queues work behind it.
     for (;;) {
-    if (threadIdx.x == 0) s_ticket = (int)atomicAdd(&g_long_ticket, 1u);
+    if (threadIdx.x == 0) s_ticket = (int)atomicAdd(a.sched, 1u);
     __syncthreads();
     const int ticket = s_ticket;
     __syncthreads();   // everyone has read the ticket before thread 0 may overwrite it
@@ -583,9 +588,9 @@ __global__ void __launch_bounds__(LongCfg<D>::THREADS, 1) spmm_long_rows(const S
     // starts from ticket 0 without host involvement
     if (threadIdx.x == 0) {
         __threadfence();
-        if (atomicAdd(&g_long_done, 1u) == gridDim.x - 1) {
-            g_long_ticket = 0;
-            g_long_done = 0;
+        if (atomicAdd(a.sched + 1, 1u) == gridDim.x - 1) {
+            a.sched[0] = 0;
+            a.sched[1] = 0;
             __threadfence();
         }
     }
@@ -637,7 +642,7 @@ __global__ void __launch_bounds__(LongCfgBar<D>::THREADS, 1) spmm_long_rows_bar(
     // so the hottest row starts first and no CTA queues work behind it.
     int &s_ticket = *reinterpret_cast<int *>(smem_raw + L::SMEM);  // one int after the rings
     for (;;) {
-    if (threadIdx.x == 0) s_ticket = (int)atomicAdd(&g_long_ticket, 1u);
+    if (threadIdx.x == 0) s_ticket = (int)atomicAdd(a.sched, 1u);
     __syncthreads();
     const int ticket = s_ticket;
     int r, start, len, part = -1;
@@ -756,9 +761,9 @@ __global__ void __launch_bounds__(LongCfgBar<D>::THREADS, 1) spmm_long_rows_bar(
     // starts from ticket 0 without host involvement
     if (threadIdx.x == 0) {
         __threadfence();
-        if (atomicAdd(&g_long_done, 1u) == gridDim.x - 1) {
-            g_long_ticket = 0;
-            g_long_done = 0;
+        if (atomicAdd(a.sched + 1, 1u) == gridDim.x - 1) {
+            a.sched[0] = 0;
+            a.sched[1] = 0;
             __threadfence();
         }
     }
@@ -797,15 +802,18 @@ struct SideStream {
     bool smem_attr_set[4] = {false, false, false, false};
 };
 
+// One high-priority side stream (+ fork/join events) per (device, caller stream): the long-row kernel of a
+// propagation runs beside its streaming kernel, and propagations issued on different caller streams do not
+// share a side stream or its events.  Host-side resource cache only (created on first use, never
+// reassigned); all device-side scheduler state lives in caller memory (SpmmArgs::sched).
 static std::mutex g_side_mu;
-static SideStream g_side[64];
+static std::map<std::pair<int, cudaStream_t>, SideStream> g_side;
 
-static int get_side(SideStream **out) {
+static int get_side(cudaStream_t caller, SideStream **out) {
     int dev = 0;
     GR_CUDA_CHECK(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= 64) return GR_ERR_INVALID;
     std::lock_guard<std::mutex> lk(g_side_mu);
-    SideStream &s = g_side[dev];
+    SideStream &s = g_side[std::make_pair(dev, caller)];
     if (!s.stream) {
         int lo = 0, hi = 0;
         GR_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
@@ -823,7 +831,7 @@ static int launch(const SpmmArgs &base, int n_long, long long n_rows, int slot, 
     SideStream *side = nullptr;
     const bool use_long = base.row_order != nullptr && n_long > 0;
     if (use_long) {
-        int rc = get_side(&side);
+        int rc = get_side(stream, &side);
         if (rc != GR_OK) return rc;
         // d <= 64: barrier pipeline; d >= 128: mbarrier pipeline (see the comments at the kernels)
         constexpr bool kBar = D <= 64;
@@ -951,9 +959,11 @@ extern "C" int gr_spmm_csr_f32(const int32_t *indptr, const int32_t *indices, co
                                int32_t n_groups, int32_t long_threshold, int64_t n_rows, int32_t d, const float *x,
                                int64_t ldx, float *y, int64_t ldy, const float *addend, int64_t lda, float *out,
                                int64_t ldo, float scale, int32_t scale_mode, float *const *peer_y_host,
-                               int32_t n_peers, int32_t peer_multicast, int64_t peer_row_offset, void *stream) {
+                               int32_t n_peers, int32_t peer_multicast, int64_t peer_row_offset, uint32_t *sched_ws,
+                               void *stream) {
     using namespace gr;
     if (n_rows == 0) return GR_OK;
+    if (row_order && n_long > 0 && !sched_ws) return GR_ERR_INVALID;      // long-row scheduler needs its 2 words
     if (n_peers < 0 || n_peers > kMaxPeers || (n_peers > 0 && !peer_y_host)) return GR_ERR_INVALID;
     if (!indptr || !indices || !vals || !x || n_rows < 0 || n_long < 0 || n_long > n_rows) return GR_ERR_INVALID;
     if (!y && !out && n_peers == 0) return GR_ERR_INVALID;
@@ -994,6 +1004,7 @@ extern "C" int gr_spmm_csr_f32(const int32_t *indptr, const int32_t *indices, co
     a.peer_multicast = (n_peers > 0 && peer_multicast) ? 1 : 0;
     if (a.peer_multicast && n_peers != 1) return GR_ERR_INVALID;
     a.peer_row_off = peer_row_offset;
+    a.sched = sched_ws;
     for (int p = 0; p < kMaxPeers; ++p) {
         a.peer_y[p] = p < n_peers ? reinterpret_cast<float4 *>(peer_y_host[p]) : nullptr;
         if (p < n_peers && (!peer_y_host[p] || !aligned16(peer_y_host[p]))) return GR_ERR_INVALID;

@@ -27,6 +27,7 @@ GROUP_NNZ = int(os.environ.get("GR_GROUP_NNZ", "0"))      # 0 = choose by graph 
 # row (max degree <= 91 599 at the Amazon-Book shape), so C1-C4 stay on the exact single chain.
 SPLIT_ROW_THRESHOLD = int(os.environ.get("GR_SPLIT_ROW_THRESHOLD", "131072"))
 SPLIT_ROW_SEGMENT = int(os.environ.get("GR_SPLIT_ROW_SEGMENT", "65536"))
+GAT_SEG_LEN = int(os.environ.get("GR_GAT_SEG_LEN", "128"))   # GAT work-item length (rows longer than this are cut)
 _NORM_MODES = {"symmetric": 0, "row": 1, "none": 2}
 
 
@@ -57,6 +58,7 @@ class NormAdjCSR:
         self.group_ptr, self.n_groups, self.group_nnz = None, 0, 0
         self.long_items, self.n_long_items, self.split_rows, self.n_split, self.n_parts = None, 0, None, 0, 0
         self._part_buf = {}
+        self._sched = {}
         self.timings = None      # set to a list to collect (start, end) CUDA events per SpMM launch
         self.launches = 0        # kernels launched by spmm() so far
         if long_threshold is not None:
@@ -148,6 +150,18 @@ class NormAdjCSR:
         self.n_long_items = int(items.shape[1])
         self.split_rows = torch.from_numpy(np.ascontiguousarray(np.asarray(sp, dtype=np.int32).T)).to(self.device)
         self.n_split, self.n_parts = len(sp), n_parts
+
+    def _sched_words(self):
+        """Two zeroed uint32 words per (adjacency, stream) for the long-row kernel's ticket counters
+        (gr_spmm_csr_f32: no library-global device state; concurrent streams get different words)."""
+        if self.n_long == 0 or self.row_order is None:
+            return None
+        key = torch.cuda.current_stream(self.device).cuda_stream
+        w = self._sched.get(key)
+        if w is None:
+            w = torch.zeros(4, dtype=torch.int32, device=self.device)
+            self._sched[key] = w
+        return w
 
     def _parts(self, d: int):
         if self.n_parts == 0:
@@ -276,6 +290,40 @@ class NormAdjCSR:
             out.append(h)
         return tuple(out)
 
+    # ---- GAT work items ------------------------------------------------------------------------
+    def gat_segments(self, seg_len: int = 0):
+        """Segment table of the rows with more than ``seg_len`` entries (include/gr_b200.h: gr_gat_segments),
+        built once per pattern with device index ops: (ctypes struct or None, n_seg, n_long).  The GAT kernels
+        give every segment its own warp, so a 17 560-entry hot row is ~140 parallel work items instead of one."""
+        seg_len = int(seg_len) if seg_len else GAT_SEG_LEN
+        hit = self._gat_segs.get(seg_len) if hasattr(self, "_gat_segs") else None
+        if hit is not None:
+            return hit
+        if not hasattr(self, "_gat_segs"):
+            self._gat_segs = {}
+        ip = self.indptr.long()
+        deg = ip[1:] - ip[:-1]
+        long_rows = torch.nonzero(deg > seg_len, as_tuple=False).flatten()
+        n_long = int(long_rows.numel())
+        if n_long == 0:
+            out = (None, 0, 0)
+        else:
+            nseg = (deg[long_rows] + seg_len - 1) // seg_len
+            ptr_ = torch.zeros(n_long + 1, dtype=torch.int64, device=self.device)
+            torch.cumsum(nseg, 0, out=ptr_[1:])
+            n_seg = int(ptr_[-1].item())
+            pos = torch.repeat_interleave(torch.arange(n_long, device=self.device), nseg)
+            k = torch.arange(n_seg, device=self.device) - ptr_[pos]
+            seg_row = long_rows[pos]
+            seg_begin = ip[seg_row] + k * seg_len
+            seg_end = torch.minimum(seg_begin + seg_len, ip[seg_row + 1])
+            keep = [t.to(torch.int32).contiguous() for t in (seg_row, seg_begin, seg_end, long_rows, ptr_)]
+            st = _lib.GatSegments(seg_len, n_seg, n_long, *[t.data_ptr() for t in keep])
+            st._keep = keep                      # the device arrays live as long as the struct
+            out = (st, n_seg, n_long)
+        self._gat_segs[seg_len] = out
+        return out
+
     # ---- views --------------------------------------------------------------------------------
     def row_ids(self) -> torch.Tensor:
         counts = (self.indptr[1:] - self.indptr[:-1]).long()
@@ -347,7 +395,7 @@ class NormAdjCSR:
                 ptr(out), out.stride(0) if out is not None else 0,
                 float(scale), int(scale_mode),
                 peers[0] if peers else None, peers[1] if peers else 0, peers[4] if peers else 0,
-                peers[2] if peers else 0, stream_ptr()), "gr_spmm_csr_f32")
+                peers[2] if peers else 0, ptr(self._sched_words()), stream_ptr()), "gr_spmm_csr_f32")
             if ev is not None:
                 ev[1].record()
                 self.timings.append(ev)

@@ -8,6 +8,7 @@ index kernel is left on the training step (what autograd would run under trainer
 """
 from __future__ import annotations
 
+import ctypes as C
 from typing import Optional, Sequence
 
 import torch
@@ -200,13 +201,16 @@ def _gat_forward_kernels(csr, x, wcat, a_self, a_neigh, heads, dh, slope, mean_h
     if keep:
         m, z = torch.empty_like(s), torch.empty_like(s)
     l = lib()
+    segs, n_seg, _ = csr.gat_segments()
+    ws_bytes = l.gr_gat_aggregate_workspace_bytes(n_seg, heads, dh) if n_seg else 0
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if ws_bytes else None
     with torch.cuda.device(dev):
         check(l.gr_gat_node_scores(ptr(h), h.stride(0), ptr(a_self), ptr(a_neigh), n, heads, dh, ptr(s), ptr(t),
                                    stream_ptr()), "gr_gat_node_scores")
         check(l.gr_gat_aggregate(ptr(csr.indptr), ptr(csr.indices), n, ptr(h), h.stride(0), ptr(s), ptr(t), heads,
                                  dh, float(slope), int(mean_heads), int(elu), float(drop_p), int(drop_seed),
-                                 csr.n_cols, ptr(out), out.stride(0), ptr(m), ptr(z), ptr(raw),
-                                 raw.stride(0) if raw is not None else 0, stream_ptr()), "gr_gat_aggregate")
+                                 csr.n_cols, C.byref(segs) if segs is not None else None, ptr(out), out.stride(0),
+                                 ptr(m), ptr(z), ptr(ws), ws_bytes, stream_ptr()), "gr_gat_aggregate")
     return out, (h, s, t, m, z, raw)
 
 
@@ -233,12 +237,16 @@ class _GatLayer(torch.autograd.Function):
         l = lib()
         dH = torch.empty((n, width), dtype=torch.float32, device=dev)
         da = torch.empty(2 * width, dtype=torch.float32, device=dev)
-        ws_bytes = l.gr_gat_bwd_workspace_bytes(n, heads, dh)
+        rsegs, n_rseg, _ = csr.gat_segments()
+        csegs, n_cseg, n_clong = csr_t.gat_segments()
+        ws_bytes = l.gr_gat_bwd_workspace_bytes(n, heads, dh, n_rseg, n_cseg, n_clong)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
             check(l.gr_gat_bwd(ptr(csr.indptr), ptr(csr.indices), ptr(csr_t.indptr), ptr(csr_t.indices), n, csr.n_cols,
                                ptr(h), h.stride(0), ptr(s), ptr(t), ptr(m), ptr(z), ptr(out), out.stride(0), ptr(g), g.stride(0), ptr(a_self), ptr(a_neigh), heads, dh,
-                               float(slope), int(mean_heads), int(elu), float(drop_p), int(drop_seed), ptr(dH), ptr(da),
+                               float(slope), int(mean_heads), int(elu), float(drop_p), int(drop_seed),
+                               C.byref(rsegs) if rsegs is not None else None,
+                               C.byref(csegs) if csegs is not None else None, ptr(dH), ptr(da),
                                ptr(ws), ws_bytes, stream_ptr()), "gr_gat_bwd")
         need = ctx.needs_input_grad
         dx, _, _, _, dw = _rowmap_bwd_raw(dH, None, x, wcat, None, None, None, None, 1.0, 0.0, ACT_NONE, 0.0, 0.0, 0,

@@ -34,11 +34,33 @@ def fused_clip_adam_supported(optimizer) -> bool:
     return True
 
 
-def fused_clip_adam_step(optimizer, max_norm: float) -> torch.Tensor:
+def adam_step_scalars(optimizer, advance: bool = True):
+    """(step_size, bias_correction2_sqrt) of the NEXT optimizer step as torch computes them (python doubles),
+    advancing every parameter's ``step`` state when ``advance``."""
+    group = optimizer.param_groups[0]
+    beta1, beta2 = group["betas"]
+    params = [p for p in group["params"] if p.grad is not None or p in optimizer.state]
+    t = None
+    for p in params:                                     # torch/optim/adam.py:_init_group
+        st = optimizer.state[p]
+        if len(st) == 0:
+            st["step"] = torch.tensor(0.0, dtype=torch.float32)
+            st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+            st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+        if advance:
+            st["step"] += 1
+        t = float(st["step"]) if advance else float(st["step"]) + 1
+    return group["lr"] / (1 - beta1 ** t), (1 - beta2 ** t) ** 0.5
+
+
+def fused_clip_adam_step(optimizer, max_norm: float, step_scalars_dev: torch.Tensor = None) -> torch.Tensor:
     """clip_grad_norm_(params, max_norm) + optimizer.step() in two passes over the tensors.
 
     Returns the total gradient norm (0-dim device tensor), as clip_grad_norm_ does.  Gradients are left
-    unscaled (the reference scales them in place, nothing reads them afterwards)."""
+    unscaled (the reference scales them in place, nothing reads them afterwards).
+    ``step_scalars_dev`` (device float32[2]): the kernel reads (step_size, bias_correction2_sqrt) from it at run
+    time and the ``step`` counters are NOT advanced here — the CUDA-graph training step (Trainer) captures this
+    call once and refreshes the two scalars before every replay (``adam_step_scalars``)."""
     group = optimizer.param_groups[0]
     params = [p for p in group["params"] if p.grad is not None]
     if not params:
@@ -51,13 +73,17 @@ def fused_clip_adam_step(optimizer, max_norm: float) -> torch.Tensor:
             st["step"] = torch.tensor(0.0, dtype=torch.float32)
             st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
             st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
-        st["step"] += 1
-    steps = {float(optimizer.state[p]["step"]) for p in params}
-    if len(steps) != 1:
-        raise RuntimeError("fused_clip_adam_step needs all parameters at the same step")
-    t = steps.pop()
-    step_size = group["lr"] / (1 - beta1 ** t)           # python doubles, as torch computes them
-    bc2_sqrt = (1 - beta2 ** t) ** 0.5
+        if step_scalars_dev is None:
+            st["step"] += 1
+    if step_scalars_dev is None:
+        steps = {float(optimizer.state[p]["step"]) for p in params}
+        if len(steps) != 1:
+            raise RuntimeError("fused_clip_adam_step needs all parameters at the same step")
+        t = steps.pop()
+        step_size = group["lr"] / (1 - beta1 ** t)           # python doubles, as torch computes them
+        bc2_sqrt = (1 - beta2 ** t) ** 0.5
+    else:
+        step_size, bc2_sqrt = 0.0, 1.0                       # read from the device at run time
     n = len(params)
     arr = C.c_void_p * n
     p_arr = arr(*[ptr(p.data) for p in params])
@@ -74,5 +100,6 @@ def fused_clip_adam_step(optimizer, max_norm: float) -> torch.Tensor:
     norm = torch.zeros((), dtype=torch.float32, device=dev)
     check(l.gr_clip_adam_fused(p_arr, g_arr, m_arr, v_arr, numel, n, float(max_norm), float(step_size), float(beta1),
                                float(beta2), float(group["eps"]), float(group["weight_decay"]), float(bc2_sqrt),
-                               ptr(norm), ptr(ws), ws.numel(), stream_ptr()), "gr_clip_adam_fused")
+                               ptr(step_scalars_dev), ptr(norm), ptr(ws), ws.numel(), stream_ptr()),
+          "gr_clip_adam_fused")
     return norm

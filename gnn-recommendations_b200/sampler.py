@@ -36,20 +36,26 @@ class BprSampler:
     def __len__(self):
         return len(self.train_user)
 
-    def sample(self, batch_size: int, generator_state: torch.Tensor | None = None):
+    def sample(self, batch_size: int, generator_state: torch.Tensor | None = None, out=None):
         """Returns (users, pos, neg) int64 numpy arrays of length min(batch_size, n_train); neg is
         one negative per sample (the reference's [B,1] column).  Uses and advances torch's global
         CPU generator unless an explicit state tensor (as from torch.get_rng_state()) is given,
-        which is then advanced in place."""
+        which is then advanced in place.  ``out`` = three int64 numpy arrays of that length (e.g. views of
+        a pinned staging tensor) to write into instead of fresh arrays."""
         own_state = generator_state is None
         st = torch.get_rng_state() if own_state else generator_state
         if st.numel() != _STATE_BYTES or st.dtype != torch.uint8:
             raise GrError("unexpected torch CPU generator state layout")
         buf = st.numpy()
         b = min(int(batch_size), len(self.train_user))
-        users = np.empty(b, dtype=np.int64)
-        pos = np.empty(b, dtype=np.int64)
-        neg = np.empty(b, dtype=np.int64)
+        if out is not None:
+            users, pos, neg = out
+            if any(a.dtype != np.int64 or a.shape != (b,) or not a.flags.c_contiguous for a in out):
+                raise ValueError("out must be three contiguous int64 arrays of the batch length")
+        else:
+            users = np.empty(b, dtype=np.int64)
+            pos = np.empty(b, dtype=np.int64)
+            neg = np.empty(b, dtype=np.int64)
         base = buf.ctypes.data
         rc = lib().gr_sample_bpr_batch(
             C.c_void_p(base + _OFF_MT), C.c_void_p(base + _OFF_LEFT), C.c_void_p(base + _OFF_NEXT),

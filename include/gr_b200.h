@@ -125,7 +125,12 @@ int gr_row_groups(const int32_t *indptr, int64_t n_rows, int32_t group_nnz, int3
  * part_buf[slot][d] and the partials added in segment order by a combine pass driven by
  * `split_rows` = int32[3][n_split] (row, first slot, number of slots).  A split row is no longer the
  * single storage-order chain (deterministic, ~1e-7 relative); the host layer only splits rows
- * above 131 072 entries, which none of the reference's dataset shapes has. */
+ * above 131 072 entries, which none of the reference's dataset shapes has.
+ *
+ * Re-entrancy: the library keeps no device-side state.  `sched_ws` = two uint32 words of DEVICE memory, zero
+ * on entry and zero again when the launch has finished (ticket / finished-CTA counters of the persistent
+ * long-row kernel); required when n_long > 0.  Launches that may run concurrently (different streams) must
+ * be given different words; launches on one stream may share them. */
 int gr_spmm_csr_f32(const int32_t *indptr, const int32_t *indices, const float *vals,
                     const int32_t *row_order, int32_t n_long, const int32_t *long_items,
                     int32_t n_long_items, const int32_t *split_rows, int32_t n_split, float *part_buf,
@@ -133,7 +138,7 @@ int gr_spmm_csr_f32(const int32_t *indptr, const int32_t *indices, const float *
                     int32_t long_threshold, int64_t n_rows, int32_t d, const float *x,
                     int64_t ldx, float *y, int64_t ldy, const float *addend, int64_t lda, float *out,
                     int64_t ldo, float scale, int32_t scale_mode, float *const *peer_y_host, int32_t n_peers,
-                    int32_t peer_multicast, int64_t peer_row_offset, void *stream);
+                    int32_t peer_multicast, int64_t peer_row_offset, uint32_t *sched_ws, void *stream);
 
 /* Fused compute + all-gather for the row-partitioned multi-GPU propagation (no reference
  * counterpart).  `peer_y_host` (HOST array of n_peers <= 8 DEVICE pointers, one per rank of the
@@ -208,32 +213,49 @@ int gr_gs_compose_bwd(const float *skew, const float *blocks, const int64_t *per
  *       heads*dh) or averaged (mean_heads = 1, width dh) (gat.py:144-147); elu = 1 applies the ELU of
  *       GAT.forward (gat.py:283).  A row without neighbours yields NaN like the reference.
  *       m_out / z_out (optional, [n_rows, heads]): softmax max / normaliser for the backward pass.
- * H: [N, heads*dh], heads*dh <= 256, dh % 4 == 0. */
+ *       drop_p > 0: the reference's dropout on the softmaxed attention weights (gat.py:138) — every edge
+ *       weight is kept with probability 1-p and scaled by 1/(1-p) (the normaliser still sums all edges);
+ *       the mask is a counter-based hash of (drop_seed, row, column, head), re-derived by the backward pass.
+ * H: [N, heads*dh], heads*dh <= 256, dh % 4 == 0.
+ *
+ * Hot rows.  One warp owns one work item: a whole row of at most seg_len entries, or one seg_len-entry
+ * segment of a longer row; segment items leave partial results (online-softmax triples forward, partial sums
+ * backward) that a combine kernel merges per long row in segment order.  The table (HOST struct of DEVICE
+ * arrays, NULL = every row is one item) lists, for the rows with more than seg_len entries:
+ *   seg_row / seg_begin / seg_end [n_seg]: row id and entry range [begin, end) of every segment, grouped by row;
+ *   long_rows [n_long], long_seg_ptr [n_long + 1]: the long rows and their segment ranges. */
+typedef struct gr_gat_segments {
+    int32_t seg_len, n_seg, n_long;
+    const int32_t *seg_row, *seg_begin, *seg_end, *long_rows, *long_seg_ptr;
+} gr_gat_segments;
+
 int gr_gat_node_scores(const float *h, int64_t ldh, const float *a_self, const float *a_neigh, int64_t n_rows,
                        int32_t heads, int32_t dh, float *s, float *t, void *stream);
+size_t gr_gat_aggregate_workspace_bytes(int32_t n_seg, int32_t heads, int32_t dh);
 int gr_gat_aggregate(const int32_t *indptr, const int32_t *indices, int64_t n_rows, const float *h, int64_t ldh,
                      const float *s, const float *t, int32_t heads, int32_t dh, float slope, int32_t mean_heads,
-                     int32_t elu, float drop_p, uint64_t drop_seed, int64_t n_cols, float *out, int64_t ldo,
-                     float *m_out, float *z_out, float *raw_out, int64_t ldraw, void *stream);
-/*   drop_p > 0: the reference's dropout on the softmaxed attention weights (gat.py:138) — every edge weight is
- *       kept with probability 1-p and scaled by 1/(1-p) (the normaliser still sums all edges); the mask is a
- *       counter-based hash of (drop_seed, row, column, head), so the backward pass re-derives it.
- *   raw_out (optional, [n_rows, heads*dh]): per-head aggregates before head-mean / ELU, for the backward pass.
- *
- * gr_gat_bwd: backward of node scores + aggregation (autograd under trainer.py:270 through gat.py:97-149).
+                     int32_t elu, float drop_p, uint64_t drop_seed, int64_t n_cols,
+                     const gr_gat_segments *segs_host, float *out, int64_t ldo, float *m_out, float *z_out,
+                     void *workspace, size_t workspace_bytes, void *stream);
+
+/* gr_gat_bwd: backward of node scores + aggregation (autograd under trainer.py:270 through gat.py:97-149).
  *   Inputs: what the forward produced (h, s, t, m, z, out) and dout = dL/dout.  (t_indptr, t_indices) is the
- *   CSR of the TRANSPOSED pattern (the same arrays as (indptr, indices) for the symmetric bipartite adjacency).
+ *   CSR of the TRANSPOSED pattern (the same arrays as (indptr, indices) for the symmetric bipartite adjacency),
+ *   row_segs / col_segs the segment tables of the two patterns.
  *   Outputs: dH [n, heads*dh] (complete gradient w.r.t. H = x Wcat, incl. the a_self / a_neigh paths) and
- *   da [2, heads*dh] = (d a_self | d a_neigh).  One warp per row recomputes the softmax weights from (m, z);
+ *   da [2, heads*dh] = (d a_self | d a_neigh).  One warp per work item recomputes the softmax weights from (m, z);
  *   the softmax-backward centring term D_i = sum_k alpha_ik <dO_i, H_k> is re-formed from the same weights
- *   (not from the forward output) so that the differences x_ik - D_i of over-smoothed deep layers survive in
- *   fp32.  No atomics, no edge-sized temporaries, deterministic.  dh/4 must be a power of two. */
-size_t gr_gat_bwd_workspace_bytes(int64_t n_rows, int32_t heads, int32_t dh);
+ *   (not from the forward output) so that the differences x_ik - D_i survive in fp32.
+ *   No atomics, no edge-sized temporaries, deterministic.  dh/4 must be a power of two. */
+size_t gr_gat_bwd_workspace_bytes(int64_t n_rows, int32_t heads, int32_t dh, int32_t n_seg_row, int32_t n_seg_col,
+                                  int32_t n_long_col);
 int gr_gat_bwd(const int32_t *indptr, const int32_t *indices, const int32_t *t_indptr, const int32_t *t_indices,
                int64_t n_rows, int64_t n_cols, const float *h, int64_t ldh, const float *s, const float *t,
-               const float *m, const float *z, const float *out, int64_t ldo, const float *dout, int64_t lddo, const float *a_self, const float *a_neigh, int32_t heads,
-               int32_t dh, float slope, int32_t mean_heads, int32_t elu, float drop_p, uint64_t drop_seed,
-               float *dH, float *da, void *workspace, size_t workspace_bytes, void *stream);
+               const float *m, const float *z, const float *out, int64_t ldo, const float *dout, int64_t lddo,
+               const float *a_self, const float *a_neigh, int32_t heads, int32_t dh, float slope,
+               int32_t mean_heads, int32_t elu, float drop_p, uint64_t drop_seed,
+               const gr_gat_segments *row_segs_host, const gr_gat_segments *col_segs_host, float *dH, float *da,
+               void *workspace, size_t workspace_bytes, void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * BPR step
@@ -307,13 +329,16 @@ int gr_temporal_split(const int64_t *user, const int64_t *item, const int64_t *t
  * bias_correction2_sqrt = sqrt(1-beta2^t) are computed by the caller in double, as torch does; the
  * scalars are doubles and rounded to fp32 once inside (1-beta in double first), like torch's.
  * The *_host arguments are host arrays of n_tensors device pointers / element counts (16-byte aligned
- * tensors).  norm_out (device float, optional) receives the total norm.  Gradients are not modified. */
+ * tensors).  norm_out (device float, optional) receives the total norm.  Gradients are not modified.
+ * step_scalars_dev (optional, DEVICE float[2] = (step_size, bias_correction2_sqrt) already rounded to fp32):
+ * when non-NULL the two step-dependent scalars are read from it at run time instead of from the arguments, so
+ * a training step captured once in a CUDA graph stays valid for every later optimizer step. */
 size_t gr_clip_adam_workspace_bytes(const int64_t *numel_host, int32_t n_tensors);
 int gr_clip_adam_fused(void *const *params_host, const void *const *grads_host, void *const *exp_avg_host,
                        void *const *exp_avg_sq_host, const int64_t *numel_host, int32_t n_tensors, double max_norm,
                        double step_size, double beta1, double beta2, double eps, double weight_decay,
-                       double bias_correction2_sqrt, float *norm_out, void *workspace, size_t workspace_bytes,
-                       void *stream);
+                       double bias_correction2_sqrt, const float *step_scalars_dev, float *norm_out,
+                       void *workspace, size_t workspace_bytes, void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * Full-ranking evaluation

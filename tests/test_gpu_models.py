@@ -205,15 +205,21 @@ def _gat_setup(tiny, heads, dh, d_in, seed=0):
     return csr, n, x, ws, a_s, a_n, gen
 
 
+@pytest.mark.parametrize("seg_len", [128, 8])
 @pytest.mark.parametrize("heads,dh,concat,elu,drop", [(4, 16, True, True, 0.0), (4, 64, False, True, 0.0),
                                                        (4, 16, True, True, 0.1), (4, 64, False, False, 0.3),
                                                        (1, 64, True, False, 0.0), (8, 8, True, True, 0.2)])
-def test_gat_layer_forward_backward_vs_torch_autograd(tiny, heads, dh, concat, elu, drop):
+def test_gat_layer_forward_backward_vs_torch_autograd(tiny, heads, dh, concat, elu, drop, seg_len, monkeypatch):
     """gr_gat_aggregate (+ attention dropout at gat.py:138's position) and gr_gat_bwd against float64 autograd of
-    the edge-list restatement with the same per-edge mask: output, dx, dW of every head, d a_self, d a_neigh."""
+    the edge-list restatement with the same per-edge mask: output, dx, dW of every head, d a_self, d a_neigh.
+    seg_len = 8 cuts most rows of the tiny graph into segments (the hot-row path: partial online-softmax
+    triples / partial sums + combine kernels); 128 leaves every row to one warp."""
+    import sys
     from gnn_recommendations_b200.layer_ops import gat_layer
     from _torch_refs import gat_drop_mask, gat_layer_torch
+    monkeypatch.setattr(sys.modules[g.NormAdjCSR.__module__], "GAT_SEG_LEN", seg_len)
     csr, n, x, ws, a_s, a_n, gen = _gat_setup(tiny, heads, dh, 64)
+    assert (csr.gat_segments()[1] > 0) == (seg_len == 8)
     leaves = [x] + ws + a_s + a_n
     for t in leaves:
         t.requires_grad_(True)

@@ -372,3 +372,33 @@ def test_partitioned_graph_build_equals_rows_of_the_full_build(shape, world, sel
         assert torch.equal(got.indices, want.indices), (shape, world, rank)
         assert torch.equal(got.vals.view(torch.int32), want.vals.view(torch.int32)), (shape, world, rank)
         assert (got.n_rows, got.n_cols) == (want.n_rows, want.n_cols)
+
+
+def test_spmm_two_streams_concurrently_share_no_state():
+    """The C-ABI keeps no device-side state (the long-row ticket counters were __device__ globals):
+    two propagations with long rows in flight on two streams — each with its own scheduler words and side
+    stream — must both give the single-stream bits, repeatedly."""
+    rng = np.random.default_rng(5)
+    nu, ni, e = 3000, 400, 300000
+    u = rng.integers(0, nu, e)
+    i = (rng.pareto(1.2, e) * 3).astype(np.int64) % ni                 # hot item rows: thousands of entries
+    csr_a = g.NormAdjCSR.from_pairs(u, i, nu, ni, device=DEV, )
+    csr_b = g.NormAdjCSR.from_pairs(u[::2], i[::2], nu, ni, device=DEV)
+    assert csr_a.n_long > 0 and csr_b.n_long > 0
+    xa = torch.randn(nu + ni, 64, generator=torch.Generator().manual_seed(1)).to(DEV)
+    xb = torch.randn(nu + ni, 128, generator=torch.Generator().manual_seed(2)).to(DEV)
+    want_a, want_b = csr_a.spmm(xa)[0].clone(), csr_b.spmm(xb)[0].clone()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    torch.cuda.synchronize()
+    outs = []
+    for _ in range(20):
+        with torch.cuda.stream(s1):
+            ya = csr_a.spmm(xa)[0]
+        with torch.cuda.stream(s2):
+            yb = csr_b.spmm(xb)[0]
+            yb2 = csr_a.spmm(xa)[0]                                     # the SAME adjacency on a second stream
+        outs.append((ya, yb, yb2))
+    torch.cuda.synchronize()
+    assert len(csr_a._sched) >= 3                                       # default + two streams: separate words
+    for ya, yb, yb2 in outs:
+        assert torch.equal(ya, want_a) and torch.equal(yb, want_b) and torch.equal(yb2, want_a)

@@ -564,3 +564,50 @@ def test_item_sharded_topk_partials_merge_to_the_single_gpu_lists(world, tc):
         parts_i.append(pi)
     got = merge_topk_partials(torch.cat(parts_s), torch.cat(parts_i), k)
     assert torch.equal(got, want)
+
+
+def test_fused_clip_adam_more_than_32_tensors_with_empty_ones():
+    """the chunk loop (32 tensors per launch) must not revisit tensors when a chunk skipped
+    zero-numel tensors — 40 tensors with empties sprinkled in vs torch's clip_grad_norm_ + Adam."""
+    gen = torch.Generator().manual_seed(0)
+    shapes = [(0,) if i in (3, 17, 30, 31) else ((5 + i, 7) if i % 3 else (33 + i,)) for i in range(40)]
+    ours = [torch.nn.Parameter(torch.randn(*s, generator=gen).to(DEV)) for s in shapes]
+    ref = [torch.nn.Parameter(p.detach().cpu().clone()) for p in ours]
+    o1 = torch.optim.Adam(ours, lr=1e-2, weight_decay=1e-4)
+    o2 = torch.optim.Adam(ref, lr=1e-2, weight_decay=1e-4)
+    for step in range(3):
+        for p, q in zip(ours, ref):
+            gq = torch.randn(*q.shape, generator=gen)
+            q.grad = gq.clone()
+            p.grad = gq.to(DEV)
+        norm = g.fused_clip_adam_step(o1, 1.0)
+        want = torch.nn.utils.clip_grad_norm_(ref, 1.0)
+        o2.step()
+        assert abs(float(norm) - float(want)) <= 1e-5 * float(want)
+        for p, q in zip(ours, ref):
+            torch.testing.assert_close(p.detach().cpu(), q.detach(), rtol=2e-6, atol=2e-7)
+
+
+def test_cuda_graph_training_step_equals_eager(tiny, tmp_path):
+    """The captured-and-replayed training step (Trainer.train_steps) must leave the same parameters, Adam state
+    and mean loss as the eager loop: same sampler stream, same kernels, Adam's step-dependent scalars fed from
+    the device.  (BPR gradient scatter uses red.global.add: order-dependent in the last bits.)"""
+    nu, ni = int(tiny["n_users"]), int(tiny["n_items"])
+    res = []
+    for use_graph in (False, True):
+        torch.manual_seed(42)
+        m = g.LightGCN(nu, ni, embedding_dim=64, n_layers=3, init_scale=0.1)
+        tr = g.Trainer(m, dataset_from(tiny), dict(CFG, cuda_graph=use_graph, checkpoint_dir=str(tmp_path / str(use_graph))),
+                       device=torch.device(DEV))
+        torch.manual_seed(123)
+        l1 = tr.train_steps(40)
+        l2 = tr.train_steps(25)                      # second call: the cached graph is replayed from step 0
+        assert (getattr(tr, "_graph", None) is not None) == use_graph
+        st = tr.optimizer.state[m.user_embedding.weight]
+        res.append((l1, l2, m.user_embedding.weight.detach().cpu(), m.item_embedding.weight.detach().cpu(),
+                    st["exp_avg_sq"].cpu(), float(st["step"])))
+    a, b = res
+    assert abs(a[0] - b[0]) <= 1e-6 * abs(a[0]) and abs(a[1] - b[1]) <= 1e-6 * abs(a[1])
+    assert a[5] == b[5] == 65.0
+    for x, y in zip(a[2:5], b[2:5]):
+        torch.testing.assert_close(x, y, rtol=1e-4, atol=1e-6)
