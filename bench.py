@@ -590,7 +590,7 @@ def run_model_extras(g, dev, hbm_peak):
         b_alg = _model_forward_bytes(name, nnz, n)
         model.train()
         n_steps = 100
-        tr.train_steps(5)
+        tr.train_steps(20)              # 3 eager steps, then the step is captured in a CUDA graph and replayed
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         loss = tr.train_steps(n_steps)
@@ -618,9 +618,11 @@ def run_model_extras(g, dev, hbm_peak):
             "train_step_ms": ms_step, "train_steps_timed": n_steps, "loss": loss,
             "epoch_s_extrapolated": ms_step * steps_epoch * 1e-3, "steps_per_epoch": steps_epoch,
             "cpu_forward_s": cpu_s, "cpu_forward_edges_per_s": 3 * nnz / cpu_s, "cpu_cores": torch.get_num_threads(),
-            "what": "eval forward through model.get_all_embeddings; training step = Trainer.train_steps body (host "
-                    "sampler, propagation, fused BPR, backward kernels gr_rowmap_bwd / gr_gat_bwd / gr_gs_compose_bwd + "
-                    "SpMM on A^T, fused clip+Adam); CPU = oracle port, one forward"}
+            "cuda_graph_step": getattr(tr, "_graph", None) is not None,
+            "what": "eval forward through model.get_all_embeddings; training step = Trainer.train_steps body in train() "
+                    "mode with the reference's default dropout (host sampler, propagation, fused BPR, backward kernels "
+                    "gr_rowmap_bwd / gr_gat_bwd / gr_gs_compose_bwd + SpMM on A^T, fused clip+Adam; captured once in a "
+                    "CUDA graph and replayed); CPU = oracle port, one forward"}
         del tr, model, ds, csr
         torch.cuda.empty_cache()
     return out

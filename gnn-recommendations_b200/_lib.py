@@ -35,20 +35,20 @@ SIGNATURES = {
                                   _p, _i64, _p, _i64, _p, _i64, _p, _i64, _f32, _i32, _p, _i32, _i32, _i64, _p, _p]),
     "gr_peer_scatter_rows": (C.c_int, [_p, _i64, _i64, _i32, _p, _i32, _i32, _i64, _i64, _p]),
     "gr_rowmap_f32": (C.c_int, [_p, _i64, _p, _p, _p, _i64, _p, _i64, _p, _p, _p, _i64, _f32, _f32, _i32, _f32,
-                                _i64, _i32, _i32, _f32, _u64, _p, _i64, _p]),
+                                _i64, _i32, _i32, _f32, _u64, _p, _p, _i64, _p]),
     "gr_rowmap_bwd_workspace_bytes": (_sz, [_i64, _i32, _i32, _i32]),
     "gr_rowmap_bwd": (C.c_int, [_p, _i64, _p, _i64, _p, _i64, _p, _p, _i64, _p, _i64, _p, _p, _i64, _f32, _f32, _i32,
-                                _f32, _i64, _i32, _i32, _f32, _u64, _p, _i64, _p, _i64, _p, _i64, _p, _i64, _p, _p,
+                                _f32, _i64, _i32, _i32, _f32, _u64, _p, _p, _i64, _p, _i64, _p, _i64, _p, _i64, _p, _p,
                                 _sz, _p]),
     "gr_gs_compose": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _i32, _p, _p, _p]),
     "gr_gs_compose_bwd": (C.c_int, [_p, _p, _p, _p, _i32, _i32, _i32, _i32, _p, _p, _p, _p]),
     "gr_gat_node_scores": (C.c_int, [_p, _i64, _p, _p, _i64, _i32, _i32, _p, _p, _p]),
     "gr_gat_aggregate_workspace_bytes": (_sz, [_i32, _i32, _i32]),
-    "gr_gat_aggregate": (C.c_int, [_p, _p, _i64, _p, _i64, _p, _p, _i32, _i32, _f32, _i32, _i32, _f32, _u64, _i64,
+    "gr_gat_aggregate": (C.c_int, [_p, _p, _i64, _p, _i64, _p, _p, _i32, _i32, _f32, _i32, _i32, _f32, _u64, _p, _i64,
                                    _p, _p, _i64, _p, _p, _p, _sz, _p]),
     "gr_gat_bwd_workspace_bytes": (_sz, [_i64, _i32, _i32, _i32, _i32, _i32]),
     "gr_gat_bwd": (C.c_int, [_p, _p, _p, _p, _i64, _i64, _p, _i64, _p, _p, _p, _p, _p, _i64, _p, _i64,
-                             _p, _p, _i32, _i32, _f32, _i32, _i32, _f32, _u64, _p, _p, _p, _p, _p, _sz, _p]),
+                             _p, _p, _i32, _i32, _f32, _i32, _i32, _f32, _u64, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "gr_sample_bpr_batch": (_i64, [_p, _p, _p, _p, _p, _i64, _i64, _i64, _p, _p, _p, _p, _p]),
     "gr_bpr_workspace_bytes": (_sz, [_i64]),
     "gr_bpr_fused": (C.c_int, [_p, _i64, _i64, _i64, _p, _p, _p, _i64, _i32, _f32, _p, _i64, _p, _p, _sz, _p]),

@@ -106,6 +106,7 @@ struct GatArgs {
     unsigned drop_thr;     // attention dropout (gat.py:138): weight kept with prob 1-p, scaled by 1/(1-p)
     float drop_scale;
     unsigned long long drop_seed;
+    const unsigned long long *drop_seed_dev;   // optional: added to drop_seed at run time (CUDA-graph replays)
     SegTable sg;
     float *p_m, *p_z;      // [n_seg, heads]
     float *p_acc;          // [n_seg, heads*dh]
@@ -168,6 +169,7 @@ __global__ void __launch_bounds__(256) gat_aggregate_kernel(const GatArgs a) {
     const int width4 = a.heads * a.dh / 4;
     const int dh4 = a.dh / 4;
     const int hgroups = (a.heads + 3) >> 2;
+    const unsigned long long seed = a.drop_seed + (a.drop_seed_dev ? *a.drop_seed_dev : 0ULL);
     int head[SLOTS];
     bool on[SLOTS];
     float si[SLOTS], m[SLOTS], z[SLOTS];
@@ -216,7 +218,7 @@ __global__ void __launch_bounds__(256) gat_aggregate_kernel(const GatArgs a) {
                             z[q] = z[q] * sc + w;
                             if (a.drop_thr) {   // the softmax normaliser keeps every edge; only the weight is dropped
                                 const unsigned long long bits = drop_bits(
-                                    a.drop_seed, ((unsigned long long)i * a.n_cols + jj[u]) * hgroups + (head[q] >> 2));
+                                    seed, ((unsigned long long)i * a.n_cols + jj[u]) * hgroups + (head[q] >> 2));
                                 w = drop_keep(bits, head[q] & 3, a.drop_thr) ? w * a.drop_scale : 0.f;
                             }
                             acc[q].x = acc[q].x * sc + w * hv[u][q].x;
@@ -340,6 +342,7 @@ struct GatBwdArgs {
     unsigned drop_thr;
     float drop_scale;
     unsigned long long drop_seed;
+    const unsigned long long *drop_seed_dev;
     SegTable rsg, csg;    // segments of the row pattern / of the column pattern
     float4 *p_S;          // [rsg.n_seg, heads]  partial (S0, S1, S2, S3)
     float *p_dt;          // [csg.n_seg, heads]
@@ -358,6 +361,7 @@ __global__ void __launch_bounds__(256) gat_bwd_row_kernel(const GatBwdArgs a) {
     if (!gat_item(a.rsg, a.indptr, a.n_rows, item, j, start, end, seg)) return;
     const int width4 = a.heads * a.dh / 4, dh4 = a.dh / 4;
     const int hgroups = (a.heads + 3) >> 2;
+    const unsigned long long seed = a.drop_seed + (a.drop_seed_dev ? *a.drop_seed_dev : 0ULL);
     int head[SLOTS];
     bool on[SLOTS];
     float4 doj[SLOTS];
@@ -408,7 +412,7 @@ __global__ void __launch_bounds__(256) gat_bwd_row_kernel(const GatBwdArgs a) {
                             float c = 1.f;
                             if (a.drop_thr) {
                                 const unsigned long long bits = drop_bits(
-                                    a.drop_seed, ((unsigned long long)j * a.n_cols + kid[u]) * hgroups + (head[q] >> 2));
+                                    seed, ((unsigned long long)j * a.n_cols + kid[u]) * hgroups + (head[q] >> 2));
                                 c = drop_keep(bits, head[q] & 3, a.drop_thr) ? a.drop_scale : 0.f;
                             }
                             const float lp = pre > 0.f ? 1.f : a.slope;
@@ -507,6 +511,7 @@ __global__ void __launch_bounds__(256) gat_bwd_col_kernel(const GatBwdArgs a) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int width4 = a.heads * a.dh / 4, dh4 = a.dh / 4;
     const int hgroups = (a.heads + 3) >> 2;
+    const unsigned long long seed = a.drop_seed + (a.drop_seed_dev ? *a.drop_seed_dev : 0ULL);
     int head[SLOTS];
     bool on[SLOTS];
     float4 as[SLOTS], an[SLOTS], gs[SLOTS], gn[SLOTS];
@@ -569,7 +574,7 @@ __global__ void __launch_bounds__(256) gat_bwd_col_kernel(const GatBwdArgs a) {
                                 float c = 1.f;
                                 if (a.drop_thr) {
                                     const unsigned long long bits = drop_bits(
-                                        a.drop_seed, ((unsigned long long)iid[u] * a.n_cols + j) * hgroups + (head[q] >> 2));
+                                        seed, ((unsigned long long)iid[u] * a.n_cols + j) * hgroups + (head[q] >> 2));
                                     c = drop_keep(bits, head[q] & 3, a.drop_thr) ? a.drop_scale : 0.f;
                                 }
                                 dt_acc[q] += alpha * (c * dot - sv[u][q].w) * (pre > 0.f ? 1.f : a.slope);
@@ -691,7 +696,7 @@ extern "C" size_t gr_gat_aggregate_workspace_bytes(int32_t n_seg, int32_t heads,
 extern "C" int gr_gat_aggregate(const int32_t *indptr, const int32_t *indices, int64_t n_rows, const float *h,
                                 int64_t ldh, const float *s, const float *t, int32_t heads, int32_t dh,
                                 float slope, int32_t mean_heads, int32_t elu, float drop_p, uint64_t drop_seed,
-                                int64_t n_cols, const gr_gat_segments *segs_host, float *out, int64_t ldo,
+                                const uint64_t *drop_seed_dev, int64_t n_cols, const gr_gat_segments *segs_host, float *out, int64_t ldo,
                                 float *m_out, float *z_out, void *workspace, size_t workspace_bytes, void *stream) {
     if (!indptr || !indices || !h || !s || !t || !out || n_rows < 0 || heads <= 0 || dh <= 0) return GR_ERR_INVALID;
     if (!(drop_p >= 0.f) || drop_p >= 1.f || n_cols < 0) return GR_ERR_INVALID;
@@ -709,6 +714,7 @@ extern "C" int gr_gat_aggregate(const int32_t *indptr, const int32_t *indices, i
     a.out = out; a.ldo = ldo; a.m_out = m_out; a.z_out = z_out;
     a.n_cols = n_cols;
     a.drop_thr = drop_threshold(drop_p); a.drop_scale = drop_scale_of(a.drop_thr); a.drop_seed = drop_seed;
+    a.drop_seed_dev = reinterpret_cast<const unsigned long long *>(drop_seed_dev);
     a.sg = seg_table(segs_host);
     a.p_m = a.p_z = a.p_acc = nullptr;
     if (a.sg.n_seg > 0) {
@@ -755,7 +761,7 @@ extern "C" int gr_gat_bwd(const int32_t *indptr, const int32_t *indices, const i
                           const float *s, const float *t, const float *m, const float *z, const float *out,
                           int64_t ldo, const float *dout, int64_t lddo, const float *a_self, const float *a_neigh,
                           int32_t heads, int32_t dh, float slope, int32_t mean_heads, int32_t elu, float drop_p,
-                          uint64_t drop_seed, const gr_gat_segments *row_segs_host,
+                          uint64_t drop_seed, const uint64_t *drop_seed_dev, const gr_gat_segments *row_segs_host,
                           const gr_gat_segments *col_segs_host, float *dH, float *da, void *workspace,
                           size_t workspace_bytes, void *stream) {
     if (!indptr || !indices || !t_indptr || !t_indices || !h || !s || !t || !m || !z || !dout || !a_self ||
@@ -808,6 +814,7 @@ extern "C" int gr_gat_bwd(const int32_t *indptr, const int32_t *indices, const i
     a.dH = dH; a.partial = partial; a.n_cols = n_cols; a.n_rows = (int)n_rows; a.heads = heads; a.dh = dh;
     a.slope = slope;
     a.drop_thr = drop_threshold(drop_p); a.drop_scale = drop_scale_of(a.drop_thr); a.drop_seed = drop_seed;
+    a.drop_seed_dev = reinterpret_cast<const unsigned long long *>(drop_seed_dev);
     a.rsg = rsg; a.csg = csg; a.p_S = p_S; a.p_dt = p_dt; a.p_dh = p_dh;
     const unsigned row_items_grid = (unsigned)((n_rows + rsg.n_seg + 7) / 8);
     if (one) gat_bwd_row_kernel<1><<<row_items_grid, 256, 0, st>>>(a);

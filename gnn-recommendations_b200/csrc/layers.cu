@@ -33,6 +33,7 @@ struct RowMapArgs {
     unsigned drop_thr;        // 0 = no dropout; else element dropped when its 16-bit uniform < drop_thr
     float drop_scale;         // 65536 / (65536 - drop_thr)
     unsigned long long drop_seed;
+    const unsigned long long *drop_seed_dev;   // optional: added to drop_seed at run time (CUDA-graph replays)
 };
 
 constexpr int RM_ROWS = 64;
@@ -145,7 +146,8 @@ __global__ void __launch_bounds__(256) rowmap_kernel(const RowMapArgs a) {
                 o[0] += a.beta * rv.x; o[1] += a.beta * rv.y; o[2] += a.beta * rv.z; o[3] += a.beta * rv.w;
             }
             if (a.drop_thr) {   // nn.Dropout on the layer output (ngcf.py:86, model.py:198-199): keep/(1-p)
-                const unsigned long long bits = drop_bits(a.drop_seed, (unsigned long long)r * nc4 + cg);
+                const unsigned long long bits = drop_bits(a.drop_seed + (a.drop_seed_dev ? *a.drop_seed_dev : 0ULL),
+                                                          (unsigned long long)r * nc4 + cg);
 #pragma unroll
                 for (int c = 0; c < 4; ++c)
                     o[c] = drop_keep(bits, c, a.drop_thr) ? o[c] * a.drop_scale : 0.f;
@@ -163,7 +165,7 @@ extern "C" int gr_rowmap_f32(const float *x1, int64_t ld1, const float *wa, cons
                              int64_t ld2, const float *x3, int64_t ld3, const float *wb, const float *bias_b,
                              const float *resid, int64_t ldr, float alpha, float beta, int32_t act, float slope,
                              int64_t n_rows, int32_t d_in, int32_t d_out, float drop_p, uint64_t drop_seed,
-                             float *out, int64_t ldo, void *stream) {
+                             const uint64_t *drop_seed_dev, float *out, int64_t ldo, void *stream) {
     if (!x1 || !wa || !out || n_rows < 0) return GR_ERR_INVALID;
     if (!(drop_p >= 0.f) || drop_p >= 1.f) return GR_ERR_INVALID;
     if (wb && (!x2 || !x3)) return GR_ERR_INVALID;
@@ -182,6 +184,7 @@ extern "C" int gr_rowmap_f32(const float *x1, int64_t ld1, const float *wa, cons
     a.out = out; a.n_rows = (int)n_rows; a.d_in = d_in; a.d_out = d_out;
     a.alpha = alpha; a.beta = beta; a.slope = slope; a.act = act;
     a.drop_thr = drop_threshold(drop_p); a.drop_scale = drop_scale_of(a.drop_thr); a.drop_seed = drop_seed;
+    a.drop_seed_dev = reinterpret_cast<const unsigned long long *>(drop_seed_dev);
     const size_t smem = ((size_t)d_in * d_out + (size_t)d_in * RM_ROWS) * 4 * (wb ? 2 : 1);
     if (smem > 227 * 1024) return GR_ERR_UNSUPPORTED;
     GR_CUDA_CHECK(cudaFuncSetAttribute(rowmap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

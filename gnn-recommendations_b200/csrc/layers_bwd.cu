@@ -41,6 +41,7 @@ struct RowMapBwdArgs {
     unsigned drop_thr;
     float drop_scale;
     unsigned long long drop_seed;
+    const unsigned long long *drop_seed_dev;
 };
 
 // dz (written for the weight-gradient kernel) and the input gradients.  Same tiling as the forward
@@ -77,7 +78,8 @@ __global__ void __launch_bounds__(256) rowmap_bwd_dx_kernel(const RowMapBwdArgs 
                 float gg[4] = {gv.x, gv.y, gv.z, gv.w};
                 float keep[4] = {1.f, 1.f, 1.f, 1.f};
                 if (a.drop_thr) {
-                    const unsigned long long bits = drop_bits(a.drop_seed, (unsigned long long)row * o4 + f);
+                    const unsigned long long bits = drop_bits(a.drop_seed + (a.drop_seed_dev ? *a.drop_seed_dev : 0ULL),
+                                                              (unsigned long long)row * o4 + f);
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         keep[c] = drop_keep(bits, c, a.drop_thr) ? a.drop_scale : 0.f;
@@ -314,7 +316,7 @@ extern "C" int gr_rowmap_bwd(const float *g, int64_t ldg, const float *out, int6
                              const float *wa, const float *x2, int64_t ld2, const float *x3, int64_t ld3,
                              const float *wb, const float *resid, int64_t ldr, float alpha, float beta, int32_t act,
                              float slope, int64_t n_rows, int32_t d_in, int32_t d_out, float drop_p, uint64_t drop_seed,
-                             float *dx1, int64_t ldd1, float *dx2, int64_t ldd2, float *dx3, int64_t ldd3,
+                             const uint64_t *drop_seed_dev, float *dx1, int64_t ldd1, float *dx2, int64_t ldd2, float *dx3, int64_t ldd3,
                              float *dresid, int64_t lddr, float *dw, void *workspace, size_t workspace_bytes,
                              void *stream) {
     if (!g || !x1 || !wa || n_rows < 0) return GR_ERR_INVALID;
@@ -362,6 +364,7 @@ extern "C" int gr_rowmap_bwd(const float *g, int64_t ldg, const float *out, int6
         a.n_rows = (int)n_rows; a.d_in = d_in; a.d_out = d_out; a.n_tiles = n_tiles;
         a.alpha = alpha; a.beta = beta; a.slope = slope; a.act = act;
         a.drop_thr = thr; a.drop_scale = drop_scale_of(thr); a.drop_seed = drop_seed;
+        a.drop_seed_dev = reinterpret_cast<const unsigned long long *>(drop_seed_dev);
         const size_t smem = dx1 ? ((size_t)d_in * d_out * (wb ? 2 : 1) + (size_t)d_out * RB_ROWS) * 4 : 0;
         if (smem > 227 * 1024) return GR_ERR_UNSUPPORTED;
         GR_CUDA_CHECK(cudaFuncSetAttribute(rowmap_bwd_dx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

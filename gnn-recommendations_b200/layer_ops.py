@@ -20,10 +20,49 @@ from .graph_builder import NormAdjCSR
 ACT_NONE, ACT_LEAKY, ACT_ELU = 0, 1, 2
 
 
-def new_dropout_seed() -> int:
+class DropSeed:
+    """Seed of one fused-dropout call: ``value`` (host integer, a kernel argument) plus, inside a CUDA-graph
+    capture, ``dev`` — a device int64 the kernels ADD to it at run time, refreshed by the Trainer before
+    every replay, so a step captured once still draws a new mask per step."""
+    __slots__ = ("value", "dev")
+
+    def __init__(self, value: int, dev: Optional[torch.Tensor] = None):
+        self.value, self.dev = int(value) & 0x7FFFFFFFFFFFFFFF, dev
+
+
+_SEED_STATE = {"dev": None, "count": 0}
+
+
+class device_dropout_seeds:
+    """Context: dropout seeds drawn inside come from ``dev`` (device int64[1]) plus a per-call offset."""
+
+    def __init__(self, dev: torch.Tensor):
+        self.dev = dev
+
+    def __enter__(self):
+        self.prev = dict(_SEED_STATE)
+        _SEED_STATE["dev"], _SEED_STATE["count"] = self.dev, 0
+        return self
+
+    def __exit__(self, *a):
+        _SEED_STATE.update(self.prev)
+        return False
+
+
+def new_dropout_seed() -> DropSeed:
     """A 63-bit seed drawn from torch's global CPU generator (the stream the reference's nn.Dropout
-    consumes), so torch.manual_seed makes train-mode runs reproducible."""
-    return int(torch.empty((), dtype=torch.int64).random_().item())
+    consumes), so torch.manual_seed makes train-mode runs reproducible; inside
+    ``device_dropout_seeds`` a distinct constant offset onto the device-resident step seed instead."""
+    if _SEED_STATE["dev"] is not None:
+        _SEED_STATE["count"] += 1
+        return DropSeed(_SEED_STATE["count"] * 0x9E3779B97F4A7C15, _SEED_STATE["dev"])
+    return DropSeed(int(torch.empty((), dtype=torch.int64).random_().item()))
+
+
+def _seed_parts(seed):
+    if isinstance(seed, DropSeed):
+        return seed.value, seed.dev
+    return int(seed), None
 
 
 class _Spmm(torch.autograd.Function):
@@ -58,6 +97,7 @@ def _ld(t: Optional[torch.Tensor]) -> int:
 
 
 def _rowmap_raw(x1, wa, ba, x2, x3, wb, bb, resid, alpha, beta, act, slope, drop_p=0.0, drop_seed=0, out=None):
+    seed, seed_dev = _seed_parts(drop_seed)
     n, d_in = x1.shape
     d_out = wa.shape[1]
     if out is None:
@@ -66,13 +106,14 @@ def _rowmap_raw(x1, wa, ba, x2, x3, wb, bb, resid, alpha, beta, act, slope, drop
         check(lib().gr_rowmap_f32(
             ptr(x1), _ld(x1), ptr(wa), ptr(ba), ptr(x2), _ld(x2), ptr(x3), _ld(x3), ptr(wb), ptr(bb), ptr(resid),
             _ld(resid), float(alpha), float(beta), int(act), float(slope), n, d_in, d_out, float(drop_p),
-            int(drop_seed), ptr(out), out.stride(0), stream_ptr()), "gr_rowmap_f32")
+            seed, ptr(seed_dev), ptr(out), out.stride(0), stream_ptr()), "gr_rowmap_f32")
     return out
 
 
 def _rowmap_bwd_raw(g, out, x1, wa, x2, x3, wb, resid, alpha, beta, act, slope, drop_p, drop_seed, need_dx, need_dx2,
                     need_dx3, need_dresid, need_dw):
     """-> (dx1, dx2, dx3, dresid, dw) — dw is the flat [nw*d_in*d_out + d_out] buffer of gr_rowmap_bwd."""
+    seed, seed_dev = _seed_parts(drop_seed)
     n, d_in = x1.shape
     d_out = wa.shape[1]
     dev = x1.device
@@ -90,7 +131,7 @@ def _rowmap_bwd_raw(g, out, x1, wa, x2, x3, wb, resid, alpha, beta, act, slope, 
         check(l.gr_rowmap_bwd(
             ptr(g), _ld(g), ptr(out), _ld(out), ptr(x1), _ld(x1), ptr(wa), ptr(x2), _ld(x2), ptr(x3), _ld(x3), ptr(wb),
             ptr(resid), _ld(resid), float(alpha), float(beta), int(act), float(slope), n, d_in, d_out, float(drop_p),
-            int(drop_seed), ptr(dx1), _ld(dx1), ptr(dx2), _ld(dx2), ptr(dx3), _ld(dx3), ptr(dres), _ld(dres), ptr(dw),
+            seed, ptr(seed_dev), ptr(dx1), _ld(dx1), ptr(dx2), _ld(dx2), ptr(dx3), _ld(dx3), ptr(dres), _ld(dres), ptr(dw),
             ptr(ws), ws_bytes, stream_ptr()), "gr_rowmap_bwd")
     return dx1, dx2, dx3, dres, dw
 
@@ -141,11 +182,11 @@ class _RowMap(torch.autograd.Function):
 
 def rowmap(x1, wa, bias_a=None, x2=None, x3=None, wb=None, bias_b=None, resid=None, alpha: float = 1.0,
            beta: float = 0.0, act: int = ACT_NONE, slope: float = 0.0, drop_p: float = 0.0,
-           drop_seed: int = 0) -> torch.Tensor:
+           drop_seed=0) -> torch.Tensor:
     """out = D * (alpha * act(x1 @ wa + bias_a + (x2 * x3) @ wb + bias_b) + beta * resid)  (gr_rowmap_f32);
     D = 1 unless drop_p > 0 (layer-output dropout, mask = hash(drop_seed, element))."""
     x3_is_x1 = x3 is not None and x3 is x1
-    return _RowMap.apply(float(alpha), float(beta), int(act), float(slope), float(drop_p), int(drop_seed), x3_is_x1,
+    return _RowMap.apply(float(alpha), float(beta), int(act), float(slope), float(drop_p), drop_seed, x3_is_x1,
                          x1, wa, bias_a, x2, None if x3_is_x1 else x3, wb, bias_b, resid)
 
 
@@ -193,6 +234,7 @@ def _gat_forward_kernels(csr, x, wcat, a_self, a_neigh, heads, dh, slope, mean_h
                          keep=False):
     n = x.shape[0]
     dev = x.device
+    seed, seed_dev = _seed_parts(drop_seed)
     h = _rowmap_raw(x, wcat, None, None, None, None, None, None, 1.0, 0.0, ACT_NONE, 0.0)     # [N, heads*dh]
     s = torch.empty((n, heads), dtype=torch.float32, device=dev)
     t = torch.empty((n, heads), dtype=torch.float32, device=dev)
@@ -208,7 +250,7 @@ def _gat_forward_kernels(csr, x, wcat, a_self, a_neigh, heads, dh, slope, mean_h
         check(l.gr_gat_node_scores(ptr(h), h.stride(0), ptr(a_self), ptr(a_neigh), n, heads, dh, ptr(s), ptr(t),
                                    stream_ptr()), "gr_gat_node_scores")
         check(l.gr_gat_aggregate(ptr(csr.indptr), ptr(csr.indices), n, ptr(h), h.stride(0), ptr(s), ptr(t), heads,
-                                 dh, float(slope), int(mean_heads), int(elu), float(drop_p), int(drop_seed),
+                                 dh, float(slope), int(mean_heads), int(elu), float(drop_p), seed, ptr(seed_dev),
                                  csr.n_cols, C.byref(segs) if segs is not None else None, ptr(out), out.stride(0),
                                  ptr(m), ptr(z), ptr(ws), ws_bytes, stream_ptr()), "gr_gat_aggregate")
     return out, (h, s, t, m, z, raw)
@@ -234,6 +276,7 @@ class _GatLayer(torch.autograd.Function):
         csr_t = csr.transpose()          # the pattern of Âᵀ (Â itself for the symmetric bipartite graph)
         g = _rows(g)
         n, width, dev = x.shape[0], heads * dh, x.device
+        seed, seed_dev = _seed_parts(drop_seed)
         l = lib()
         dH = torch.empty((n, width), dtype=torch.float32, device=dev)
         da = torch.empty(2 * width, dtype=torch.float32, device=dev)
@@ -244,7 +287,7 @@ class _GatLayer(torch.autograd.Function):
         with torch.cuda.device(dev):
             check(l.gr_gat_bwd(ptr(csr.indptr), ptr(csr.indices), ptr(csr_t.indptr), ptr(csr_t.indices), n, csr.n_cols,
                                ptr(h), h.stride(0), ptr(s), ptr(t), ptr(m), ptr(z), ptr(out), out.stride(0), ptr(g), g.stride(0), ptr(a_self), ptr(a_neigh), heads, dh,
-                               float(slope), int(mean_heads), int(elu), float(drop_p), int(drop_seed),
+                               float(slope), int(mean_heads), int(elu), float(drop_p), seed, ptr(seed_dev),
                                C.byref(rsegs) if rsegs is not None else None,
                                C.byref(csegs) if csegs is not None else None, ptr(dH), ptr(da),
                                ptr(ws), ws_bytes, stream_ptr()), "gr_gat_bwd")
@@ -257,7 +300,7 @@ class _GatLayer(torch.autograd.Function):
 
 def gat_layer(csr: NormAdjCSR, x, weights: Sequence[torch.Tensor], a_self: Sequence[torch.Tensor],
               a_neigh: Sequence[torch.Tensor], slope: float, concat_heads: bool, elu: bool, drop_p: float = 0.0,
-              drop_seed: int = 0) -> torch.Tensor:
+              drop_seed=0) -> torch.Tensor:
     """One GATLayer.forward (gat.py:76-151) + the ELU GAT.forward applies after it (gat.py:283).
     ``weights[h]``: nn.Linear.weight [dh, d_in]; ``a_self[h]`` / ``a_neigh[h]``: [dh, 1].
     ``drop_p`` > 0: dropout on the softmaxed attention weights (gat.py:138)."""
@@ -266,4 +309,4 @@ def gat_layer(csr: NormAdjCSR, x, weights: Sequence[torch.Tensor], a_self: Seque
     a_s = torch.cat([a.reshape(-1) for a in a_self])
     a_n = torch.cat([a.reshape(-1) for a in a_neigh])
     return _GatLayer.apply(x, wcat, a_s, a_n, csr, heads, dh, float(slope), not concat_heads, elu, float(drop_p),
-                           int(drop_seed))
+                           drop_seed)

@@ -63,6 +63,8 @@ class _LightGCNPropagate(torch.autograd.Function):
 
 
 class LightGCN(BaseRecommender):
+    _graph_safe = True      # the training step can be captured in a CUDA graph (no host-seeded torch RNG ops)
+
     def __init__(self, n_users: int, n_items: int, embedding_dim: int = 64, n_layers: int = 3,
                  init_scale: float = 0.01):
         super().__init__(n_users, n_items, embedding_dim)

@@ -33,6 +33,8 @@ class NGCFLayer(nn.Module):
 
 
 class NGCF(BaseRecommender):
+    _graph_safe = True      # the training step can be captured in a CUDA graph (no host-seeded torch RNG ops)
+
     def __init__(self, n_users: int, n_items: int, embedding_dim: int = 64, layer_sizes: Optional[List[int]] = None,
                  dropout: float = 0.1, init_scale: float = 0.01):
         super().__init__(n_users, n_items, embedding_dim)

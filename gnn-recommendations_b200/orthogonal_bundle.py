@@ -88,6 +88,8 @@ class BundleConnectionLayer(nn.Module):
 
 
 class OrthogonalBundleGNN(BaseRecommender):
+    _graph_safe = True      # the training step can be captured in a CUDA graph (no host-seeded torch RNG ops)
+
     def __init__(self, n_users: int, n_items: int, embedding_dim: int = 64, n_layers: int = 3, block_size: int = 8,
                  residual_alpha: float = 0.1, dropout: float = 0.0, init_scale: float = 0.01,
                  use_parallel_transport: bool = True, use_edge_index: bool = False):

@@ -23,6 +23,7 @@ import torch
 import torch.optim as optim
 
 from .evaluator import _pairs, full_rank_topk, ground_truth_dict, seen_csr
+from .layer_ops import device_dropout_seeds, new_dropout_seed
 from .optim import fused_clip_adam_step, fused_clip_adam_supported
 from .losses import BPRLoss, bpr_fused
 from .metrics import compute_metrics_from_topk, topk_metrics_device
@@ -43,17 +44,20 @@ class _GraphStep:
         sampler = tr._get_sampler()
         self.b = min(tr.batch_size, len(sampler))
         dev = tr.device
-        self.idx = torch.zeros((3, self.b), dtype=torch.int64, device=dev)
+        # one staged int64 vector per step: users | positives | negatives | dropout seed of the step
+        self.flat = torch.zeros(3 * self.b + 1, dtype=torch.int64, device=dev)
+        self.idx = self.flat[:3 * self.b].view(3, self.b)
+        self.seed = self.flat[3 * self.b:]
         self.sc = torch.ones(2, dtype=torch.float32, device=dev)
-        self.stage = [(torch.zeros((3, self.b), dtype=torch.int64, pin_memory=True),
+        self.stage = [(torch.zeros(3 * self.b + 1, dtype=torch.int64, pin_memory=True),
                        torch.zeros(2, dtype=torch.float32, pin_memory=True), torch.cuda.Event()) for _ in range(self.RING)]
-        self.views = [tuple(st[0][r].numpy() for r in range(3)) for st in self.stage]
+        self.views = [tuple(st[0][r * self.b:(r + 1) * self.b].numpy() for r in range(3)) for st in self.stage]
         self.used = [False] * self.RING
         self.k = 0
         model, opt = tr.model, tr.optimizer
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        with torch.cuda.graph(self.graph, stream=torch.cuda.current_stream(dev)), device_dropout_seeds(self.seed):
             x = tr._propagated(adj)
             loss = bpr_fused(x, model.n_users, self.idx[0], self.idx[1], self.idx[2].view(-1, 1))
             opt.zero_grad()
@@ -74,9 +78,10 @@ class _GraphStep:
         if self.used[k]:
             ev.synchronize()                         # the copy that last read this staging slot has run
         tr._get_sampler().sample(tr.batch_size, out=self.views[k])
+        idx_h[3 * self.b] = new_dropout_seed().value           # one draw of the CPU generator per step
         step_size, bc2 = self._scalars(tr.optimizer)          # advances the optimizer's step counters
         sc_h[0], sc_h[1] = step_size, bc2
-        self.idx.copy_(idx_h, non_blocking=True)
+        self.flat.copy_(idx_h, non_blocking=True)
         self.sc.copy_(sc_h, non_blocking=True)
         ev.record(torch.cuda.current_stream(tr.device))
         self.used[k] = True
@@ -173,6 +178,19 @@ class Trainer:
         three eager steps it is captured ONCE into a CUDA graph — propagation, fused BPR, backward kernels,
         fused clip+Adam — and replayed; per step the host only draws the batch (bit-exact sampler), stages the
         3B indices and Adam's two step-dependent scalars in pinned memory and launches the graph."""
+        # All steps run on one dedicated non-default stream: autograd ties each parameter's AccumulateGrad node to
+        # the stream it was created on, and a node created on the legacy default stream cannot be used inside
+        # a stream capture ("would make the legacy stream depend on a capturing stream").
+        cur = torch.cuda.current_stream(self.device)
+        if getattr(self, "_train_stream", None) is None:
+            self._train_stream = torch.cuda.Stream(self.device)
+        self._train_stream.wait_stream(cur)
+        with torch.cuda.stream(self._train_stream):
+            out = self._train_steps(n_steps)
+        cur.wait_stream(self._train_stream)
+        return out
+
+    def _train_steps(self, n_steps: int) -> float:
         self.model.train()
         adj = self.dataset.get_torch_adjacency(normalized=True).to(self.device)
         if getattr(self, "_loss_acc", None) is None:
@@ -185,6 +203,7 @@ class Trainer:
             graph = self._graph = None
         for it in range(n_steps):
             if graph is None and it >= 3 and n_steps - it >= 8 and self._graph_ok(adj):
+                x = loss = users = pos = neg = None          # drop the last eager step's autograd graph
                 graph = self._graph = self._capture_step(adj, total)
             if graph is not None:
                 if graph.run():
@@ -213,8 +232,8 @@ class Trainer:
 
     # ------------------------------------------------------------------ CUDA-graph step
     def _graph_ok(self, adj, need_grads: bool = True) -> bool:
-        """Capture needs: the fused optimizer, a device-resident CSR, one negative per sample, and no active
-        dropout (its per-step seed is a kernel argument and would be frozen into the graph)."""
+        """Capture needs: the fused optimizer, a device-resident CSR, one negative per sample and a model whose
+        train-mode randomness (fused dropout) takes its seed from device memory (``_graph_safe``)."""
         from .graph_builder import NormAdjCSR
 
         if not self.config.get("cuda_graph", True) or not self.fused_optimizer:
@@ -225,12 +244,8 @@ class Trainer:
             return False
         if need_grads and any(p.grad is None for p in self.model.parameters()):
             return False
-        if hasattr(self.model, "get_regularization_loss"):
+        if hasattr(self.model, "get_regularization_loss") or not getattr(self.model, "_graph_safe", False):
             return False
-        for m in self.model.modules():
-            p = getattr(m, "p", None) if isinstance(m, torch.nn.Dropout) else getattr(m, "dropout", None)
-            if isinstance(p, (int, float)) and p > 0:
-                return False
         return len(self._get_sampler()) > 0
 
     def _capture_step(self, adj, total):

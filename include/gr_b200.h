@@ -166,12 +166,15 @@ int gr_peer_scatter_rows(const float *src, int64_t lds, int64_t n_rows, int32_t 
 int gr_rowmap_f32(const float *x1, int64_t ld1, const float *wa, const float *bias_a, const float *x2, int64_t ld2,
                   const float *x3, int64_t ld3, const float *wb, const float *bias_b, const float *resid,
                   int64_t ldr, float alpha, float beta, int32_t act, float slope, int64_t n_rows, int32_t d_in,
-                  int32_t d_out, float drop_p, uint64_t drop_seed, float *out, int64_t ldo, void *stream);
+                  int32_t d_out, float drop_p, uint64_t drop_seed, const uint64_t *drop_seed_dev, float *out, int64_t ldo,
+                  void *stream);
 
 /* Backward of gr_rowmap_f32 — replaces what autograd runs under loss.backward() (src/training/trainer.py:270)
  * for NGCFLayer.forward (ngcf.py:69-84), the Group-and-Shuffle maps (model.py:176-195) and the GAT head
  * projections (gat.py:99).  With drop_p > 0 the forward output is  D * (alpha*act(z) + beta*R),  D = keep/(1-p)
  * re-derived from drop_seed (the layer-output nn.Dropout of ngcf.py:86 / model.py:198-199 fused).
+ * drop_seed_dev (optional DEVICE uint64, here and in gr_rowmap_f32 / gr_gat_aggregate / gr_gat_bwd): added to
+ * drop_seed at run time, so a training step captured once in a CUDA graph draws a new mask on every replay.
  * Given g = dL/dout [n, d_out]:
  *     dz = alpha * D*g * act'(z)   (act' recovered from `out`, required when act != 0)
  *     dx1 = dz Wa^T;  dP = dz Wb^T;  dx2 = dP*X3;  dx3 = dP*X2;  dresid = beta * D*g
@@ -183,7 +186,8 @@ size_t gr_rowmap_bwd_workspace_bytes(int64_t n_rows, int32_t d_in, int32_t d_out
 int gr_rowmap_bwd(const float *g, int64_t ldg, const float *out, int64_t ldo, const float *x1, int64_t ld1,
                   const float *wa, const float *x2, int64_t ld2, const float *x3, int64_t ld3, const float *wb,
                   const float *resid, int64_t ldr, float alpha, float beta, int32_t act, float slope,
-                  int64_t n_rows, int32_t d_in, int32_t d_out, float drop_p, uint64_t drop_seed, float *dx1,
+                  int64_t n_rows, int32_t d_in, int32_t d_out, float drop_p, uint64_t drop_seed,
+                  const uint64_t *drop_seed_dev, float *dx1,
                   int64_t ldd1, float *dx2, int64_t ldd2, float *dx3, int64_t ldd3, float *dresid, int64_t lddr,
                   float *dw, void *workspace, size_t workspace_bytes, void *stream);
 
@@ -234,7 +238,7 @@ int gr_gat_node_scores(const float *h, int64_t ldh, const float *a_self, const f
 size_t gr_gat_aggregate_workspace_bytes(int32_t n_seg, int32_t heads, int32_t dh);
 int gr_gat_aggregate(const int32_t *indptr, const int32_t *indices, int64_t n_rows, const float *h, int64_t ldh,
                      const float *s, const float *t, int32_t heads, int32_t dh, float slope, int32_t mean_heads,
-                     int32_t elu, float drop_p, uint64_t drop_seed, int64_t n_cols,
+                     int32_t elu, float drop_p, uint64_t drop_seed, const uint64_t *drop_seed_dev, int64_t n_cols,
                      const gr_gat_segments *segs_host, float *out, int64_t ldo, float *m_out, float *z_out,
                      void *workspace, size_t workspace_bytes, void *stream);
 
@@ -253,7 +257,7 @@ int gr_gat_bwd(const int32_t *indptr, const int32_t *indices, const int32_t *t_i
                int64_t n_rows, int64_t n_cols, const float *h, int64_t ldh, const float *s, const float *t,
                const float *m, const float *z, const float *out, int64_t ldo, const float *dout, int64_t lddo,
                const float *a_self, const float *a_neigh, int32_t heads, int32_t dh, float slope,
-               int32_t mean_heads, int32_t elu, float drop_p, uint64_t drop_seed,
+               int32_t mean_heads, int32_t elu, float drop_p, uint64_t drop_seed, const uint64_t *drop_seed_dev,
                const gr_gat_segments *row_segs_host, const gr_gat_segments *col_segs_host, float *dH, float *da,
                void *workspace, size_t workspace_bytes, void *stream);
 

@@ -1,5 +1,7 @@
 """GPU parity of the NGCF / GAT / Group-and-Shuffle drop-ins against the reference's golden
 forward outputs and autograd gradients (eval() mode: dropout is the identity), 1e-5 relative."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -205,7 +207,7 @@ def _gat_setup(tiny, heads, dh, d_in, seed=0):
     return csr, n, x, ws, a_s, a_n, gen
 
 
-@pytest.mark.parametrize("seg_len", [128, 8])
+@pytest.mark.parametrize("seg_len", [4096, 8])
 @pytest.mark.parametrize("heads,dh,concat,elu,drop", [(4, 16, True, True, 0.0), (4, 64, False, True, 0.0),
                                                        (4, 16, True, True, 0.1), (4, 64, False, False, 0.3),
                                                        (1, 64, True, False, 0.0), (8, 8, True, True, 0.2)])
@@ -213,13 +215,13 @@ def test_gat_layer_forward_backward_vs_torch_autograd(tiny, heads, dh, concat, e
     """gr_gat_aggregate (+ attention dropout at gat.py:138's position) and gr_gat_bwd against float64 autograd of
     the edge-list restatement with the same per-edge mask: output, dx, dW of every head, d a_self, d a_neigh.
     seg_len = 8 cuts most rows of the tiny graph into segments (the hot-row path: partial online-softmax
-    triples / partial sums + combine kernels); 128 leaves every row to one warp."""
+    triples / partial sums + combine kernels); 4096 leaves every row to one warp."""
     import sys
     from gnn_recommendations_b200.layer_ops import gat_layer
     from _torch_refs import gat_drop_mask, gat_layer_torch
     monkeypatch.setattr(sys.modules[g.NormAdjCSR.__module__], "GAT_SEG_LEN", seg_len)
     csr, n, x, ws, a_s, a_n, gen = _gat_setup(tiny, heads, dh, 64)
-    assert (csr.gat_segments()[1] > 0) == (seg_len == 8)
+    assert (csr.gat_segments()[1] > 0) == (seg_len == 8)       # tiny graph: max degree ~300
     leaves = [x] + ws + a_s + a_n
     for t in leaves:
         t.requires_grad_(True)
@@ -447,3 +449,50 @@ def test_full_size_model_families_vs_oracle(case):
     for r, c in zip(*np.nonzero(~same)):
         a, b = so[r, want_ref[r, c]], so[r, want_own[r, c]]
         assert abs(a - b) <= 1e-4 * max(abs(a), abs(b), 1e-12), (case, r, c, a, b)
+
+
+def test_dropout_seed_from_device_memory_equals_host_seed(tiny):
+    """CUDA-graph replays refresh the dropout seed in DEVICE memory (layer_ops.DropSeed.dev): the kernels must
+    draw the mask of host seed (value + device word), forward and backward, for the rowmap epilogue and the GAT
+    attention dropout alike."""
+    from gnn_recommendations_b200.layer_ops import DropSeed, gat_layer, rowmap
+    gen = torch.Generator().manual_seed(0)
+    x = torch.randn(300, 64, generator=gen).to(DEV).requires_grad_(True)
+    w = (torch.randn(64, 64, generator=gen) * 0.2).to(DEV).requires_grad_(True)
+    word = torch.tensor([123456789], dtype=torch.int64, device=DEV)
+    a = rowmap(x, w, act=1, slope=0.2, drop_p=0.3, drop_seed=DropSeed(1000, word))
+    b = rowmap(x, w, act=1, slope=0.2, drop_p=0.3, drop_seed=1000 + 123456789)
+    assert torch.equal(a, b) and float((a == 0).float().mean()) > 0.2
+    ga = torch.autograd.grad(a.sum(), [x, w])
+    gb = torch.autograd.grad(b.sum(), [x, w])
+    assert all(torch.equal(p, q) for p, q in zip(ga, gb))
+    word += 1                                                         # what the Trainer does before the next replay
+    assert not torch.equal(rowmap(x, w, act=1, slope=0.2, drop_p=0.3, drop_seed=DropSeed(1000, word)), b)
+    csr, n, xg, ws, a_s, a_n, _ = _gat_setup(tiny, 4, 16, 64)
+    xg.requires_grad_(True)
+    word.fill_(77)
+    o1 = gat_layer(csr, xg, ws, a_s, a_n, 0.2, True, True, drop_p=0.2, drop_seed=DropSeed(5, word))
+    o2 = gat_layer(csr, xg, ws, a_s, a_n, 0.2, True, True, drop_p=0.2, drop_seed=82)
+    assert torch.equal(o1, o2)
+    assert torch.equal(torch.autograd.grad(o1.sum(), [xg])[0], torch.autograd.grad(o2.sum(), [xg])[0])
+
+
+def test_cuda_graph_step_with_dropout_models(tiny, tmp_path):
+    """NGCF / GAT with their default dropout 0.1 train through the captured step (seeds from device memory):
+    the graph is used, losses stay finite and the same torch seed reproduces the same run."""
+    import sys
+    sys.path.insert(0, os.path.dirname(__file__))
+    from test_gpu_train_eval import CFG, dataset_from
+    nu, ni = int(tiny["n_users"]), int(tiny["n_items"])
+    for make in (lambda: g.NGCF(nu, ni, 64, [64, 64], 0.1, 0.1), lambda: g.GAT(nu, ni, 64, 2, 4, 0.1, 0.2, 0.1)):
+        runs = []
+        for rep in range(2):
+            torch.manual_seed(42)
+            m = make()
+            tr = g.Trainer(m, dataset_from(tiny), dict(CFG, checkpoint_dir=str(tmp_path / "c")), device=torch.device(DEV))
+            torch.manual_seed(7)
+            loss = tr.train_steps(30)
+            assert getattr(tr, "_graph", None) is not None and np.isfinite(loss)
+            runs.append((loss, m.user_embedding.weight.detach().cpu().clone()))
+        assert abs(runs[0][0] - runs[1][0]) <= 1e-6 * abs(runs[0][0])
+        torch.testing.assert_close(runs[0][1], runs[1][1], rtol=1e-4, atol=1e-6)
