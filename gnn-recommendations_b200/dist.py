@@ -480,3 +480,261 @@ class ShardedLightGCN:
 
     def gathered_weight(self) -> torch.Tensor:
         return gather_rows(self.part, self.rank, self.weight.detach(), self.group)
+
+
+# ------------------------------------------------------------------------------------------------
+# user-owner ("1.5-D") propagation: item rows as reduced partial sums  (SURVEY.md §8e bipartite refinement)
+# ------------------------------------------------------------------------------------------------
+class BipartitePartition:
+    """Users are OWNED by ranks (cyclically: user u lives on rank u % G as local row u // G; its embedding row
+    never leaves the rank), items are replicated: every rank holds the full item table of the current layer.
+
+    Why: in the exact row partition every rank must receive every row of every layer — (G-1)/G x N x 4d bytes
+    of NVLink egress per rank and layer, 11.2 GB at C5 on 8 GPUs against 9.8 ms of SpMM.  But a user row only
+    reads ITEM columns and an item row only USER columns.  So a rank can (1) advance its own users from the
+    replicated item table with no communication, and (2) compute, for ALL items, the partial sum over the users
+    it owns; the partials are then reduced per item block (rank r owns items [r*Ib, (r+1)*Ib) for the reduction)
+    and the reduced block is broadcast: 2 x (G-1)/G x I x 4d bytes per rank and layer (4.5 GB at C5), in opposite
+    NVLink directions, overlapped with step (1) of the same layer.
+
+    An item row is then  sum_g (chain over rank g's users, ascending)  added in rank order — deterministic and
+    reproducible, but not the single ascending chain of the 1-GPU kernel: ~1e-7 relative (BASELINE north_star
+    asks 1e-5 for embeddings).  The exact all-gather partition (RowPartition) remains the bit-exact mode."""
+
+    def __init__(self, n_users: int, n_items: int, world_size: int):
+        self.n_users, self.n_items, self.world_size = int(n_users), int(n_items), int(world_size)
+        G = self.world_size
+        self.user_rows = max(4, (-(-self.n_users // G) + 3) // 4 * 4)        # padded local user height
+        self.item_block = max(4, (-(-self.n_items // G) + 3) // 4 * 4)       # Ib
+        self.items_padded = self.item_block * G
+
+    def n_users_local(self, rank: int) -> int:
+        return len(range(rank, self.n_users, self.world_size))
+
+    def item_range(self, rank: int):
+        lo = min(self.n_items, rank * self.item_block)
+        return lo, min(self.n_items, lo + self.item_block)
+
+    def take_users(self, x_users: torch.Tensor, rank: int) -> torch.Tensor:
+        return x_users[rank::self.world_size].contiguous()
+
+    def local_csrs(self, full: NormAdjCSR, rank: int):
+        """(A_u, A_i) cut out of the full [N, N] matrix (users first):
+        A_u [n_users_local, items_padded]: this rank's user rows, columns = item index;
+        A_i [items_padded, n_users_local]: ALL item rows restricted to this rank's users, columns = local user row.
+        Entry order inside a row stays ascending (the chain order within a rank)."""
+        G, U, dev = self.world_size, self.n_users, full.indptr.device
+        ip = full.indptr.long()
+        # ---- A_u: rows rank, rank+G, ... of the user block
+        rows = torch.arange(rank, U, G, device=dev)
+        starts, counts = ip[rows], ip[rows + 1] - ip[rows]
+        uptr = torch.zeros(rows.numel() + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(counts, 0, out=uptr[1:])
+        total = int(uptr[-1].item())
+        src = torch.repeat_interleave(starts - uptr[:-1], counts) + torch.arange(total, device=dev)
+        a_u = NormAdjCSR(uptr.to(torch.int32), (full.indices[src].long() - U).to(torch.int32).contiguous(),
+                         full.vals[src].contiguous(), int(rows.numel()), self.items_padded,
+                         long_threshold=full.long_threshold)
+        # ---- A_i: item rows, entries whose column (a user) belongs to this rank
+        lo = int(ip[U].item())
+        seg_cols = full.indices[lo:].long()
+        mine = (seg_cols % G) == rank
+        csum = torch.zeros(seg_cols.numel() + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(mine, 0, out=csum[1:])
+        iptr = torch.zeros(self.items_padded + 1, dtype=torch.int64, device=dev)
+        iptr[: self.n_items + 1] = csum[ip[U:] - lo]
+        iptr[self.n_items + 1:] = iptr[self.n_items]
+        a_i = NormAdjCSR(iptr.to(torch.int32), (seg_cols[mine] // G).to(torch.int32).contiguous(),
+                         full.vals[lo:][mine].contiguous(), self.items_padded, self.n_users_local(rank),
+                         long_threshold=full.long_threshold)
+        return a_u, a_i
+
+
+class ItemExchange:
+    """Peer-mapped buffers of the 1.5-D propagation: two full item tables T[2] [items_padded, d] (layer parity)
+    and one partial buffer P [items_padded, d] per rank, allocated with torch's symmetric-memory allocator so every
+    rank can load peers' partials and store into peers' tables over NVLink."""
+
+    def __init__(self, part: BipartitePartition, d: int, device, group=None):
+        import ctypes
+
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        self.part, self.d = part, d
+
+        def alloc():
+            t = symm_mem.empty((part.items_padded, d), dtype=torch.float32, device=device)
+            h = symm_mem.rendezvous(t, self.group)
+            t.zero_()
+            return t, h, (ctypes.c_void_p * self.world)(*[int(p) for p in h.buffer_ptrs])
+
+        self.tables, self.table_ptrs, self.handles = [], [], []
+        for _ in range(2):
+            t, h, arr = alloc()
+            self.tables.append(t)
+            self.table_ptrs.append(arr)
+            self.handles.append(h)
+        self.partial, self.partial_handle, self.partial_ptrs = alloc()
+        self.comm_stream = torch.cuda.Stream(device)
+        torch.cuda.synchronize(device)
+        dist.barrier(self.group)
+
+    def barrier(self):
+        self.partial_handle.barrier()
+
+
+class EmulatedItemExchange:
+    """The same buffers for G ranks emulated on ONE device (tests): plain tensors, pointer tables over them."""
+
+    def __init__(self, part: BipartitePartition, d: int, device):
+        import ctypes
+
+        G = part.world_size
+        self.world, self.part, self.d = G, part, d
+        self._tables = [[torch.zeros((part.items_padded, d), device=device) for _ in range(G)] for _ in range(2)]
+        self._partials = [torch.zeros((part.items_padded, d), device=device) for _ in range(G)]
+        self.table_ptrs = [(ctypes.c_void_p * G)(*[t.data_ptr() for t in self._tables[k]]) for k in range(2)]
+        self.partial_ptrs = (ctypes.c_void_p * G)(*[t.data_ptr() for t in self._partials])
+        self.comm_stream = None
+
+    def view(self, rank: int):
+        ex = EmulatedItemExchange.__new__(EmulatedItemExchange)
+        ex.__dict__.update(self.__dict__)
+        ex.rank = rank
+        ex.tables = [self._tables[0][rank], self._tables[1][rank]]
+        ex.partial = self._partials[rank]
+        return ex
+
+    def barrier(self):
+        pass
+
+
+def _reduce_bcast(ex, row0: int, n_rows: int, d: int, dst_ptrs, n_dst: int, addend, out, scale: float, mode: int):
+    from ._lib import check, lib, ptr, stream_ptr
+
+    with torch.cuda.device(ex.partial.device):
+        check(lib().gr_reduce_bcast_rows(ex.partial_ptrs, ex.world, d, dst_ptrs, n_dst, d, row0, n_rows, d,
+                                         ptr(addend), addend.stride(0) if addend is not None else 0, ptr(out),
+                                         out.stride(0) if out is not None else 0, None, 0, float(scale), int(mode),
+                                         stream_ptr()), "gr_reduce_bcast_rows")
+
+
+def _propagate_user_owner_steps(a_u: NormAdjCSR, a_i: NormAdjCSR, ex, xu0: torch.Tensor, xi0_block: torch.Tensor,
+                                n_layers: int, result: dict):
+    """Generator: one rank's LightGCN propagation in the user-owner layout; yields at every point where all
+    ranks must have arrived (cross-rank barrier).  ``xu0`` [n_users_local, d]: the rank's user rows;
+    ``xi0_block`` [item block rows, d]: the rank's block of the item table.  result['users'] / ['items'] receive
+    mean_l of the rank's user rows / item block."""
+    from ._lib import check, lib, ptr, stream_ptr
+
+    part, d, rank, G = ex.part, xu0.shape[1], ex.rank, ex.world
+    lo, hi = part.item_range(rank)
+    nb = hi - lo
+    L = n_layers
+    if L == 0:
+        result["users"], result["items"] = xu0.clone(), xi0_block[:nb].clone()
+        return
+    dev = xu0.device
+    # layer-0 item table: every rank broadcasts its block (peer stores)
+    yield "enter"                                            # nobody still reads T[0] / P from a previous call
+    cur = 0
+    if nb > 0:
+        with torch.cuda.device(dev):
+            check(lib().gr_peer_scatter_rows(ptr(xi0_block), xi0_block.stride(0), nb, d, ex.table_ptrs[cur], G, 0, d, lo,
+                                             stream_ptr()), "gr_peer_scatter_rows")
+    yield "table0"
+    acc_u = torch.empty_like(xu0)
+    out_u = torch.empty_like(xu0)
+    acc_i = torch.empty((max(nb, 1), d), dtype=torch.float32, device=dev)
+    out_i = torch.empty((max(nb, 1), d), dtype=torch.float32, device=dev)
+    xu = xu0
+    xu_next = [torch.empty_like(xu0), torch.empty_like(xu0)]
+    main = torch.cuda.current_stream(dev)
+    for l in range(L):
+        last = l == L - 1
+        nxt = cur ^ 1
+        # (2) partial sums of ALL item rows over this rank's users  ->  P_rank
+        a_i.spmm(xu, y=ex.partial, want_y=True)
+        yield "partials"                                     # every rank's P is complete
+        # (3) reduce my item block over the ranks' partials, broadcast it into every T[nxt], fold into the layer sum
+        side = ex.comm_stream
+        if side is not None:
+            side.wait_stream(main)
+        ctx = torch.cuda.stream(side) if side is not None else _NullCtx()
+        with ctx:
+            if nb > 0:
+                addend = xi0_block if l == 0 else acc_i
+                if last:
+                    _reduce_bcast(ex, lo, nb, d, None, 0, addend, out_i, float(L + 1), _lib.GR_SCALE_DIV)
+                else:
+                    _reduce_bcast(ex, lo, nb, d, ex.table_ptrs[nxt], G, addend, acc_i, 1.0, _lib.GR_SCALE_NONE)
+        # (1) this rank's users from the replicated item table of layer l — overlaps (3)
+        addend_u = xu0 if l == 0 else acc_u
+        if last:
+            a_u.spmm(ex.tables[cur], addend=addend_u, out=out_u, scale=float(L + 1), scale_mode=_lib.GR_SCALE_DIV,
+                     want_y=False)
+        else:
+            a_u.spmm(ex.tables[cur], y=xu_next[l & 1], addend=addend_u, out=acc_u)
+            xu = xu_next[l & 1]
+        if side is not None:
+            main.wait_stream(side)
+        if not last:
+            yield "table"                                    # every rank's stores into T[nxt] have landed
+            cur = nxt
+    result["users"], result["items"] = out_u, out_i[:nb]
+
+
+class _NullCtx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+def lightgcn_propagate_user_owner(a_u: NormAdjCSR, a_i: NormAdjCSR, ex, xu0: torch.Tensor, xi0_block: torch.Tensor,
+                                  n_layers: int):
+    """-> (users_local [n_users_local, d], items_block [block rows, d]) = mean_{l<=L} of the propagated rows."""
+    res = {}
+    for _ in _propagate_user_owner_steps(a_u, a_i, ex, xu0, xi0_block, n_layers, res):
+        ex.barrier()
+    return res["users"], res["items"]
+
+
+def emulate_user_owner(full: NormAdjCSR, n_users: int, n_items: int, x0: torch.Tensor, n_layers: int, world: int):
+    """All G ranks of the user-owner propagation on ONE device, advanced in lockstep between barriers (tests and
+    single-GPU validation).  Returns the assembled [N, d] result in natural row order."""
+    part = BipartitePartition(n_users, n_items, world)
+    d = x0.shape[1]
+    shared = EmulatedItemExchange(part, d, x0.device)
+    gens, results = [], []
+    for r in range(world):
+        a_u, a_i = part.local_csrs(full, r)
+        lo, hi = part.item_range(r)
+        blk = torch.zeros((part.item_block, d), device=x0.device)
+        blk[: hi - lo] = x0[n_users + lo: n_users + hi]
+        res = {}
+        results.append(res)
+        gens.append(_propagate_user_owner_steps(a_u, a_i, shared.view(r), part.take_users(x0[:n_users], r), blk,
+                                                n_layers, res))
+    live = list(range(world))
+    while live:
+        nxt = []
+        for r in live:
+            try:
+                next(gens[r])
+                nxt.append(r)
+            except StopIteration:
+                pass
+        torch.cuda.synchronize(x0.device)
+        live = nxt
+    out = torch.empty_like(x0)
+    for r in range(world):
+        out[r:n_users:world] = results[r]["users"]
+        lo, hi = part.item_range(r)
+        out[n_users + lo: n_users + hi] = results[r]["items"]
+    return out

@@ -44,7 +44,12 @@ class device_dropout_seeds:
         _SEED_STATE["dev"], _SEED_STATE["count"] = self.dev, 0
         return self
 
+    def drawn(self) -> int:
+        """Number of seeds handed out inside the context so far."""
+        return _SEED_STATE["count"] if _SEED_STATE["dev"] is self.dev else self._count
+
     def __exit__(self, *a):
+        self._count = _SEED_STATE["count"]
         _SEED_STATE.update(self.prev)
         return False
 

@@ -57,13 +57,17 @@ class _GraphStep:
         model, opt = tr.model, tr.optimizer
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph, stream=torch.cuda.current_stream(dev)), device_dropout_seeds(self.seed):
+        with torch.cuda.graph(self.graph, stream=torch.cuda.current_stream(dev)), \
+                device_dropout_seeds(self.seed) as seeds:
             x = tr._propagated(adj)
             loss = bpr_fused(x, model.n_users, self.idx[0], self.idx[1], self.idx[2].view(-1, 1))
             opt.zero_grad()
             loss.backward()
             fused_clip_adam_step(opt, tr.max_grad_norm, step_scalars_dev=self.sc)
             total += loss.detach().double()
+            # did the step ask for dropout seeds?  Only then is the CPU generator consumed per step (a model
+            # without active dropout must leave the sampler's mt19937 stream exactly as the reference does)
+            self.uses_seed = seeds.drawn() > 0
 
     def valid_for(self, adj) -> bool:
         tr = self.tr
@@ -78,7 +82,8 @@ class _GraphStep:
         if self.used[k]:
             ev.synchronize()                         # the copy that last read this staging slot has run
         tr._get_sampler().sample(tr.batch_size, out=self.views[k])
-        idx_h[3 * self.b] = new_dropout_seed().value           # one draw of the CPU generator per step
+        if self.uses_seed:
+            idx_h[3 * self.b] = new_dropout_seed().value       # one draw of the CPU generator per step
         step_size, bc2 = self._scalars(tr.optimizer)          # advances the optimizer's step counters
         sc_h[0], sc_h[1] = step_size, bc2
         self.flat.copy_(idx_h, non_blocking=True)

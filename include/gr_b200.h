@@ -154,6 +154,18 @@ int gr_peer_scatter_rows(const float *src, int64_t lds, int64_t n_rows, int32_t 
                          int32_t n_peers, int32_t peer_multicast, int64_t ldd, int64_t peer_row_offset,
                          void *stream);
 
+/* Reduce + broadcast of partial item rows over NVLink peer memory: the exchange of the user-owner ("1.5-D")
+ * multi-GPU propagation (SURVEY.md §8e "bipartite refinement"; no reference counterpart).  Every rank holds
+ * partial sums of ALL item rows computed from the users it owns; for the rows [row0, row0 + n_rows) of its block
+ * this call forms  v[j] = ((P_0[j] + P_1[j]) + ...)  over the n_src partial buffers (HOST array of DEVICE
+ * pointers, peer-mapped; fixed order = deterministic), stores v into row j of the n_dst item tables (peer
+ * stores; n_dst = 0 on the last layer), optionally into `own` [n_rows, ldw] and into the running layer sum
+ *   out[j - row0] = scale_op(addend[j - row0] + v[j])   (same scale modes as gr_spmm_csr_f32). */
+int gr_reduce_bcast_rows(const float *const *src_host, int32_t n_src, int64_t ld_src, float *const *dst_host,
+                         int32_t n_dst, int64_t ld_dst, int64_t row0, int64_t n_rows, int32_t d,
+                         const float *addend, int64_t lda, float *out, int64_t ldo, float *own, int64_t ldw,
+                         float scale, int32_t scale_mode, void *stream);
+
 /* Per-row dense epilogue shared by the NGCF, Group-and-Shuffle and GAT layers:
  *     out = alpha * act( X1 Wa + bias_a  +  (X2 * X3) Wb + bias_b ) + beta * R
  * Wa, Wb: [d_in, d_out] row-major (i.e. nn.Linear.weight TRANSPOSED); the (X2*X3) term, the

@@ -402,3 +402,34 @@ def test_spmm_two_streams_concurrently_share_no_state():
     assert len(csr_a._sched) >= 3                                       # default + two streams: separate words
     for ya, yb, yb2 in outs:
         assert torch.equal(ya, want_a) and torch.equal(yb, want_b) and torch.equal(yb2, want_a)
+
+
+# ----------------------------------------------------------------------------- user-owner (1.5-D) propagation
+@pytest.mark.parametrize("shape,world,d,L", [("tiny", 2, 64, 3), ("tiny", 3, 32, 2), ("tiny", 8, 128, 4), ("C1", 4, 64, 3),
+                                             ("C1", 8, 128, 1)])
+def test_user_owner_propagation_matches_single_gpu(shape, world, d, L):
+    """The 1.5-D multi-GPU mode (dist.BipartitePartition: users owned by ranks, item rows = partial sums reduced
+    and broadcast by gr_reduce_bcast_rows), all ranks emulated on one GPU in lockstep: equal to the single-GPU
+    propagation within BASELINE's 1e-5 (item rows are per-rank chains added in rank order, not the single chain),
+    user rows of a 1-layer propagation bit-identical, and deterministic (two runs bit-equal)."""
+    from gnn_recommendations_b200.dist import BipartitePartition, emulate_user_owner
+    from gnn_recommendations_b200.synthetic import synth_split
+    sp = synth_split(shape, 42)
+    nu, ni = sp["n_users"], sp["n_items"]
+    full = g.NormAdjCSR.from_pairs(*sp["train"], nu, ni, device=DEV)
+    x0 = (torch.randn(nu + ni, d, generator=torch.Generator().manual_seed(3)) * 0.1).to(DEV)
+    want = g.lightgcn_propagate(full, x0, L)
+    got = emulate_user_owner(full, nu, ni, x0, L, world)
+    scale = float(want.abs().max())
+    assert float((got - want).abs().max()) <= 1e-5 * scale
+    assert torch.equal(got, emulate_user_owner(full, nu, ni, x0, L, world))
+    if L == 1:      # user rows read the exact layer-0 item table: the very same chain as on one GPU
+        assert torch.equal(got[:nu], want[:nu])
+    # the partition covers every entry exactly once
+    part = BipartitePartition(nu, ni, world)
+    nnz = 0
+    for r in range(world):
+        a_u, a_i = part.local_csrs(full, r)
+        assert a_u.nnz == a_i.nnz                                          # each owned edge: once per direction
+        nnz += a_u.nnz + a_i.nnz
+    assert nnz == full.nnz
