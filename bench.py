@@ -175,13 +175,18 @@ def reference_config(name, sample, n_gpus):
     return cfg
 
 
-def workload_config(name, n_gpus):
+def workload_config(name, n_gpus, mode="rows"):
     nu, ni, e, d, L = WORKLOADS[name]
     return {"workload": f"{name}: LightGCN {L}-layer d={d} fp32 propagation, synthetic power-law graph "
                         f"{nu} users x {ni} items, {e} edges (nnz(A_hat)={2 * e})",
-            "partition": "single GPU" if n_gpus == 1 else f"rows distributed cyclically over {n_gpus} ranks; layer rows "
-                                                           "exchanged by P2P stores from the SpMM epilogue (fused "
-                                                           "all-gather) or NCCL all-gather (--nccl-allgather)",
+            "partition": "single GPU" if n_gpus == 1 else (
+                f"user-owner (1.5-D) over {n_gpus} ranks: users owned cyclically (their rows never leave the rank), every "
+                "rank computes partial sums of ALL item rows from its users; partials reduced per item block and the "
+                "block broadcast over NVLink peer memory (gr_reduce_bcast_rows), overlapped with the user-row SpMM; "
+                "embeddings equal the 1-GPU result to 1e-5 (--partition rows = the bit-exact all-gather mode)"
+                if mode == "user-owner" else
+                f"rows distributed cyclically over {n_gpus} ranks; layer rows exchanged by P2P stores from the SpMM "
+                "epilogue (fused all-gather) or NCCL all-gather (--nccl-allgather); bit-identical to 1 GPU"),
             "l2": f"inputs larger than L2 (table {(nu + ni) * d * 4 / 1e9:.2f} GB, CSR {2 * e * 8 / 1e9:.2f} GB)"
             if (nu + ni) * d * 4 + 2 * e * 8 > 2 * 126e6 else "L2 flushed between iterations (256 MB write)"}
 
@@ -222,23 +227,40 @@ def run_b200(args):
     t_setup = time.perf_counter() - t_setup
 
     gen = torch.Generator(device=dev).manual_seed(1234)
+    exchange = part = x0_local = None
+    mode = "single"
     if world == 1:
         with torch.device(dev):
             model = g.LightGCN(nu, ni, embedding_dim=d, n_layers=L, init_scale=0.1)
-        csr = full
+        graphs = [full]
 
-        def step():
+        def propagate_on(gs):
             with torch.no_grad():
-                return model.get_all_embeddings(csr)
-        n_rows_local = n
+                return [model.propagate(gs[0])]
+    elif args.partition == "user-owner":
+        # users owned by ranks, item rows as reduced partial sums (1.5-D; 1e-5 parity, see dist.BipartitePartition)
+        from gnn_recommendations_b200.dist import BipartitePartition, ItemExchange, lightgcn_propagate_user_owner
+
+        mode = "user-owner"
+        part = BipartitePartition(nu, ni, world)
+        graphs = list(part.local_csrs(full, rank))
+        del full
+        torch.cuda.empty_cache()
+        exchange = ItemExchange(part, d, dev)
+        xu0 = torch.randn(part.n_users_local(rank), d, device=dev, generator=gen) * 0.1
+        lo_i, hi_i = part.item_range(rank)
+        xi0 = torch.randn(part.item_block, d, device=dev, generator=gen) * 0.1
+
+        def propagate_on(gs):
+            return list(lightgcn_propagate_user_owner(gs[0], gs[1], exchange, xu0, xi0, L))
     else:
+        mode = "rows"
         part = RowPartition(full.indptr, world)
-        csr = part.local_csr(full, rank)
+        graphs = [part.local_csr(full, rank)]
         n_loc = part.n_local(rank)
         del full
         torch.cuda.empty_cache()
         x0_local = torch.randn(n_loc, d, device=dev, generator=gen) * 0.1
-        exchange = None
         if not args.nccl_allgather:
             try:
                 from gnn_recommendations_b200.dist import PeerExchange, lightgcn_propagate_fused
@@ -253,11 +275,13 @@ def run_b200(args):
         if int(ok.item()) == 0:
             exchange = None
 
-        def step():
+        def propagate_on(gs):
             if exchange is not None:
-                return lightgcn_propagate_fused(csr, exchange, x0_local, L)
-            return lightgcn_propagate_sharded(csr, part, rank, x0_local, L)
-        n_rows_local = n_loc
+                return [lightgcn_propagate_fused(gs[0], exchange, x0_local, L)]
+            return [lightgcn_propagate_sharded(gs[0], part, rank, x0_local, L)]
+
+    def step():
+        return propagate_on(graphs)
 
     def barrier():
         if world > 1:
@@ -297,31 +321,33 @@ def run_b200(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()) / steps
 
-    n_long = int(csr.n_long)
+    n_long = int(sum(c.n_long for c in graphs))
     # ---- value: inputs resident in HBM -------------------------------------------------------
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    csr.timings = None
+    for c in graphs:
+        c.timings = None
     for _ in range(args.warmup):
         step()
-    csr.timings = []
-    launches0 = csr.launches
+    for c in graphs:
+        c.timings = []
+    launches0 = sum(c.launches for c in graphs)
     ms_step = timed(step, args.steps, 0, sampler)
-    launches = csr.launches - launches0
+    launches = sum(c.launches for c in graphs) - launches0
     torch.cuda.synchronize()
-    kernel_ms = [a.elapsed_time(b) for a, b in csr.timings]
-    csr.timings = None
+    kernel_ms, b_alg_total = [], 0.0
+    for c in graphs:
+        t_c = [a.elapsed_time(b) for a, b in c.timings]
+        kernel_ms += t_c
+        b_alg_total += len(t_c) * alg_bytes_per_layer(c.nnz, c.n_rows, d)
+        c.timings = None
     value = L * nnz / (ms_step * 1e-3)
 
-    # ---- roofline of the dominant kernel (one SpMM launch = one layer on this rank's rows) -----
+    # ---- roofline of the dominant kernel (gr_spmm_csr_f32 launches on this rank's row blocks) -----
     hbm_peak, peak_src = peaks()
-    b_alg = alg_bytes_per_layer(csr.nnz, n_rows_local, d)
+    b_alg = b_alg_total / max(1, len(kernel_ms))
     avg_kernel_ms = float(np.mean(kernel_ms))
     achieved = b_alg / (avg_kernel_ms * 1e-3) / 1e9
-    traffic = None
-    tpath = os.path.join(REPO, "profiles", "roofline_traffic.json")
-    if os.path.exists(tpath):
-        with open(tpath) as f:
-            traffic = json.load(f).get(f"{args.workload}@{world}")
+    traffic = _traffic(f"{args.workload}@{world}")
     roofline = {"bound": "hbm", "kernel": f"gr_spmm_csr_f32 (spmm_stream_rows<{d}> + spmm_long_rows<{d}>)",
                 "achieved": achieved, "peak": hbm_peak, "peak_source": peak_src, "unit": "GB/s",
                 "frac": achieved / hbm_peak, "traffic": traffic, "algorithmic_bytes_per_launch": b_alg,
@@ -334,28 +360,26 @@ def run_b200(args):
     # Same schedule at every N (each rank moves its own row block and its own output rows).
     e2e = None
     if not args.no_e2e:
-        ip_h, ix_h, vl_h = csr.to_host(pin=True)
-        out_host = torch.empty((n_rows_local, d), dtype=torch.float32, pin_memory=True)
-        n_cols, thr = csr.n_cols, csr.long_threshold
-        h2d_bytes = int(ip_h.numel() * 4 + ix_h.numel() * 4 + vl_h.numel() * 4)
+        host = [c.to_host(pin=True) for c in graphs]
+        meta = [(c.n_rows, c.n_cols, c.long_threshold) for c in graphs]
+        outs0 = step()
+        out_host = [torch.empty(tuple(o.shape), dtype=torch.float32, pin_memory=True) for o in outs0]
+        del outs0
+        h2d_bytes = int(sum(t.numel() * 4 for h in host for t in h))
+        d2h_bytes = int(sum(o.numel() * 4 for o in out_host))
         torch.cuda.empty_cache()
 
-        def propagate_on(loc):
-            if world == 1:
-                with torch.no_grad():
-                    return model.propagate(loc)
-            return (lightgcn_propagate_fused(loc, exchange, x0_local, L) if exchange is not None
-                    else lightgcn_propagate_sharded(loc, part, rank, x0_local, L))
+        def rebuild(dev_arrays):
+            return [g.NormAdjCSR(ip, ix, vl, m[0], m[1], symmetric=True, long_threshold=m[2])
+                    for (ip, ix, vl), m in zip(dev_arrays, meta)]
 
         def e2e_step():
-            loc = g.NormAdjCSR(ip_h.to(dev, non_blocking=True), ix_h.to(dev, non_blocking=True),
-                               vl_h.to(dev, non_blocking=True), n_rows_local, n_cols, symmetric=True,
-                               long_threshold=thr)
-            with torch.no_grad():
-                out = propagate_on(loc)
-            out_host.copy_(out, non_blocking=True)
+            gs = rebuild([tuple(t.to(dev, non_blocking=True) for t in h) for h in host])
+            outs = propagate_on(gs)
+            for oh, o in zip(out_host, outs):
+                oh.copy_(o, non_blocking=True)
             torch.cuda.current_stream().synchronize()
-            return float(out_host[0, 0])
+            return float(out_host[0][0, 0])
 
         ms_serial = timed(e2e_step, args.steps, min(args.warmup, 3))
 
@@ -365,34 +389,32 @@ def run_b200(args):
         # buffers alternate so that an upload never overwrites the graph a propagation is reading.
         s_h2d, s_d2h = torch.cuda.Stream(), torch.cuda.Stream()
         cur = torch.cuda.current_stream()
-        bufs = [(torch.empty_like(csr.indptr), torch.empty_like(csr.indices), torch.empty_like(csr.vals))
-                for _ in range(2)]
+        bufs = [[tuple(torch.empty_like(t) for t in (c.indptr, c.indices, c.vals)) for c in graphs] for _ in range(2)]
         free_ev = [None, None]
         state = {"i": 0}
 
         def pipelined_step():
             k = state["i"] & 1
             state["i"] += 1
-            ip_d, ix_d, vl_d = bufs[k]
             with torch.cuda.stream(s_h2d):
                 if free_ev[k] is not None:
                     s_h2d.wait_event(free_ev[k])          # the propagation that read this buffer has finished
-                ip_d.copy_(ip_h, non_blocking=True)
-                ix_d.copy_(ix_h, non_blocking=True)
-                vl_d.copy_(vl_h, non_blocking=True)
+                for dst, src in zip(bufs[k], host):
+                    for td, th in zip(dst, src):
+                        td.copy_(th, non_blocking=True)
                 up = torch.cuda.Event()
                 up.record(s_h2d)
             cur.wait_event(up)
-            loc = g.NormAdjCSR(ip_d, ix_d, vl_d, n_rows_local, n_cols, symmetric=True, long_threshold=thr)
-            with torch.no_grad():
-                out = propagate_on(loc)
+            outs = propagate_on(rebuild(bufs[k]))
             done = torch.cuda.Event()
             done.record(cur)
             free_ev[k] = done
             with torch.cuda.stream(s_d2h):
                 s_d2h.wait_event(done)
-                out_host.copy_(out, non_blocking=True)
-            out.record_stream(s_d2h)
+                for oh, o in zip(out_host, outs):
+                    oh.copy_(o, non_blocking=True)
+            for o in outs:
+                o.record_stream(s_d2h)
 
         def drain():
             cur.wait_stream(s_d2h)
@@ -413,10 +435,10 @@ def run_b200(args):
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_e2e = float(t.item())
-        assert float(out_host[0, 0]) == float(out_host[0, 0])
+        assert float(out_host[0][0, 0]) == float(out_host[0][0, 0])
         del bufs
         e2e = {"value": L * nnz / (ms_e2e * 1e-3), "unit": "edges/s", "ms_per_step": ms_e2e,
-               "h2d_bytes_per_step": h2d_bytes * world, "d2h_bytes_per_step": int(out_host.numel() * 4) * world,
+               "h2d_bytes_per_step": h2d_bytes * world, "d2h_bytes_per_step": d2h_bytes * world,
                "bytes_are": "summed over all ranks (each rank uploads its row block, downloads its output rows)",
                "schedule": "software-pipelined at every N: upload of step i+1 and download of step i-1 on copy streams "
                            "overlap the propagation of step i; timed over all steps incl. pipeline fill and drain",
@@ -424,10 +446,11 @@ def run_b200(args):
                "path": "32-bit CSR (int32 indptr/indices, f32 values: NormAdjCSR.to_host layout, 8 B per entry) in pinned "
                        "host memory -> device -> row schedule -> model.propagate(adj) -> embeddings copied to pinned "
                        "host memory"}
-        del ip_h, ix_h, vl_h
+        del host
         # the reference's own delivery format, for comparison (N=1): torch sparse COO with int64 indices
         # (20 B per entry, graph_builder.py:163-172) -> .to(device) -> as_csr -> propagate -> host
         if world == 1:
+            csr = graphs[0]
             rows_h = csr.row_ids().to(torch.int64)
             idx_host = torch.empty((2, csr.nnz), dtype=torch.int64, pin_memory=True)
             idx_host[0].copy_(rows_h)
@@ -444,7 +467,7 @@ def run_b200(args):
                 del adj
                 with torch.no_grad():
                     out = model.propagate(loc)
-                out_host.copy_(out, non_blocking=True)
+                out_host[0].copy_(out, non_blocking=True)
                 torch.cuda.current_stream().synchronize()
 
             ms_coo = timed(coo_step, max(2, args.steps // 3), 1)
@@ -475,28 +498,31 @@ def run_b200(args):
         torch_main = None
         try:        # stock torch.sparse.mm (cuSPARSE) on the same resident graph and table
             x0 = torch.cat([model.user_embedding.weight, model.item_embedding.weight]).detach()
-            torch_main = run_torch_gpu_baseline(csr, x0, L, dev)
+            torch_main = run_torch_gpu_baseline(graphs[0], x0, L, dev)
             del x0
         except Exception as err:
             torch_main = {"error": f"{type(err).__name__}: {str(err)[:200]}"}
-        model = csr = full = None
+        model = graphs = full = None
         torch.cuda.empty_cache()
         extras = run_extras(g, dev, hbm_peak)
         extras["torch_gpu"][f"spmm_{args.workload.lower().replace('/', '_')}"] = torch_main
     elif world > 1 and not args.no_extras:
-        extras = run_extras_multi(g, dev, rank, world, csr, part, exchange, x0_local, nu, ni, L, d, ms_step, kernel_ms)
+        extras = run_extras_multi(g, dev, rank, world, mode, graphs, part, exchange, x0_local, nu, ni, L, d, ms_step,
+                                  kernel_ms)
 
     if rank == 0:
         line = {
             "metric": "lightgcn_propagation_edges_per_s", "value": value, "unit": "edges/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args.workload, world),
+            "config": workload_config(args.workload, world, mode),
             "clocks": sampler.summary() if sampler else None,
             "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
             "setup_s": t_setup, "nnz": nnz, "long_rows": n_long, "extras": extras,
-            "exchange": None if world == 1 else (("fused_multicast_stores" if exchange.multicast else "fused_peer_stores")
-                                                  if exchange is not None else "nccl_all_gather"),
+            "exchange": None if world == 1 else (
+                "user_owner_reduce_broadcast" if mode == "user-owner" else
+                (("fused_multicast_stores" if exchange.multicast else "fused_peer_stores") if exchange is not None
+                 else "nccl_all_gather")),
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -672,33 +698,46 @@ def run_torch_gpu_baseline(csr, x, L, dev):
             "what": f"torch {torch.__version__} torch.sparse.mm (CSR, CUDA) x {L} layers + layer mean, same graph and table"}
 
 
-def run_extras_multi(g, dev, rank, world, csr, part, exchange, x0_local, nu, ni, L, d, ms_step, kernel_ms):
+def run_extras_multi(g, dev, rank, world, mode, graphs, part, exchange, x0_local, nu, ni, L, d, ms_step, kernel_ms):
     """N > 1: (1) NVLink bytes and rate of one layer exchange; (2) BASELINE.metric's epoch time through the
-    row-partitioned training step (ShardedLightGCN: two propagations + replicated BPR batch + local clip/Adam),
-    timed over a few steps and extrapolated to the E/B + 1 steps of an epoch; (3) BASELINE configs[3]: full-ranking
-    top-20 at the Amazon-Book shape with the item catalogue sharded over the ranks and the per-shard lists merged."""
+    partitioned training step (two propagations + replicated BPR batch + local clip/Adam), timed over a few
+    steps and extrapolated to the E/B + 1 steps of an epoch; (3) BASELINE configs[3]: full-ranking top-20 at the
+    Amazon-Book shape with the item catalogue sharded over the ranks and the per-shard lists merged."""
     import torch.distributed as dist
 
-    from gnn_recommendations_b200.dist import ShardedLightGCN, full_rank_topk_sharded, item_shard
+    from gnn_recommendations_b200.dist import (ShardedLightGCN, UserOwnerLightGCN, full_rank_topk_sharded, item_shard)
     from gnn_recommendations_b200.evaluator import seen_csr
     from gnn_recommendations_b200.synthetic import synth_pairs_device
 
     out = {}
-    n_loc = csr.n_rows
-    egress = n_loc * d * 4 * (world - 1)
-    layer_ms = float(np.mean(kernel_ms)) if kernel_ms else None
-    out["exchange"] = {"egress_bytes_per_layer_per_rank": egress, "layer_kernel_ms": layer_ms,
+    layer_ms = float(np.sum(kernel_ms)) / max(1, len(kernel_ms)) * len(graphs) if kernel_ms else None
+    if mode == "user-owner":
+        lo_i, hi_i = part.item_range(rank)
+        egress = (hi_i - lo_i) * d * 4 * (world - 1)
+        what = ("user-owner exchange per layer and rank: its item block is loaded from the other ranks' partial buffers "
+                "(ingress) and the reduced block stored into their item tables (egress), both (G-1)/G x I x 4d bytes, in "
+                "opposite NVLink directions; time = that layer's SpMM launches (the exchange kernel overlaps the user-row SpMM)")
+    else:
+        egress = graphs[0].n_rows * d * 4 * (world - 1)
+        what = ("rows this rank stores into the other ranks' layer buffers from the SpMM epilogue (fused all-gather) per "
+                "layer, over the CUDA-event time of that layer's launch")
+    out["exchange"] = {"mode": mode, "egress_bytes_per_layer_per_rank": egress,
+                       "ingress_bytes_per_layer_per_rank": egress if mode == "user-owner" else egress,
+                       "layer_ms": layer_ms,
                        "nvlink_egress_gb_per_s": (egress / (layer_ms * 1e-3) / 1e9) if layer_ms else None,
-                       "nvlink_peak_gb_per_s": 900.0,
-                       "what": "rows this rank stores into the other ranks' layer buffers from the SpMM epilogue (fused "
-                               "all-gather) per layer, over the CUDA-event time of that layer's launch"}
-    # ---- epoch time at this workload, row-partitioned training step
-    e_total = csr.nnz  # local entries; global edges = nnz_global / 2
-    nnz_t = torch.tensor([csr.nnz], dtype=torch.int64, device=dev)
+                       "nvlink_peak_gb_per_s": 900.0, "step_ms": ms_step, "what": what}
+    # ---- epoch time at this workload, partitioned training step
+    nnz_t = torch.tensor([sum(c.nnz for c in graphs)], dtype=torch.int64, device=dev)
     dist.all_reduce(nnz_t)
     n_edges = int(nnz_t.item()) // 2
-    csr.full_symmetric = True
-    sm = ShardedLightGCN(csr, part, rank, x0_local, nu, L, exchange=exchange)
+    if mode == "user-owner":
+        gen0 = torch.Generator(device=dev).manual_seed(99 + rank)
+        xu0 = torch.randn(part.n_users_local(rank), d, device=dev, generator=gen0) * 0.1
+        xi0 = torch.randn(part.item_block, d, device=dev, generator=gen0) * 0.1
+        sm = UserOwnerLightGCN(graphs[0], graphs[1], exchange, xu0, xi0, L)
+    else:
+        graphs[0].full_symmetric = True
+        sm = ShardedLightGCN(graphs[0], part, rank, x0_local, nu, L, exchange=exchange)
     gen = torch.Generator(device=dev).manual_seed(7)          # same batch on every rank
     B = 512
 
@@ -721,7 +760,7 @@ def run_extras_multi(g, dev, rank, world, csr, part, exchange, x0_local, nu, ni,
     steps_epoch = n_edges // B + 1
     out["epoch"] = {"train_step_ms": float(sec.item()) * 1e3, "steps_timed": n_steps, "steps_per_epoch": steps_epoch,
                     "epoch_s_extrapolated": float(sec.item()) * steps_epoch, "loss": loss,
-                    "what": "ShardedLightGCN.train_step (forward propagation, replicated B=512 batch with one [3B,d] "
+                    "what": f"{type(sm).__name__}.train_step (forward propagation, replicated B=512 batch with one [3B,d] "
                             "all-reduce, fused B x B BPR, backward = the same propagation on the gradient, global-norm "
                             "clip, local fused Adam); epoch = E // B + 1 such steps (trainer.py:237), extrapolated"}
     del sm
@@ -877,6 +916,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--partition", default=os.environ.get("GR_BENCH_PARTITION", "user-owner"), choices=["user-owner", "rows"],
+                    help="N>1: user-owner = 1.5-D (item partial sums reduced + broadcast, 1e-5 parity, default); "
+                         "rows = exact row partition with fused all-gather (bit-identical to 1 GPU)")
     ap.add_argument("--nccl-allgather", action="store_true", help="N>1: NCCL all-gather per layer instead of the "
                     "fused peer-store exchange")
     args = ap.parse_args()

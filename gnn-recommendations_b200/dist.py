@@ -738,3 +738,66 @@ def emulate_user_owner(full: NormAdjCSR, n_users: int, n_items: int, x0: torch.T
         lo, hi = part.item_range(r)
         out[n_users + lo: n_users + hi] = results[r]["items"]
     return out
+
+
+class UserOwnerLightGCN:
+    """ShardedLightGCN in the user-owner layout: parameters (and Adam state) are this rank's user rows and its
+    block of the item table.  One step = forward propagation (lightgcn_propagate_user_owner), the replicated
+    B x B BPR on the 3B touched rows (collected with one all-reduce; each row has one owner), backward = the same
+    propagation applied to the gradient (mean_l Â^l is symmetric and the layout is the same), global-norm clip,
+    fused Adam on the local rows."""
+
+    def __init__(self, a_u: NormAdjCSR, a_i: NormAdjCSR, ex, xu0: torch.Tensor, xi0_block: torch.Tensor, n_layers: int,
+                 lr: float = 1e-3, weight_decay: float = 1e-4, max_grad_norm: float = 1.0, group=None):
+        self.a_u, self.a_i, self.ex, self.part, self.group = a_u, a_i, ex, ex.part, group
+        self.rank, self.n_layers, self.max_grad_norm = ex.rank, int(n_layers), float(max_grad_norm)
+        self.lo, self.hi = self.part.item_range(self.rank)
+        self.users = torch.nn.Parameter(xu0.detach().clone())
+        self.items = torch.nn.Parameter(xi0_block.detach().clone())          # [item_block, d]; rows >= hi - lo unused
+        self.optimizer = torch.optim.Adam([self.users, self.items], lr=lr, weight_decay=weight_decay)
+
+    def propagate(self, xu: torch.Tensor, xi_block: torch.Tensor):
+        return lightgcn_propagate_user_owner(self.a_u, self.a_i, self.ex, xu, xi_block, self.n_layers)
+
+    def _all_reduce(self, t: torch.Tensor) -> torch.Tensor:
+        import torch.distributed as dist
+
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            dist.all_reduce(t, group=self.group)
+        return t
+
+    def train_step(self, users: torch.Tensor, pos: torch.Tensor, neg: torch.Tensor) -> float:
+        from .losses import bpr_fused
+        from .optim import fused_clip_adam_step
+
+        G, B, dev = self.part.world_size, int(users.numel()), self.users.device
+        users, items = users.to(dev).view(-1).long(), torch.cat([pos.to(dev).view(-1), neg.to(dev).view(-1)]).long()
+        with torch.no_grad():
+            out_u, out_i = self.propagate(self.users.detach(), self.items.detach())
+            mine_u = (users % G) == self.rank
+            mine_i = (items >= self.lo) & (items < self.hi)
+            table = torch.zeros((3 * B, out_u.shape[1]), dtype=out_u.dtype, device=dev)
+            table[:B][mine_u] = out_u[users[mine_u] // G]
+            table[B:][mine_i] = out_i[items[mine_i] - self.lo]
+            self._all_reduce(table)
+        ar = torch.arange(B, device=dev)
+        table.requires_grad_(True)
+        loss = bpr_fused(table, B, ar, ar, (B + ar).view(-1, 1))
+        loss.backward()
+        with torch.no_grad():
+            gu = torch.zeros_like(self.users)
+            gi = torch.zeros_like(self.items)
+            gu.index_add_(0, users[mine_u] // G, table.grad[:B][mine_u])           # duplicates accumulate
+            gi.index_add_(0, items[mine_i] - self.lo, table.grad[B:][mine_i])
+            du, di = self.propagate(gu, gi)                                        # mean_l Â^l g
+            self.users.grad = du
+            self.items.grad = torch.zeros_like(self.items)
+            self.items.grad[: self.hi - self.lo] = di
+            if self.max_grad_norm > 0:
+                sq = self._all_reduce((du.double().pow(2).sum() + di.double().pow(2).sum()).view(1))
+                coef = self.max_grad_norm / (float(sq.sqrt()) + 1e-6)
+                if coef < 1.0:
+                    self.users.grad.mul_(coef)
+                    self.items.grad.mul_(coef)
+            fused_clip_adam_step(self.optimizer, 0.0)                              # already clipped with the GLOBAL norm
+        return float(loss.detach())

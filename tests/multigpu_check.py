@@ -79,13 +79,49 @@ def main():
         torch.cuda.synchronize(); t_1 += time.perf_counter() - t0
         ok_train = ok_train and abs(loss_sh - float(loss_1)) <= 1e-6 * abs(float(loss_1))
     ok_train = ok_train and bool(torch.allclose(sharded.gathered_weight(), w_full.detach(), rtol=1e-4, atol=2e-6))
-    flags = torch.tensor([int(ok_prop), int(ok_topk), int(ok_fused), int(ok_train)], device=dev)
+    # ---- user-owner (1.5-D) mode: item rows = partial sums reduced + broadcast over peer memory (1e-5 parity)
+    from gnn_recommendations_b200.dist import (BipartitePartition, ItemExchange, UserOwnerLightGCN,
+                                               lightgcn_propagate_user_owner)
+    bp = BipartitePartition(nu, ni, world)
+    a_u, a_i = bp.local_csrs(full, rank)
+    iex = ItemExchange(bp, d, dev)
+    lo_b, hi_b = bp.item_range(rank)
+    xi_blk = torch.zeros((bp.item_block, d), device=dev)
+    xi_blk[: hi_b - lo_b] = x0[nu + lo_b: nu + hi_b]
+    xu_mine = bp.take_users(x0[:nu], rank)
+    ok_uo = True
+    scale = float(single.abs().max())
+    for _ in range(3):
+        ou, oi = lightgcn_propagate_user_owner(a_u, a_i, iex, xu_mine, xi_blk, L)
+        err = max(float((ou - single[:nu][rank::world]).abs().max()),
+                  float((oi - single[nu + lo_b: nu + hi_b]).abs().max()) if hi_b > lo_b else 0.0)
+        ok_uo = ok_uo and err <= 1e-5 * scale
+    uo = UserOwnerLightGCN(a_u, a_i, iex, xu_mine, xi_blk, L)
+    w2 = torch.nn.Parameter(x0.clone())
+    opt2 = torch.optim.Adam([w2], lr=1e-3, weight_decay=1e-4)
+    ok_uo_train, t_uo = True, 0.0
+    for users, pos, neg in batches[:10]:
+        torch.cuda.synchronize(); dist.barrier(); t0 = time.perf_counter()
+        loss_uo = uo.train_step(users, pos, neg)
+        torch.cuda.synchronize(); dist.barrier(); t_uo += time.perf_counter() - t0
+        opt2.zero_grad()
+        loss_1 = bpr_fused(g.lightgcn._LightGCNPropagate.apply(w2, full, L), nu, users, pos, neg)
+        loss_1.backward()
+        fused_clip_adam_step(opt2, 1.0)
+        ok_uo_train = ok_uo_train and abs(loss_uo - float(loss_1)) <= 1e-6 * abs(float(loss_1))
+    ok_uo_train = ok_uo_train and bool(torch.allclose(uo.users.detach(), w2.detach()[:nu][rank::world], rtol=1e-4, atol=2e-6))
+    if hi_b > lo_b:
+        ok_uo_train = ok_uo_train and bool(torch.allclose(uo.items.detach()[: hi_b - lo_b], w2.detach()[nu + lo_b: nu + hi_b],
+                                                          rtol=1e-4, atol=2e-6))
+    flags = torch.tensor([int(ok_prop), int(ok_topk), int(ok_fused), int(ok_train), int(ok_uo), int(ok_uo_train)], device=dev)
     dist.all_reduce(flags, op=dist.ReduceOp.MIN)
     if rank == 0:
         print(f"multigpu_check shape={shape} world={world} rows/rank={[part.n_local(r) for r in range(world)]} "
               f"propagation_bit_identical={bool(flags[0])} topk_bit_identical={bool(flags[1])} "
               f"fused_peer_exchange_bit_identical={bool(flags[2])} sharded_training_matches={bool(flags[3])} "
-              f"train_step_ms: sharded {1e3 * t_sh / n_steps:.3f} vs 1 GPU {1e3 * t_1 / n_steps:.3f}", flush=True)
+              f"user_owner_propagation_within_1e-5={bool(flags[4])} user_owner_training_matches={bool(flags[5])} "
+              f"train_step_ms: sharded {1e3 * t_sh / n_steps:.3f} / user-owner {1e3 * t_uo / 10:.3f} vs 1 GPU "
+              f"{1e3 * t_1 / n_steps:.3f}", flush=True)
     dist.destroy_process_group()
     sys.exit(0 if bool(flags.min()) else 1)
 
