@@ -334,9 +334,10 @@ def run_b200(args):
     ms_step = timed(step, args.steps, 0, sampler)
     launches = sum(c.launches for c in graphs) - launches0
     torch.cuda.synchronize()
-    kernel_ms, b_alg_total = [], 0.0
+    kernel_ms, b_alg_total, per_graph_ms = [], 0.0, []
     for c in graphs:
         t_c = [a.elapsed_time(b) for a, b in c.timings]
+        per_graph_ms.append(float(np.mean(t_c)) if t_c else None)
         kernel_ms += t_c
         b_alg_total += len(t_c) * alg_bytes_per_layer(c.nnz, c.n_rows, d)
         c.timings = None
@@ -351,7 +352,7 @@ def run_b200(args):
     roofline = {"bound": "hbm", "kernel": f"gr_spmm_csr_f32 (spmm_stream_rows<{d}> + spmm_long_rows<{d}>)",
                 "achieved": achieved, "peak": hbm_peak, "peak_source": peak_src, "unit": "GB/s",
                 "frac": achieved / hbm_peak, "traffic": traffic, "algorithmic_bytes_per_launch": b_alg,
-                "avg_launch_ms": avg_kernel_ms, "launches_timed": len(kernel_ms),
+                "avg_launch_ms": avg_kernel_ms, "launches_timed": len(kernel_ms), "avg_launch_ms_per_graph": per_graph_ms,
                 "kernel_share_of_step": sum(kernel_ms) / (ms_step * args.steps)}
 
     # ---- e2e: the propagation as a user with a HOST-resident graph runs it — every step uploads the

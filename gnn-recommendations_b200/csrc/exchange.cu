@@ -3,14 +3,16 @@
 // parity target is the single-GPU result, 1e-5 for embeddings per BASELINE.json north_star).
 //
 // Layout: users are owned by ranks (their rows never leave the rank); every rank computes PARTIAL sums of ALL
-// item rows from its own users (P_g = A_items,users(g) X_users(g)).  The item rows are owned in contiguous
-// blocks for the reduction: for each row j of its block a rank
-//     loads P_0[j] .. P_{G-1}[j]    (G-1 of them over NVLink, peer loads)
-//     v = ((P_0[j] + P_1[j]) + ...) (fixed rank order: deterministic, identical on every run)
+// item rows from its own users (P_g = A_items,users(g) X_users(g)) and pushes each row from the SpMM epilogue to
+// the rank owning the row's item block (routed peer stores of gr_spmm_csr_f32, one staging slot per sender).  For
+// each row j of its block the owner then
+//     loads slot_0[j] .. slot_{G-1}[j]  (local HBM; a first version PULLED them over NVLink: peer loads ran at
+//                                        370 GB/s against 650 GB/s for peer stores on 8 B200s, hence the push)
+//     v = ((slot_0[j] + slot_1[j]) + ...) (fixed rank order: deterministic, identical on every run)
 //     stores v into row j of every rank's item table  (G-1 peer stores)   [skipped on the last layer]
 //     folds v into the running layer sum of its own block   (out = scale_op(addend + v))
-// Per layer a rank moves 2 x (G-1)/G x I x 4d bytes (in + out, opposite NVLink directions) instead of the
-// (G-1)/G x N x 4d egress of the exact all-gather: 4.5 GB instead of 11.2 GB at C5 on 8 GPUs.
+// Per layer a rank sends 2 x (G-1)/G x I x 4d bytes instead of the (G-1)/G x N x 4d of the exact all-gather:
+// 4.5 GB instead of 11.2 GB at C5 on 8 GPUs.
 #include "gr_common.cuh"
 
 namespace gr {
@@ -22,7 +24,7 @@ struct ReduceBcastArgs {
     float4 *dst[kMaxRanks];         // item tables of all ranks (n_dst may be 0)
     int n_src, n_dst;
     long long ld_src4, ld_dst4;
-    long long row0, n_rows;         // block [row0, row0 + n_rows) of the item rows
+    long long row0, dst_row0, n_rows;   // source rows [row0, row0 + n_rows) -> table rows [dst_row0, dst_row0 + n_rows)
     int f4;                         // d / 4
     const float4 *addend;           // [n_rows, lda4] running layer sum of the block (optional)
     float4 *out;                    // [n_rows, ldo4]
@@ -32,6 +34,8 @@ struct ReduceBcastArgs {
     int scale_mode;
 };
 
+// Partial rows are written by other GPUs (peer stores) or by an earlier kernel of this GPU; a system-scope
+// relaxed load never hits a stale L1 line.
 __device__ __forceinline__ float4 ld_peer_f4(const float4 *p) {
     float4 v;
     asm volatile("ld.global.relaxed.sys.v4.f32 {%0,%1,%2,%3}, [%4];"
@@ -81,7 +85,7 @@ __global__ void __launch_bounds__(256) reduce_bcast_rows_kernel(const ReduceBcas
                 const int f = (int)(idx[u] % a.f4);
 #pragma unroll
                 for (int g = 0; g < kMaxRanks; ++g)
-                    if (g < a.n_dst) a.dst[g][(a.row0 + r) * a.ld_dst4 + f] = v[u];
+                    if (g < a.n_dst) a.dst[g][(a.dst_row0 + r) * a.ld_dst4 + f] = v[u];
                 if (a.own) a.own[r * a.ldw4 + f] = v[u];
                 if (a.out) {
                     float4 o = v[u];
@@ -105,12 +109,12 @@ using namespace gr;
 
 extern "C" int gr_reduce_bcast_rows(const float *const *src_host, int32_t n_src, int64_t ld_src,
                                     float *const *dst_host, int32_t n_dst, int64_t ld_dst, int64_t row0,
-                                    int64_t n_rows, int32_t d, const float *addend, int64_t lda, float *out,
+                                    int64_t dst_row0, int64_t n_rows, int32_t d, const float *addend, int64_t lda, float *out,
                                     int64_t ldo, float *own, int64_t ldw, float scale, int32_t scale_mode,
                                     void *stream) {
     if (!src_host || n_src < 1 || n_src > kMaxRanks || n_dst < 0 || n_dst > kMaxRanks || (n_dst > 0 && !dst_host))
         return GR_ERR_INVALID;
-    if (n_rows < 0 || row0 < 0 || d <= 0 || (d & 3) || (ld_src & 3) || ld_src < d) return GR_ERR_INVALID;
+    if (n_rows < 0 || row0 < 0 || dst_row0 < 0 || d <= 0 || (d & 3) || (ld_src & 3) || ld_src < d) return GR_ERR_INVALID;
     if (n_dst > 0 && ((ld_dst & 3) || ld_dst < d)) return GR_ERR_INVALID;
     if (addend && (!out || (lda & 3) || lda < d)) return GR_ERR_INVALID;
     if (out && ((ldo & 3) || ldo < d)) return GR_ERR_INVALID;
@@ -128,7 +132,7 @@ extern "C" int gr_reduce_bcast_rows(const float *const *src_host, int32_t n_src,
         a.dst[g] = reinterpret_cast<float4 *>(dst_host[g]);
     }
     a.n_src = n_src; a.n_dst = n_dst; a.ld_src4 = ld_src / 4; a.ld_dst4 = ld_dst / 4;
-    a.row0 = row0; a.n_rows = n_rows; a.f4 = d / 4;
+    a.row0 = row0; a.dst_row0 = dst_row0; a.n_rows = n_rows; a.f4 = d / 4;
     a.addend = reinterpret_cast<const float4 *>(addend); a.out = reinterpret_cast<float4 *>(out);
     a.own = reinterpret_cast<float4 *>(own);
     a.lda4 = lda / 4; a.ldo4 = ldo / 4; a.ldw4 = ldw / 4;

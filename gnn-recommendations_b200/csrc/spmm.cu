@@ -63,6 +63,10 @@ struct SpmmArgs {
     int n_peers;
     int peer_multicast;     // peer_y[0] is a multicast address
     long long peer_row_off;
+    // routed mode (route_block > 0): row r goes to ONE peer, g = r / route_block, as row
+    // peer_row_off + r % route_block of its buffer (user-owner propagation: partial item rows are pushed to
+    // the rank that owns the item block, into the slot of the sending rank)
+    int route_block;
     // long-row scheduler state in CALLER memory: [0] ticket counter, [1] finished-CTA counter.  Zero on
     // entry; the last CTA of a launch zeroes both again.  (No library-global device state: two
     // propagations in flight on different streams use different words.)
@@ -235,8 +239,13 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) spmm_stream_rows(const Spmm
             const int off = gl + j * LPR;
             if (a.y) st_stream_f4(a.y + (long long)row * a.ldy4 + off, acc[j]);
             if constexpr (PEERS == kPeersP2P) {
+                if (a.route_block > 0) {
+                    const int pg = row / a.route_block;
+                    a.peer_y[pg][(a.peer_row_off + (row - pg * a.route_block)) * a.ldy4 + off] = acc[j];
+                } else {
 #pragma unroll 1
-                for (int p = 0; p < a.n_peers; ++p) a.peer_y[p][(a.peer_row_off + row) * a.ldy4 + off] = acc[j];
+                    for (int p = 0; p < a.n_peers; ++p) a.peer_y[p][(a.peer_row_off + row) * a.ldy4 + off] = acc[j];
+                }
             } else if constexpr (PEERS == kPeersMulticast) {
                 st_multimem_f4(a.peer_y[0] + (a.peer_row_off + row) * a.ldy4 + off, acc[j]);
             }
@@ -571,9 +580,14 @@ __global__ void __launch_bounds__(LongCfg<D>::THREADS, 1) spmm_long_rows(const S
         const int f = warp * 32 + lane;
         if (a.y) reinterpret_cast<float *>(a.y + (long long)r * a.ldy4)[f] = acc;
         if constexpr (PEERS == kPeersP2P) {
+            if (a.route_block > 0) {
+                const int pg = r / a.route_block;
+                reinterpret_cast<float *>(a.peer_y[pg] + (a.peer_row_off + (r - pg * a.route_block)) * a.ldy4)[f] = acc;
+            } else {
 #pragma unroll 1
-            for (int p = 0; p < a.n_peers; ++p)
-                reinterpret_cast<float *>(a.peer_y[p] + (a.peer_row_off + r) * a.ldy4)[f] = acc;
+                for (int p = 0; p < a.n_peers; ++p)
+                    reinterpret_cast<float *>(a.peer_y[p] + (a.peer_row_off + r) * a.ldy4)[f] = acc;
+            }
         } else if constexpr (PEERS == kPeersMulticast) {
             st_multimem_f1(reinterpret_cast<float *>(a.peer_y[0] + (a.peer_row_off + r) * a.ldy4) + f, acc);
         }
@@ -743,9 +757,14 @@ __global__ void __launch_bounds__(LongCfgBar<D>::THREADS, 1) spmm_long_rows_bar(
         const int f = warp * 32 + lane;
         if (a.y) reinterpret_cast<float *>(a.y + (long long)r * a.ldy4)[f] = acc;
         if constexpr (PEERS == kPeersP2P) {
+            if (a.route_block > 0) {
+                const int pg = r / a.route_block;
+                reinterpret_cast<float *>(a.peer_y[pg] + (a.peer_row_off + (r - pg * a.route_block)) * a.ldy4)[f] = acc;
+            } else {
 #pragma unroll 1
-            for (int p = 0; p < a.n_peers; ++p)
-                reinterpret_cast<float *>(a.peer_y[p] + (a.peer_row_off + r) * a.ldy4)[f] = acc;
+                for (int p = 0; p < a.n_peers; ++p)
+                    reinterpret_cast<float *>(a.peer_y[p] + (a.peer_row_off + r) * a.ldy4)[f] = acc;
+            }
         } else if constexpr (PEERS == kPeersMulticast) {
             st_multimem_f1(reinterpret_cast<float *>(a.peer_y[0] + (a.peer_row_off + r) * a.ldy4) + f, acc);
         }
@@ -781,6 +800,9 @@ __global__ void spmm_combine_parts(const SpmmArgs a, int d) {
         if (a.y) reinterpret_cast<float *>(a.y + (long long)r * a.ldy4)[f] = t;
         if (a.peer_multicast) {
             st_multimem_f1(reinterpret_cast<float *>(a.peer_y[0] + (a.peer_row_off + r) * a.ldy4) + f, t);
+        } else if (a.route_block > 0 && a.n_peers > 0) {
+            const int pg = r / a.route_block;
+            reinterpret_cast<float *>(a.peer_y[pg] + (a.peer_row_off + (r - pg * a.route_block)) * a.ldy4)[f] = t;
         } else {
             for (int p = 0; p < a.n_peers; ++p)
                 reinterpret_cast<float *>(a.peer_y[p] + (a.peer_row_off + r) * a.ldy4)[f] = t;
@@ -959,8 +981,8 @@ extern "C" int gr_spmm_csr_f32(const int32_t *indptr, const int32_t *indices, co
                                int32_t n_groups, int32_t long_threshold, int64_t n_rows, int32_t d, const float *x,
                                int64_t ldx, float *y, int64_t ldy, const float *addend, int64_t lda, float *out,
                                int64_t ldo, float scale, int32_t scale_mode, float *const *peer_y_host,
-                               int32_t n_peers, int32_t peer_multicast, int64_t peer_row_offset, uint32_t *sched_ws,
-                               void *stream) {
+                               int32_t n_peers, int32_t peer_multicast, int64_t peer_row_offset, int32_t peer_route_block,
+                               uint32_t *sched_ws, void *stream) {
     using namespace gr;
     if (n_rows == 0) return GR_OK;
     if (row_order && n_long > 0 && !sched_ws) return GR_ERR_INVALID;      // long-row scheduler needs its 2 words
@@ -1004,6 +1026,9 @@ extern "C" int gr_spmm_csr_f32(const int32_t *indptr, const int32_t *indices, co
     a.peer_multicast = (n_peers > 0 && peer_multicast) ? 1 : 0;
     if (a.peer_multicast && n_peers != 1) return GR_ERR_INVALID;
     a.peer_row_off = peer_row_offset;
+    a.route_block = peer_route_block > 0 ? peer_route_block : 0;
+    if (a.route_block > 0 && (a.peer_multicast || n_peers < 1 || (n_rows + a.route_block - 1) / a.route_block > n_peers))
+        return GR_ERR_INVALID;
     a.sched = sched_ws;
     for (int p = 0; p < kMaxPeers; ++p) {
         a.peer_y[p] = p < n_peers ? reinterpret_cast<float4 *>(peer_y_host[p]) : nullptr;

@@ -493,9 +493,11 @@ class BipartitePartition:
     of NVLink egress per rank and layer, 11.2 GB at C5 on 8 GPUs against 9.8 ms of SpMM.  But a user row only
     reads ITEM columns and an item row only USER columns.  So a rank can (1) advance its own users from the
     replicated item table with no communication, and (2) compute, for ALL items, the partial sum over the users
-    it owns; the partials are then reduced per item block (rank r owns items [r*Ib, (r+1)*Ib) for the reduction)
-    and the reduced block is broadcast: 2 x (G-1)/G x I x 4d bytes per rank and layer (4.5 GB at C5), in opposite
-    NVLink directions, overlapped with step (1) of the same layer.
+    it owns.  Every partial row is pushed from the SpMM epilogue to the rank that owns the row's item block (rank r
+    owns items [r*Ib, (r+1)*Ib); routed P2P stores, one staging slot per sender), the owner adds its G slots in rank
+    order and broadcasts the block (P2P stores again): 2 x (G-1)/G x I x 4d bytes of egress per rank and layer
+    (4.5 GB at C5), all as stores (measured: peer LOADS reached 370 GB/s, stores 650), the first half overlapped
+    with the partial-sum SpMM itself, the second with the user-row SpMM.
 
     An item row is then  sum_g (chain over rank g's users, ascending)  added in rank order — deterministic and
     reproducible, but not the single ascending chain of the 1-GPU kernel: ~1e-7 relative (BASELINE north_star
@@ -579,6 +581,7 @@ class ItemExchange:
             self.table_ptrs.append(arr)
             self.handles.append(h)
         self.partial, self.partial_handle, self.partial_ptrs = alloc()
+        self.slot_ptrs = _slot_ptrs(self.partial, part)
         self.comm_stream = torch.cuda.Stream(device)
         torch.cuda.synchronize(device)
         dist.barrier(self.group)
@@ -607,17 +610,29 @@ class EmulatedItemExchange:
         ex.rank = rank
         ex.tables = [self._tables[0][rank], self._tables[1][rank]]
         ex.partial = self._partials[rank]
+        ex.slot_ptrs = _slot_ptrs(ex.partial, self.part)
         return ex
 
     def barrier(self):
         pass
 
 
+def _slot_ptrs(partial: torch.Tensor, part: "BipartitePartition"):
+    """The G slots of a rank's staging buffer: slot k = rows [k*Ib, (k+1)*Ib) = the partial rows of this rank's item
+    block pushed by rank k."""
+    import ctypes
+
+    step = part.item_block * partial.stride(0) * 4
+    return (ctypes.c_void_p * part.world_size)(*[partial.data_ptr() + k * step for k in range(part.world_size)])
+
+
 def _reduce_bcast(ex, row0: int, n_rows: int, d: int, dst_ptrs, n_dst: int, addend, out, scale: float, mode: int):
+    """Sum the G slots of the local staging buffer (rank order), store the block into rows [row0, ..) of the given
+    item tables, fold into the layer sum."""
     from ._lib import check, lib, ptr, stream_ptr
 
     with torch.cuda.device(ex.partial.device):
-        check(lib().gr_reduce_bcast_rows(ex.partial_ptrs, ex.world, d, dst_ptrs, n_dst, d, row0, n_rows, d,
+        check(lib().gr_reduce_bcast_rows(ex.slot_ptrs, ex.world, d, dst_ptrs, n_dst, d, 0, row0, n_rows, d,
                                          ptr(addend), addend.stride(0) if addend is not None else 0, ptr(out),
                                          out.stride(0) if out is not None else 0, None, 0, float(scale), int(mode),
                                          stream_ptr()), "gr_reduce_bcast_rows")
@@ -657,11 +672,12 @@ def _propagate_user_owner_steps(a_u: NormAdjCSR, a_i: NormAdjCSR, ex, xu0: torch
     for l in range(L):
         last = l == L - 1
         nxt = cur ^ 1
-        # (2) partial sums of ALL item rows over this rank's users  ->  P_rank
-        a_i.spmm(xu, y=ex.partial, want_y=True)
-        yield "partials"                                     # every rank's P is complete
+        # (2) partial sums of ALL item rows over this rank's users, each row pushed from the SpMM epilogue straight
+        #     into slot `rank` of the staging buffer of the rank that owns the row's item block (routed P2P stores)
+        a_i.spmm(xu, want_y=False, peers=(ex.partial_ptrs, G, rank * part.item_block, d, 0, part.item_block))
+        yield "partials"                                     # every rank's staging buffer is complete
         # (3) reduce my item block over the ranks' partials, broadcast it into every T[nxt], fold into the layer sum
-        side = ex.comm_stream
+        side = None if os.environ.get("GR_UO_SERIAL", "0") == "1" else ex.comm_stream
         if side is not None:
             side.wait_stream(main)
         ctx = torch.cuda.stream(side) if side is not None else _NullCtx()

@@ -365,8 +365,9 @@ class NormAdjCSR:
              out: Optional[torch.Tensor] = None, scale: float = 1.0, scale_mode: int = _lib.GR_SCALE_NONE,
              want_y: bool = True, peers=None) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
         """t = Â x;  y = t (if want_y);  out = scale_op(addend + t) (if out/addend given).
-        ``peers`` = (ctypes array of device pointers, n_peers, row offset, leading dim, multicast): t is also
-        stored into every peer's gathered buffer (fused all-gather, dist.PeerExchange)."""
+        ``peers`` = (ctypes array of device pointers, n_peers, row offset, leading dim, multicast[, route block]): t
+        is also stored into every peer's gathered buffer (fused all-gather, dist.PeerExchange), or — with a route
+        block — each row into the one peer that owns it (dist.ItemExchange)."""
         if x.dtype != torch.float32 or x.dim() != 2 or x.stride(1) != 1:
             raise ValueError("x must be a row-major float32 matrix")
         if x.shape[0] != self.n_cols:
@@ -395,7 +396,8 @@ class NormAdjCSR:
                 ptr(out), out.stride(0) if out is not None else 0,
                 float(scale), int(scale_mode),
                 peers[0] if peers else None, peers[1] if peers else 0, peers[4] if peers else 0,
-                peers[2] if peers else 0, ptr(self._sched_words()), stream_ptr()), "gr_spmm_csr_f32")
+                peers[2] if peers else 0, peers[5] if (peers and len(peers) > 5) else 0,
+                ptr(self._sched_words()), stream_ptr()), "gr_spmm_csr_f32")
             if ev is not None:
                 ev[1].record()
                 self.timings.append(ev)

@@ -138,7 +138,8 @@ int gr_spmm_csr_f32(const int32_t *indptr, const int32_t *indices, const float *
                     int32_t long_threshold, int64_t n_rows, int32_t d, const float *x,
                     int64_t ldx, float *y, int64_t ldy, const float *addend, int64_t lda, float *out,
                     int64_t ldo, float scale, int32_t scale_mode, float *const *peer_y_host, int32_t n_peers,
-                    int32_t peer_multicast, int64_t peer_row_offset, uint32_t *sched_ws, void *stream);
+                    int32_t peer_multicast, int64_t peer_row_offset, int32_t peer_route_block, uint32_t *sched_ws,
+                    void *stream);
 
 /* Fused compute + all-gather for the row-partitioned multi-GPU propagation (no reference
  * counterpart).  `peer_y_host` (HOST array of n_peers <= 8 DEVICE pointers, one per rank of the
@@ -149,20 +150,25 @@ int gr_spmm_csr_f32(const int32_t *indptr, const int32_t *indices, const float *
  * With peer_multicast = 1, peer_y_host[0] (n_peers = 1) is an NVSwitch MULTICAST address of the
  * buffer (symmetric memory multicast_ptr): each row is written once with multimem.st and replicated
  * to every rank inside the switch (NVLS), so a rank's NVLink egress is 1x the layer instead of (G-1)x.
- * gr_peer_scatter_rows does the same store fan-out for an existing matrix (the layer-0 exchange). */
+ * gr_peer_scatter_rows does the same store fan-out for an existing matrix (the layer-0 exchange).
+ * Routed mode (peer_route_block > 0, gr_spmm_csr_f32 only): row r is stored to ONE peer, g = r / peer_route_block,
+ * as row peer_row_offset + r % peer_route_block of its buffer — the user-owner propagation pushes every partial
+ * item row straight to the rank that owns the item block, into the slot of the sending rank. */
 int gr_peer_scatter_rows(const float *src, int64_t lds, int64_t n_rows, int32_t d, float *const *peer_dst_host,
                          int32_t n_peers, int32_t peer_multicast, int64_t ldd, int64_t peer_row_offset,
                          void *stream);
 
 /* Reduce + broadcast of partial item rows over NVLink peer memory: the exchange of the user-owner ("1.5-D")
  * multi-GPU propagation (SURVEY.md §8e "bipartite refinement"; no reference counterpart).  Every rank holds
- * partial sums of ALL item rows computed from the users it owns; for the rows [row0, row0 + n_rows) of its block
- * this call forms  v[j] = ((P_0[j] + P_1[j]) + ...)  over the n_src partial buffers (HOST array of DEVICE
- * pointers, peer-mapped; fixed order = deterministic), stores v into row j of the n_dst item tables (peer
- * stores; n_dst = 0 on the last layer), optionally into `own` [n_rows, ldw] and into the running layer sum
- *   out[j - row0] = scale_op(addend[j - row0] + v[j])   (same scale modes as gr_spmm_csr_f32). */
+ * partial sums of ALL item rows computed from the users it owns and pushes them (routed gr_spmm_csr_f32 epilogue)
+ * to the rank owning the item block, one slot per sending rank.  This call forms, for the n_rows rows of the
+ * block,  v[j] = ((P_0[row0 + j] + P_1[row0 + j]) + ...)  over the n_src source buffers (HOST array of DEVICE
+ * pointers: the G slots of the local staging buffer, or peer-mapped buffers; fixed order = deterministic), stores
+ * v into row dst_row0 + j of the n_dst item tables (peer stores over NVLink; n_dst = 0 on the last layer),
+ * optionally into `own` [n_rows, ldw], and folds it into the running layer sum
+ *   out[j] = scale_op(addend[j] + v[j])   (same scale modes as gr_spmm_csr_f32). */
 int gr_reduce_bcast_rows(const float *const *src_host, int32_t n_src, int64_t ld_src, float *const *dst_host,
-                         int32_t n_dst, int64_t ld_dst, int64_t row0, int64_t n_rows, int32_t d,
+                         int32_t n_dst, int64_t ld_dst, int64_t row0, int64_t dst_row0, int64_t n_rows, int32_t d,
                          const float *addend, int64_t lda, float *out, int64_t ldo, float *own, int64_t ldw,
                          float scale, int32_t scale_mode, void *stream);
 
