@@ -517,13 +517,18 @@ class BipartitePartition:
         lo = min(self.n_items, rank * self.item_block)
         return lo, min(self.n_items, lo + self.item_block)
 
+    def item_shift(self, rank: int) -> int:
+        """First item of the row order of rank's partial-sum matrix A_i (the next rank's block)."""
+        return ((rank + 1) % self.world_size) * self.item_block
+
     def take_users(self, x_users: torch.Tensor, rank: int) -> torch.Tensor:
         return x_users[rank::self.world_size].contiguous()
 
     def local_csrs(self, full: NormAdjCSR, rank: int):
         """(A_u, A_i) cut out of the full [N, N] matrix (users first):
         A_u [n_users_local, items_padded]: this rank's user rows, columns = item index;
-        A_i [items_padded, n_users_local]: ALL item rows restricted to this rank's users, columns = local user row.
+        A_i [items_padded, n_users_local]: ALL item rows (rotated, see below) restricted to this rank's users, columns
+        = local user row.
         Entry order inside a row stays ascending (the chain order within a rank)."""
         G, U, dev = self.world_size, self.n_users, full.indptr.device
         ip = full.indptr.long()
@@ -546,9 +551,20 @@ class BipartitePartition:
         iptr = torch.zeros(self.items_padded + 1, dtype=torch.int64, device=dev)
         iptr[: self.n_items + 1] = csum[ip[U:] - lo]
         iptr[self.n_items + 1:] = iptr[self.n_items]
-        a_i = NormAdjCSR(iptr.to(torch.int32), (seg_cols[mine] // G).to(torch.int32).contiguous(),
-                         full.vals[lo:][mine].contiguous(), self.items_padded, self.n_users_local(rank),
-                         long_threshold=full.long_threshold)
+        cols_i = (seg_cols[mine] // G).to(torch.int32)
+        vals_i = full.vals[lo:][mine]
+        # Rows ROTATED so that local row rho is item (rho + shift) mod I_pad, shift = start of the NEXT rank's block:
+        # all ranks walk their rows in ascending order, and without the rotation they would all push to rank 0's
+        # staging buffer first, then all to rank 1's, ... (measured on 8 GPUs: 10 ms per layer of NVLink ingress
+        # hot-spotting); rotated, at any moment the G senders target G different owners.
+        shift = self.item_shift(rank)
+        cut = int(iptr[shift].item())
+        counts = iptr[1:] - iptr[:-1]
+        rptr = torch.zeros_like(iptr)
+        torch.cumsum(torch.cat([counts[shift:], counts[:shift]]), 0, out=rptr[1:])
+        a_i = NormAdjCSR(rptr.to(torch.int32), torch.cat([cols_i[cut:], cols_i[:cut]]).contiguous(),
+                         torch.cat([vals_i[cut:], vals_i[:cut]]).contiguous(), self.items_padded,
+                         self.n_users_local(rank), long_threshold=full.long_threshold)
         return a_u, a_i
 
 
@@ -617,6 +633,14 @@ class EmulatedItemExchange:
         pass
 
 
+def _rotated(ptrs, rank: int, world: int):
+    """Peer pointer table in the order rank+1, rank+2, ..., rank: entry k is the owner of the k-th block of rank's
+    rotated A_i rows."""
+    import ctypes
+
+    return (ctypes.c_void_p * world)(*[ptrs[(k + rank + 1) % world] for k in range(world)])
+
+
 def _slot_ptrs(partial: torch.Tensor, part: "BipartitePartition"):
     """The G slots of a rank's staging buffer: slot k = rows [k*Ib, (k+1)*Ib) = the partial rows of this rank's item
     block pushed by rank k."""
@@ -674,7 +698,8 @@ def _propagate_user_owner_steps(a_u: NormAdjCSR, a_i: NormAdjCSR, ex, xu0: torch
         nxt = cur ^ 1
         # (2) partial sums of ALL item rows over this rank's users, each row pushed from the SpMM epilogue straight
         #     into slot `rank` of the staging buffer of the rank that owns the row's item block (routed P2P stores)
-        a_i.spmm(xu, want_y=False, peers=(ex.partial_ptrs, G, rank * part.item_block, d, 0, part.item_block))
+        a_i.spmm(xu, want_y=False, peers=(_rotated(ex.partial_ptrs, rank, G), G, rank * part.item_block, d, 0,
+                                          part.item_block))
         yield "partials"                                     # every rank's staging buffer is complete
         # (3) reduce my item block over the ranks' partials, broadcast it into every T[nxt], fold into the layer sum
         side = None if os.environ.get("GR_UO_SERIAL", "0") == "1" else ex.comm_stream
