@@ -13,6 +13,8 @@
 //     folds v into the running layer sum of its own block   (out = scale_op(addend + v))
 // Per layer a rank sends 2 x (G-1)/G x I x 4d bytes instead of the (G-1)/G x N x 4d of the exact all-gather:
 // 4.5 GB instead of 11.2 GB at C5 on 8 GPUs.
+#include <cstdlib>
+
 #include "gr_common.cuh"
 
 namespace gr {
@@ -139,7 +141,11 @@ extern "C" int gr_reduce_bcast_rows(const float *const *src_host, int32_t n_src,
     a.scale = scale; a.scale_mode = scale_mode;
     const long long total = n_rows * (d / 4);
     long long blocks = (total + 256 * 2 - 1) / (256 * 2);
-    const long long cap = (long long)sm_count() * 8;
+    // NVLink-bound, and meant to run BESIDE the user-row SpMM: a persistent grid that filled every thread slot
+    // (8 CTAs per SM) kept the SpMM's CTAs out until it retired (measured: no overlap at all).  One CTA per SM
+    // keeps ~19 MB of peer stores in flight, far more than the links need.
+    static const int per_sm = [] { const char *e = getenv("GR_REDUCE_CTAS_PER_SM"); int v = e ? atoi(e) : 1; return v > 0 ? v : 1; }();
+    const long long cap = (long long)sm_count() * per_sm;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     reduce_bcast_rows_kernel<2><<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);

@@ -966,7 +966,7 @@ extern "C" int gr_peer_scatter_rows(const float *src, int64_t lds, int64_t n_row
     }
     const long long total = n_rows * (d / 4);
     long long blocks = (total + 255) / 256;
-    const long long cap = (long long)sm_count() * 16;
+    const long long cap = (long long)sm_count() * 2;     // NVLink-bound; leaves the SMs to a concurrent SpMM
     if (blocks > cap) blocks = cap;
     peer_scatter_rows_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<const float4 *>(src), lds / 4, n_rows, d / 4, a);

@@ -678,21 +678,25 @@ def _propagate_user_owner_steps(a_u: NormAdjCSR, a_i: NormAdjCSR, ex, xu0: torch
         result["users"], result["items"] = xu0.clone(), xi0_block[:nb].clone()
         return
     dev = xu0.device
-    # layer-0 item table: every rank broadcasts its block (peer stores)
-    yield "enter"                                            # nobody still reads T[0] / P from a previous call
+    yield "enter"                                            # nobody still reads the tables / staging from a previous call
     cur = 0
-    if nb > 0:
-        with torch.cuda.device(dev):
-            check(lib().gr_peer_scatter_rows(ptr(xi0_block), xi0_block.stride(0), nb, d, ex.table_ptrs[cur], G, 0, d, lo,
-                                             stream_ptr()), "gr_peer_scatter_rows")
-    yield "table0"
+    main = torch.cuda.current_stream(dev)
+    side0 = None if os.environ.get("GR_UO_SERIAL", "0") == "1" else ex.comm_stream
+    # layer-0 item table: every rank broadcasts its block (peer stores) — on the comm stream, beside the first
+    # partial-sum SpMM (which only needs this rank's user rows)
+    if side0 is not None:
+        side0.wait_stream(main)
+    with (torch.cuda.stream(side0) if side0 is not None else _NullCtx()):
+        if nb > 0:
+            with torch.cuda.device(dev):
+                check(lib().gr_peer_scatter_rows(ptr(xi0_block), xi0_block.stride(0), nb, d, ex.table_ptrs[cur], G, 0, d,
+                                                 lo, stream_ptr()), "gr_peer_scatter_rows")
     acc_u = torch.empty_like(xu0)
     out_u = torch.empty_like(xu0)
     acc_i = torch.empty((max(nb, 1), d), dtype=torch.float32, device=dev)
     out_i = torch.empty((max(nb, 1), d), dtype=torch.float32, device=dev)
     xu = xu0
     xu_next = [torch.empty_like(xu0), torch.empty_like(xu0)]
-    main = torch.cuda.current_stream(dev)
     for l in range(L):
         last = l == L - 1
         nxt = cur ^ 1
@@ -700,7 +704,9 @@ def _propagate_user_owner_steps(a_u: NormAdjCSR, a_i: NormAdjCSR, ex, xu0: torch
         #     into slot `rank` of the staging buffer of the rank that owns the row's item block (routed P2P stores)
         a_i.spmm(xu, want_y=False, peers=(_rotated(ex.partial_ptrs, rank, G), G, rank * part.item_block, d, 0,
                                           part.item_block))
-        yield "partials"                                     # every rank's staging buffer is complete
+        if l == 0 and side0 is not None:
+            main.wait_stream(side0)                          # the layer-0 table broadcast
+        yield "partials"                                     # every rank's staging buffer (and T[0]) is complete
         # (3) reduce my item block over the ranks' partials, broadcast it into every T[nxt], fold into the layer sum
         side = None if os.environ.get("GR_UO_SERIAL", "0") == "1" else ex.comm_stream
         if side is not None:
