@@ -44,6 +44,9 @@ __device__ __forceinline__ float act_apply(float z, int act, float slope) {
     return z;
 }
 
+// NG = number of 16-float4 column groups a thread owns: 1 for d_out <= 64 (16 accumulators per map: ~64 registers,
+// several CTAs per SM so that one CTA's staging overlaps another's FFMA loop), 2 / 4 for d_out <= 128 / 256.
+template <int NG>
 __global__ void __launch_bounds__(256) rowmap_kernel(const RowMapArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int d_in = a.d_in, d_out = a.d_out;
@@ -60,8 +63,11 @@ __global__ void __launch_bounds__(256) rowmap_kernel(const RowMapArgs a) {
         if (has_b) reinterpret_cast<float4 *>(Wb)[i] = __ldg(reinterpret_cast<const float4 *>(a.wb) + i);
     }
     const int f4 = d_in / 4;
+    // lane -> row (consecutive lanes stage consecutive rows): the transposed stores Xs[k][r] then hit 32
+    // different banks; with lane -> column they were 16-way conflicted (measured: the staging cost as much as
+    // the FFMA loop)
     for (int i = tid; i < RM_ROWS * f4; i += 256) {
-        const int r = i / f4, f = i % f4;
+        const int r = i % RM_ROWS, f = i / RM_ROWS;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f), y = v;
         if (row0 + r < a.n_rows) {
             v = __ldg(reinterpret_cast<const float4 *>(a.x1 + (long long)(row0 + r) * a.ld1) + f);
@@ -85,11 +91,11 @@ __global__ void __launch_bounds__(256) rowmap_kernel(const RowMapArgs a) {
     __syncthreads();
 
     const int nc4 = d_out / 4;  // float4 column groups; thread tx owns groups tx, tx+16, tx+32, tx+48
-    float accA[4][4][4], accB[4][4][4];
+    float accA[4][NG][4], accB[4][NG][4];
 #pragma unroll
     for (int m = 0; m < 4; ++m)
 #pragma unroll
-        for (int g = 0; g < 4; ++g)
+        for (int g = 0; g < NG; ++g)
 #pragma unroll
             for (int c = 0; c < 4; ++c) accA[m][g][c] = accB[m][g][c] = 0.f;
 
@@ -102,7 +108,7 @@ __global__ void __launch_bounds__(256) rowmap_kernel(const RowMapArgs a) {
             ym[0] = yv.x; ym[1] = yv.y; ym[2] = yv.z; ym[3] = yv.w;
         }
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
+        for (int g = 0; g < NG; ++g) {
             const int cg = tx + 16 * g;
             if (cg < nc4) {
                 const float4 w = *reinterpret_cast<const float4 *>(Wa + (size_t)k * d_out + cg * 4);
@@ -123,7 +129,7 @@ __global__ void __launch_bounds__(256) rowmap_kernel(const RowMapArgs a) {
         }
     }
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
+    for (int g = 0; g < NG; ++g) {
         const int cg = tx + 16 * g;
         if (cg >= nc4) continue;
         float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bb = ba;
@@ -187,8 +193,18 @@ extern "C" int gr_rowmap_f32(const float *x1, int64_t ld1, const float *wa, cons
     a.drop_seed_dev = reinterpret_cast<const unsigned long long *>(drop_seed_dev);
     const size_t smem = ((size_t)d_in * d_out + (size_t)d_in * RM_ROWS) * 4 * (wb ? 2 : 1);
     if (smem > 227 * 1024) return GR_ERR_UNSUPPORTED;
-    GR_CUDA_CHECK(cudaFuncSetAttribute(rowmap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    rowmap_kernel<<<(unsigned)((n_rows + RM_ROWS - 1) / RM_ROWS), 256, smem, static_cast<cudaStream_t>(stream)>>>(a);
+    const unsigned grid = (unsigned)((n_rows + RM_ROWS - 1) / RM_ROWS);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (d_out <= 64) {
+        GR_CUDA_CHECK(cudaFuncSetAttribute(rowmap_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        rowmap_kernel<1><<<grid, 256, smem, st>>>(a);
+    } else if (d_out <= 128) {
+        GR_CUDA_CHECK(cudaFuncSetAttribute(rowmap_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        rowmap_kernel<2><<<grid, 256, smem, st>>>(a);
+    } else {
+        GR_CUDA_CHECK(cudaFuncSetAttribute(rowmap_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        rowmap_kernel<4><<<grid, 256, smem, st>>>(a);
+    }
     GR_LAUNCH_CHECK();
     return GR_OK;
 }
