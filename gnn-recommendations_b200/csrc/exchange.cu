@@ -152,3 +152,15 @@ extern "C" int gr_reduce_bcast_rows(const float *const *src_host, int32_t n_src,
     GR_LAUNCH_CHECK();
     return GR_OK;
 }
+
+/* Asynchronous copy between device buffers that may live on different GPUs of the box (peer-mapped symmetric
+ * memory): plain cudaMemcpyAsync, i.e. the COPY ENGINES move the bytes over NVLink and no SM is involved — the
+ * user-owner propagation sends its partial item blocks and broadcasts the reduced blocks this way, beside the
+ * SpMM kernels (an SM kernel doing the same stores took a third of the register file of every SM it ran on and
+ * slowed the HBM-bound SpMM by as much as it saved). */
+extern "C" int gr_peer_copy_async(void *dst, const void *src, size_t bytes, void *stream) {
+    if ((!dst || !src) && bytes) return GR_ERR_INVALID;
+    if (bytes == 0) return GR_OK;
+    GR_CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, static_cast<cudaStream_t>(stream)));
+    return GR_OK;
+}

@@ -596,9 +596,11 @@ class ItemExchange:
             self.tables.append(t)
             self.table_ptrs.append(arr)
             self.handles.append(h)
-        self.partial, self.partial_handle, self.partial_ptrs = alloc()
+        self.partial, self.partial_handle, self.partial_ptrs = alloc()          # staging: G slots of Ib rows
         self.slot_ptrs = _slot_ptrs(self.partial, part)
-        self.comm_stream = torch.cuda.Stream(device)
+        self.partial_local = torch.empty((part.items_padded, d), dtype=torch.float32, device=device)
+        n_copy = int(os.environ.get("GR_UO_COPY_STREAMS", str(self.world)))
+        self.copy_streams = [torch.cuda.Stream(device) for _ in range(max(0, n_copy))]
         torch.cuda.synchronize(device)
         dist.barrier(self.group)
 
@@ -618,7 +620,8 @@ class EmulatedItemExchange:
         self._partials = [torch.zeros((part.items_padded, d), device=device) for _ in range(G)]
         self.table_ptrs = [(ctypes.c_void_p * G)(*[t.data_ptr() for t in self._tables[k]]) for k in range(2)]
         self.partial_ptrs = (ctypes.c_void_p * G)(*[t.data_ptr() for t in self._partials])
-        self.comm_stream = None
+        self._partial_local = [torch.zeros((part.items_padded, d), device=device) for _ in range(G)]
+        self.copy_streams = []
 
     def view(self, rank: int):
         ex = EmulatedItemExchange.__new__(EmulatedItemExchange)
@@ -627,18 +630,11 @@ class EmulatedItemExchange:
         ex.tables = [self._tables[0][rank], self._tables[1][rank]]
         ex.partial = self._partials[rank]
         ex.slot_ptrs = _slot_ptrs(ex.partial, self.part)
+        ex.partial_local = self._partial_local[rank]
         return ex
 
     def barrier(self):
         pass
-
-
-def _rotated(ptrs, rank: int, world: int):
-    """Peer pointer table in the order rank+1, rank+2, ..., rank: entry k is the owner of the k-th block of rank's
-    rotated A_i rows."""
-    import ctypes
-
-    return (ctypes.c_void_p * world)(*[ptrs[(k + rank + 1) % world] for k in range(world)])
 
 
 def _slot_ptrs(partial: torch.Tensor, part: "BipartitePartition"):
@@ -662,15 +658,31 @@ def _reduce_bcast(ex, row0: int, n_rows: int, d: int, dst_ptrs, n_dst: int, adde
                                          stream_ptr()), "gr_reduce_bcast_rows")
 
 
+def _copy_async(dst_ptr: int, src_ptr: int, nbytes: int, device):
+    from ._lib import check, lib, stream_ptr
+
+    if nbytes > 0:
+        with torch.cuda.device(device):
+            check(lib().gr_peer_copy_async(dst_ptr, src_ptr, nbytes, stream_ptr()), "gr_peer_copy_async")
+
+
 def _propagate_user_owner_steps(a_u: NormAdjCSR, a_i: NormAdjCSR, ex, xu0: torch.Tensor, xi0_block: torch.Tensor,
                                 n_layers: int, result: dict):
     """Generator: one rank's LightGCN propagation in the user-owner layout; yields at every point where all
     ranks must have arrived (cross-rank barrier).  ``xu0`` [n_users_local, d]: the rank's user rows;
     ``xi0_block`` [item block rows, d]: the rank's block of the item table.  result['users'] / ['items'] receive
-    mean_l of the rank's user rows / item block."""
-    from ._lib import check, lib, ptr, stream_ptr
+    mean_l of the rank's user rows / item block.
 
+    Per layer l (main stream = SpMM kernels, copy streams = cudaMemcpyAsync over NVLink, no SM involved):
+        main   P = A_i x_u(l)                     partial sums of ALL item rows, written locally
+        copy   block g of P  ->  slot `rank` of rank g's staging buffer        (G-1 copies, beside the next SpMM)
+        main   x_u(l+1) = A_u T(l)                this rank's users from the replicated item table
+        ---- barrier: every staging buffer is complete
+        main   block = slot_0 + slot_1 + ... (rank order) -> own rows of T(l+1), layer sum     (local reduce)
+        copy   own block  ->  rows [lo, hi) of every other rank's T(l+1)        (G-1 copies, beside the next A_i SpMM)
+        ---- barrier (before the next A_u SpMM): every T(l+1) is complete"""
     part, d, rank, G = ex.part, xu0.shape[1], ex.rank, ex.world
+    Ib = part.item_block
     lo, hi = part.item_range(rank)
     nb = hi - lo
     L = n_layers
@@ -678,48 +690,63 @@ def _propagate_user_owner_steps(a_u: NormAdjCSR, a_i: NormAdjCSR, ex, xu0: torch
         result["users"], result["items"] = xu0.clone(), xi0_block[:nb].clone()
         return
     dev = xu0.device
-    yield "enter"                                            # nobody still reads the tables / staging from a previous call
-    cur = 0
+    row_bytes = d * 4
     main = torch.cuda.current_stream(dev)
-    side0 = None if os.environ.get("GR_UO_SERIAL", "0") == "1" else ex.comm_stream
-    # layer-0 item table: every rank broadcasts its block (peer stores) — on the comm stream, beside the first
-    # partial-sum SpMM (which only needs this rank's user rows)
-    if side0 is not None:
-        side0.wait_stream(main)
-    with (torch.cuda.stream(side0) if side0 is not None else _NullCtx()):
-        if nb > 0:
-            with torch.cuda.device(dev):
-                check(lib().gr_peer_scatter_rows(ptr(xi0_block), xi0_block.stride(0), nb, d, ex.table_ptrs[cur], G, 0, d,
-                                                 lo, stream_ptr()), "gr_peer_scatter_rows")
+    serial = os.environ.get("GR_UO_SERIAL", "0") == "1" or not ex.copy_streams
+    streams = [main] * G if serial else [ex.copy_streams[k % len(ex.copy_streams)] for k in range(G)]
+    pending = []                                     # copy streams with work the main stream has not waited for
+
+    def fan_out(copies):
+        """copies: (peer k, dst ptr, src ptr, bytes); each on its own copy stream, after what main has enqueued."""
+        ev = None if serial else torch.cuda.Event()
+        if ev is not None:
+            ev.record(main)
+        for k, dst, src, nbytes in copies:
+            st = streams[k]
+            if st is not main:
+                st.wait_event(ev)
+                pending.append(st)
+            with (torch.cuda.stream(st) if st is not main else _NullCtx()):
+                _copy_async(dst, src, nbytes, dev)
+
+    def join():
+        for st in pending:
+            main.wait_stream(st)
+        pending.clear()
+
+    yield "enter"                                    # nobody still reads the tables / staging from a previous call
+    cur = 0
+    # layer-0 item table: own block into every rank's T[0] (own copy on main, the others by the copy engines)
+    src0 = xi0_block.contiguous()
+    fan_out([(k, int(ex.table_ptrs[cur][k]) + lo * row_bytes, src0.data_ptr(), nb * row_bytes) for k in range(G)])
     acc_u = torch.empty_like(xu0)
     out_u = torch.empty_like(xu0)
     acc_i = torch.empty((max(nb, 1), d), dtype=torch.float32, device=dev)
     out_i = torch.empty((max(nb, 1), d), dtype=torch.float32, device=dev)
     xu = xu0
     xu_next = [torch.empty_like(xu0), torch.empty_like(xu0)]
+    p_local = ex.partial_local                       # [items_padded, d], rows in A_i's rotated order
+    shift_blocks = (rank + 1) % G
     for l in range(L):
         last = l == L - 1
         nxt = cur ^ 1
-        # (2) partial sums of ALL item rows over this rank's users, each row pushed from the SpMM epilogue straight
-        #     into slot `rank` of the staging buffer of the rank that owns the row's item block (routed P2P stores)
-        a_i.spmm(xu, want_y=False, peers=(_rotated(ex.partial_ptrs, rank, G), G, rank * part.item_block, d, 0,
-                                          part.item_block))
-        if l == 0 and side0 is not None:
-            main.wait_stream(side0)                          # the layer-0 table broadcast
-        yield "partials"                                     # every rank's staging buffer (and T[0]) is complete
-        # (3) reduce my item block over the ranks' partials, broadcast it into every T[nxt], fold into the layer sum
-        side = None if os.environ.get("GR_UO_SERIAL", "0") == "1" else ex.comm_stream
-        if side is not None:
-            side.wait_stream(main)
-        ctx = torch.cuda.stream(side) if side is not None else _NullCtx()
-        with ctx:
-            if nb > 0:
-                addend = xi0_block if l == 0 else acc_i
-                if last:
-                    _reduce_bcast(ex, lo, nb, d, None, 0, addend, out_i, float(L + 1), _lib.GR_SCALE_DIV)
-                else:
-                    _reduce_bcast(ex, lo, nb, d, ex.table_ptrs[nxt], G, addend, acc_i, 1.0, _lib.GR_SCALE_NONE)
-        # (1) this rank's users from the replicated item table of layer l — overlaps (3)
+        # (a) partial sums of ALL item rows over this rank's users (rotated row order: block k of P is item block
+        #     (k + rank + 1) mod G)
+        a_i.spmm(xu, y=p_local, want_y=True)
+        if l > 0:
+            join()                                   # the broadcast of T[cur] (this rank's copies) has been issued...
+            yield "table"                            # ... and everybody's has landed: T[cur] is complete
+        else:
+            join()
+            yield "table0"
+        # (b) push block k of P to its owner's staging slot `rank` (copy engines), beside (c)
+        copies = []
+        for k in range(G):
+            owner = (k + shift_blocks) % G
+            copies.append((owner, int(ex.partial_ptrs[owner]) + rank * Ib * row_bytes,
+                           p_local.data_ptr() + k * Ib * row_bytes, Ib * row_bytes))
+        fan_out(copies)
+        # (c) this rank's users from the replicated item table of layer l
         addend_u = xu0 if l == 0 else acc_u
         if last:
             a_u.spmm(ex.tables[cur], addend=addend_u, out=out_u, scale=float(L + 1), scale_mode=_lib.GR_SCALE_DIV,
@@ -727,12 +754,28 @@ def _propagate_user_owner_steps(a_u: NormAdjCSR, a_i: NormAdjCSR, ex, xu0: torch
         else:
             a_u.spmm(ex.tables[cur], y=xu_next[l & 1], addend=addend_u, out=acc_u)
             xu = xu_next[l & 1]
-        if side is not None:
-            main.wait_stream(side)
+        join()
+        yield "partials"                             # every rank's staging buffer is complete
+        # (d) local reduce of the G slots (rank order) -> own rows of T[nxt] + layer sum; (e) broadcast by copies
+        if nb > 0:
+            addend = xi0_block if l == 0 else acc_i
+            if last:
+                _reduce_bcast(ex, lo, nb, d, None, 0, addend, out_i, float(L + 1), _lib.GR_SCALE_DIV)
+            else:
+                own = (ctypes_array([int(ex.table_ptrs[nxt][rank])]), 1)
+                _reduce_bcast(ex, lo, nb, d, own[0], 1, addend, acc_i, 1.0, _lib.GR_SCALE_NONE)
         if not last:
-            yield "table"                                    # every rank's stores into T[nxt] have landed
+            src = int(ex.table_ptrs[nxt][rank]) + lo * row_bytes
+            fan_out([(k, int(ex.table_ptrs[nxt][k]) + lo * row_bytes, src, nb * row_bytes) for k in range(G) if k != rank])
             cur = nxt
+    join()
     result["users"], result["items"] = out_u, out_i[:nb]
+
+
+def ctypes_array(ptrs):
+    import ctypes
+
+    return (ctypes.c_void_p * len(ptrs))(*ptrs)
 
 
 class _NullCtx:

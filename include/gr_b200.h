@@ -172,6 +172,11 @@ int gr_reduce_bcast_rows(const float *const *src_host, int32_t n_src, int64_t ld
                          const float *addend, int64_t lda, float *out, int64_t ldo, float *own, int64_t ldw,
                          float scale, int32_t scale_mode, void *stream);
 
+/* cudaMemcpyAsync between device buffers of this box (local or peer-mapped): the copy engines move the bytes over
+ * NVLink, no SM is involved.  Used by the user-owner propagation for the partial-block pushes and the reduced-block
+ * broadcasts, which run beside the SpMM kernels. */
+int gr_peer_copy_async(void *dst, const void *src, size_t bytes, void *stream);
+
 /* Per-row dense epilogue shared by the NGCF, Group-and-Shuffle and GAT layers:
  *     out = alpha * act( X1 Wa + bias_a  +  (X2 * X3) Wb + bias_b ) + beta * R
  * Wa, Wb: [d_in, d_out] row-major (i.e. nn.Linear.weight TRANSPOSED); the (X2*X3) term, the

@@ -433,3 +433,25 @@ def test_user_owner_propagation_matches_single_gpu(shape, world, d, L):
         assert a_u.nnz == a_i.nnz                                          # each owned edge: once per direction
         nnz += a_u.nnz + a_i.nnz
     assert nnz == full.nnz
+
+
+def test_spmm_routed_peer_stores(tiny_ref):
+    """gr_spmm_csr_f32 routed mode: row r is stored to ONE peer buffer, g = r / route_block, at row
+    offset + r % route_block (the push variant of the user-owner exchange); here the 'peers' are G buffers on one GPU,
+    incl. long rows (long_threshold 16) and the empty tail rows."""
+    import ctypes
+    full = g.NormAdjCSR.from_pairs(tiny_ref["rows"][tiny_ref["rows"] < 300], tiny_ref["indices"][tiny_ref["rows"] < 300] - 300,
+                                   300, 200, device=DEV)
+    csr = g.NormAdjCSR(full.indptr, full.indices, full.vals, full.n_rows, full.n_cols, long_threshold=16)
+    assert csr.n_long > 0
+    x = torch.randn(csr.n_cols, 64, generator=torch.Generator().manual_seed(0)).to(DEV)
+    want = csr.spmm(x)[0]
+    G, blk, slot = 4, 128, 2                                      # 500 rows -> blocks of 128 rows over 4 'ranks'
+    bufs = [torch.full((G * blk, 64), float("nan"), device=DEV) for _ in range(G)]
+    ptrs = (ctypes.c_void_p * G)(*[b.data_ptr() for b in bufs])
+    csr.spmm(x, want_y=False, peers=(ptrs, G, slot * blk, 64, 0, blk))
+    torch.cuda.synchronize()
+    for k in range(G):
+        rows = want[k * blk: min((k + 1) * blk, csr.n_rows)]
+        assert torch.equal(bufs[k][slot * blk: slot * blk + rows.shape[0]], rows)
+        assert torch.isnan(bufs[k][: slot * blk]).all()            # nothing else touched
