@@ -37,6 +37,7 @@ SIGNATURES = {
     "gr_reduce_bcast_rows": (C.c_int, [_p, _i32, _i64, _p, _i32, _i64, _i64, _i64, _i64, _i32, _p, _i64, _p, _i64, _p,
                                        _i64, _f32, _i32, _p]),
     "gr_peer_copy_async": (C.c_int, [_p, _p, _sz, _p]),
+    "gr_peer_copy_multi": (C.c_int, [_p, _p, _p, _i32, _i32, _p]),
     "gr_rowmap_f32": (C.c_int, [_p, _i64, _p, _p, _p, _i64, _p, _i64, _p, _p, _p, _i64, _f32, _f32, _i32, _f32,
                                 _i64, _i32, _i32, _f32, _u64, _p, _p, _i64, _p]),
     "gr_rowmap_bwd_workspace_bytes": (_sz, [_i64, _i32, _i32, _i32]),

@@ -153,6 +153,56 @@ extern "C" int gr_reduce_bcast_rows(const float *const *src_host, int32_t n_src,
     return GR_OK;
 }
 
+namespace gr {
+struct MultiCopyArgs {
+    float4 *dst[kMaxRanks];
+    const float4 *src[kMaxRanks];
+    long long n4[kMaxRanks];     // float4 elements per segment
+    int n_seg, parts;            // CTAs per segment
+};
+
+// Up to 8 independent copies (local -> local or peer-mapped memory) in ONE small launch: CTA b works on part
+// b / n_seg of segment b % n_seg, 4 independent 16-byte loads in flight per thread, plain stores (posted writes
+// over NVLink).  ~30 registers and a few dozen CTAs: it runs beside an SpMM without taking its occupancy.
+__global__ void __launch_bounds__(256) peer_copy_multi_kernel(const MultiCopyArgs a) {
+    const int seg = blockIdx.x % a.n_seg, part = blockIdx.x / a.n_seg;
+    const long long n = a.n4[seg];
+    const long long per = (n + a.parts - 1) / a.parts;
+    const long long begin = per * part, end = min(n, begin + per);
+    const float4 *src = a.src[seg];
+    float4 *dst = a.dst[seg];
+    long long i = begin + threadIdx.x;
+    for (; i + 3 * 256 < end; i += 4 * 256) {
+        const float4 v0 = __ldg(src + i), v1 = __ldg(src + i + 256), v2 = __ldg(src + i + 512), v3 = __ldg(src + i + 768);
+        dst[i] = v0; dst[i + 256] = v1; dst[i + 512] = v2; dst[i + 768] = v3;
+    }
+    for (; i < end; i += 256) dst[i] = __ldg(src + i);
+}
+}  // namespace gr
+
+extern "C" int gr_peer_copy_multi(void *const *dst_host, const void *const *src_host, const size_t *bytes_host,
+                                  int32_t n_seg, int32_t ctas, void *stream) {
+    if (!dst_host || !src_host || !bytes_host || n_seg < 1 || n_seg > kMaxRanks) return GR_ERR_INVALID;
+    MultiCopyArgs a = {};
+    int n = 0;
+    for (int s = 0; s < n_seg; ++s) {
+        if (bytes_host[s] == 0) continue;
+        if (!dst_host[s] || !src_host[s] || (bytes_host[s] & 15) || !aligned16(dst_host[s]) || !aligned16(src_host[s]))
+            return GR_ERR_INVALID;
+        a.dst[n] = static_cast<float4 *>(dst_host[s]);
+        a.src[n] = static_cast<const float4 *>(src_host[s]);
+        a.n4[n] = (long long)(bytes_host[s] / 16);
+        ++n;
+    }
+    if (n == 0) return GR_OK;
+    a.n_seg = n;
+    if (ctas < n) ctas = n;
+    a.parts = ctas / n;
+    peer_copy_multi_kernel<<<a.parts * n, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    GR_LAUNCH_CHECK();
+    return GR_OK;
+}
+
 /* Asynchronous copy between device buffers that may live on different GPUs of the box (peer-mapped symmetric
  * memory): plain cudaMemcpyAsync, i.e. the COPY ENGINES move the bytes over NVLink and no SM is involved — the
  * user-owner propagation sends its partial item blocks and broadcasts the reduced blocks this way, beside the

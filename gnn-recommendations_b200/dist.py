@@ -696,11 +696,34 @@ def _propagate_user_owner_steps(a_u: NormAdjCSR, a_i: NormAdjCSR, ex, xu0: torch
     streams = [main] * G if serial else [ex.copy_streams[k % len(ex.copy_streams)] for k in range(G)]
     pending = []                                     # copy streams with work the main stream has not waited for
 
+    copy_mode = os.environ.get("GR_UO_COPY", "sm")
+    copy_ctas = int(os.environ.get("GR_UO_COPY_CTAS", "64"))
+
     def fan_out(copies):
-        """copies: (peer k, dst ptr, src ptr, bytes); each on its own copy stream, after what main has enqueued."""
+        """copies: (peer k, dst ptr, src ptr, bytes), issued after what main has enqueued so far: 'sm' = one small
+        multi-copy kernel on a side stream (gr_peer_copy_multi), 'dma' = one cudaMemcpyAsync per copy, each on its
+        own copy stream (copy engines)."""
         ev = None if serial else torch.cuda.Event()
         if ev is not None:
             ev.record(main)
+        if copy_mode == "sm":
+            import ctypes
+
+            from ._lib import check, lib, stream_ptr
+            live = [c for c in copies if c[3] > 0]
+            if not live:
+                return
+            st = main if serial else ex.copy_streams[0]
+            if st is not main:
+                st.wait_event(ev)
+                pending.append(st)
+            n = len(live)
+            dsts = (ctypes.c_void_p * n)(*[c[1] for c in live])
+            srcs = (ctypes.c_void_p * n)(*[c[2] for c in live])
+            sizes = (ctypes.c_size_t * n)(*[c[3] for c in live])
+            with (torch.cuda.stream(st) if st is not main else _NullCtx()), torch.cuda.device(dev):
+                check(lib().gr_peer_copy_multi(dsts, srcs, sizes, n, copy_ctas, stream_ptr()), "gr_peer_copy_multi")
+            return
         for k, dst, src, nbytes in copies:
             st = streams[k]
             if st is not main:

@@ -176,6 +176,10 @@ int gr_reduce_bcast_rows(const float *const *src_host, int32_t n_src, int64_t ld
  * NVLink, no SM is involved.  Used by the user-owner propagation for the partial-block pushes and the reduced-block
  * broadcasts, which run beside the SpMM kernels. */
 int gr_peer_copy_async(void *dst, const void *src, size_t bytes, void *stream);
+/* The same transfers by a small SM kernel: up to 8 (dst, src, bytes) segments in one launch of `ctas` CTAs (a few
+ * dozen; ~30 registers per thread), plain peer stores.  bytes multiples of 16, pointers 16-byte aligned. */
+int gr_peer_copy_multi(void *const *dst_host, const void *const *src_host, const size_t *bytes_host, int32_t n_seg,
+                       int32_t ctas, void *stream);
 
 /* Per-row dense epilogue shared by the NGCF, Group-and-Shuffle and GAT layers:
  *     out = alpha * act( X1 Wa + bias_a  +  (X2 * X3) Wb + bias_b ) + beta * R
