@@ -1,7 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
 i=0
-for v in "GR_UO_COPY=sm GR_UO_COPY_CTAS=64" "GR_UO_COPY=sm GR_UO_COPY_CTAS=128" "GR_UO_COPY=sm GR_UO_COPY_CTAS=32"; do
+for v in "GR_UO_COPY_CTAS=16" "GR_UO_COPY_CTAS=24"; do
 i=$((i+1))
 env $v timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 2952$i bench.py --gpus 8 --steps 10 --warmup 3 --no-cpu --no-e2e --no-extras > gpurun_out/r02_uo8_v$i.json 2> gpurun_out/r02_uo8_v$i.err
 python -c "
