@@ -44,6 +44,9 @@ SIGNATURES = {
     "gr_rowmap_bwd": (C.c_int, [_p, _i64, _p, _i64, _p, _i64, _p, _p, _i64, _p, _i64, _p, _p, _i64, _f32, _f32, _i32,
                                 _f32, _i64, _i32, _i32, _f32, _u64, _p, _p, _i64, _p, _i64, _p, _i64, _p, _i64, _p, _p,
                                 _sz, _p]),
+    "gr_layer_combine": (C.c_int, [_p, _p, _i32, _p, _i64, _i32, _p, _i64, _p]),
+    "gr_layer_combine_bwd_workspace_bytes": (_sz, []),
+    "gr_layer_combine_dw": (C.c_int, [_p, _p, _i32, _p, _i64, _i64, _i32, _p, _p, _sz, _p]),
     "gr_gs_compose": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _i32, _p, _p, _p]),
     "gr_gs_compose_bwd": (C.c_int, [_p, _p, _p, _p, _i32, _i32, _i32, _i32, _p, _p, _p, _p]),
     "gr_gat_node_scores": (C.c_int, [_p, _i64, _p, _p, _i64, _i32, _i32, _p, _p, _p]),

@@ -209,3 +209,144 @@ extern "C" int gr_rowmap_f32(const float *x1, int64_t ld1, const float *wa, cons
     return GR_OK;
 }
 
+
+// =============================================================================================
+// layer combination:  out = sum_l w_l * x_l   (GAT: mean of the L+1 layer outputs, gat.py:287-288;
+// Group-and-Shuffle: sum_l softmax(layer_weights)_l x_l, model.py:204-207) and its backward
+// =============================================================================================
+namespace gr {
+constexpr int LC_MAX = 8;
+struct CombineArgs {
+    const float4 *x[LC_MAX];
+    long long ld4[LC_MAX];
+    const float *w;        // device [n_in] weights, or NULL: out = (x_0 + x_1 + ...) / n_in (torch.mean of the stack)
+    int n_in;
+    long long n_rows;
+    int f4;
+    float4 *out;
+    long long ldo4;
+};
+
+// Forward.  Weighted: ((w0 x0) + (w1 x1)) + ... with separately rounded products, the order of the reference's
+// python sum(); mean: left-to-right sum divided by n_in.
+__global__ void __launch_bounds__(256) layer_combine_kernel(const CombineArgs a) {
+    const long long total = a.n_rows * a.f4;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    float w[LC_MAX];
+#pragma unroll
+    for (int l = 0; l < LC_MAX; ++l) w[l] = (a.w && l < a.n_in) ? __ldg(a.w + l) : 1.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const long long r = i / a.f4;
+        const int f = (int)(i % a.f4);
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int l = 0; l < LC_MAX; ++l)
+            if (l < a.n_in) {
+                const float4 v = __ldg(a.x[l] + r * a.ld4[l] + f);
+                if (a.w) {
+                    const float4 p = make_float4(__fmul_rn(w[l], v.x), __fmul_rn(w[l], v.y), __fmul_rn(w[l], v.z), __fmul_rn(w[l], v.w));
+                    s = l == 0 ? p : make_float4(__fadd_rn(s.x, p.x), __fadd_rn(s.y, p.y), __fadd_rn(s.z, p.z), __fadd_rn(s.w, p.w));
+                } else {
+                    s = l == 0 ? v : make_float4(__fadd_rn(s.x, v.x), __fadd_rn(s.y, v.y), __fadd_rn(s.z, v.z), __fadd_rn(s.w, v.w));
+                }
+            }
+        if (!a.w) {
+            const float n = (float)a.n_in;
+            s = make_float4(__fdiv_rn(s.x, n), __fdiv_rn(s.y, n), __fdiv_rn(s.z, n), __fdiv_rn(s.w, n));
+        }
+        a.out[r * a.ldo4 + f] = s;
+    }
+}
+
+// Backward of the weighted form: per-CTA partials of dw_l = <g, x_l> (double accumulation per thread, block tree),
+// reduced by launch_reduce_partials.  (dx_l = w_l g is the forward kernel with one input.)
+__global__ void __launch_bounds__(256) layer_combine_dw_kernel(const CombineArgs a, const float4 *g, long long ldg4,
+                                                               float *partial) {
+    __shared__ float red[LC_MAX][8];
+    const long long total = a.n_rows * a.f4;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    float acc[LC_MAX];
+#pragma unroll
+    for (int l = 0; l < LC_MAX; ++l) acc[l] = 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const long long r = i / a.f4;
+        const int f = (int)(i % a.f4);
+        const float4 gv = __ldg(g + r * ldg4 + f);
+#pragma unroll
+        for (int l = 0; l < LC_MAX; ++l)
+            if (l < a.n_in) {
+                const float4 v = __ldg(a.x[l] + r * a.ld4[l] + f);
+                acc[l] += gv.x * v.x + gv.y * v.y + gv.z * v.z + gv.w * v.w;
+            }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int l = 0; l < LC_MAX; ++l) {
+        float v = acc[l];
+#pragma unroll
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) red[l][warp] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < LC_MAX) {
+        float t = 0.f;
+        for (int w8 = 0; w8 < 8; ++w8) t += red[threadIdx.x][w8];
+        partial[(long long)blockIdx.x * LC_MAX + threadIdx.x] = t;
+    }
+}
+}  // namespace gr
+
+extern "C" int gr_layer_combine(const float *const *x_host, const int64_t *ld_host, int32_t n_in, const float *w_dev,
+                                int64_t n_rows, int32_t d, float *out, int64_t ldo, void *stream) {
+    if (!x_host || !ld_host || !out || n_in < 1 || n_in > LC_MAX || n_rows < 0 || d <= 0 || (d & 3)) return GR_ERR_INVALID;
+    if ((ldo & 3) || ldo < d || !aligned16(out)) return GR_ERR_INVALID;
+    if (n_rows == 0) return GR_OK;
+    CombineArgs a = {};
+    for (int l = 0; l < n_in; ++l) {
+        if (!x_host[l] || !aligned16(x_host[l]) || (ld_host[l] & 3) || ld_host[l] < d) return GR_ERR_INVALID;
+        a.x[l] = reinterpret_cast<const float4 *>(x_host[l]);
+        a.ld4[l] = ld_host[l] / 4;
+    }
+    a.w = w_dev; a.n_in = n_in; a.n_rows = n_rows; a.f4 = d / 4;
+    a.out = reinterpret_cast<float4 *>(out); a.ldo4 = ldo / 4;
+    const long long total = n_rows * (d / 4);
+    const int grid = persistent_grid((int)((total + 255) / 256 > 0x7fffffff ? 0x7fffffff : (total + 255) / 256), 8);
+    layer_combine_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    GR_LAUNCH_CHECK();
+    return GR_OK;
+}
+
+extern "C" size_t gr_layer_combine_bwd_workspace_bytes(void) { return (size_t)(kSmCountFallback * 4 + 64) * LC_MAX * 4 + 256; }
+
+extern "C" int gr_layer_combine_dw(const float *const *x_host, const int64_t *ld_host, int32_t n_in, const float *g,
+                                   int64_t ldg, int64_t n_rows, int32_t d, float *dw, void *workspace,
+                                   size_t workspace_bytes, void *stream) {
+    if (!x_host || !ld_host || !g || !dw || !workspace || n_in < 1 || n_in > LC_MAX || n_rows < 0 || d <= 0 || (d & 3))
+        return GR_ERR_INVALID;
+    if ((ldg & 3) || ldg < d || !aligned16(g) || !aligned16(workspace)) return GR_ERR_INVALID;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (n_rows == 0) {
+        GR_CUDA_CHECK(cudaMemsetAsync(dw, 0, LC_MAX * 4, st));
+        return GR_OK;
+    }
+    CombineArgs a = {};
+    for (int l = 0; l < n_in; ++l) {
+        if (!x_host[l] || !aligned16(x_host[l]) || (ld_host[l] & 3) || ld_host[l] < d) return GR_ERR_INVALID;
+        a.x[l] = reinterpret_cast<const float4 *>(x_host[l]);
+        a.ld4[l] = ld_host[l] / 4;
+    }
+    a.n_in = n_in; a.n_rows = n_rows; a.f4 = d / 4;
+    const long long total = n_rows * (d / 4);
+    int grid = persistent_grid((int)((total + 255) / 256 > 0x7fffffff ? 0x7fffffff : (total + 255) / 256), 4);
+    const size_t cap = (workspace_bytes - 256) / (LC_MAX * 4);
+    if ((size_t)grid > cap) grid = (int)cap;
+    if (grid < 1) return GR_ERR_WORKSPACE;
+    float *partial = static_cast<float *>(workspace);
+    layer_combine_dw_kernel<<<grid, 256, 0, st>>>(a, reinterpret_cast<const float4 *>(g), ldg / 4, partial);
+    GR_LAUNCH_CHECK();
+    if (launch_reduce_partials(partial, grid, LC_MAX, dw, st)) {      // dw: float[8], entries >= n_in are zero
+        set_last_cuda_error(cudaPeekAtLastError());
+        return GR_ERR_CUDA;
+    }
+    return GR_OK;
+}

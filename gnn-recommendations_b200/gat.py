@@ -18,7 +18,7 @@ import torch.nn as nn
 
 from .base import BaseRecommender
 from .graph_builder import as_csr
-from .layer_ops import gat_layer, new_dropout_seed
+from .layer_ops import gat_layer, layer_combine, new_dropout_seed
 
 
 class GATLayer(nn.Module):
@@ -76,7 +76,7 @@ class GAT(BaseRecommender):
         for layer in self.layers:
             x = layer(x, csr, elu=True)                       # ELU of gat.py:283 fused into the kernel
             outs.append(x)
-        return torch.mean(torch.stack(outs, dim=0), dim=0)
+        return layer_combine(outs)                            # torch.mean(torch.stack(outs)) of gat.py:287-288
 
     def forward(self, adj_matrix) -> Tuple[torch.Tensor, torch.Tensor]:
         x = self.propagate(adj_matrix)

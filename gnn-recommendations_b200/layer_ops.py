@@ -196,6 +196,70 @@ def rowmap(x1, wa, bias_a=None, x2=None, x3=None, wb=None, bias_b=None, resid=No
 
 
 # ------------------------------------------------------------------------------------------------
+# combination of the layer outputs (GAT: mean; Group-and-Shuffle: softmax-weighted sum)
+# ------------------------------------------------------------------------------------------------
+_INV_N = {}
+
+
+def _combine_raw(xs, w_dev, out=None):
+    n, d = xs[0].shape
+    if out is None:
+        out = torch.empty((n, d), dtype=torch.float32, device=xs[0].device)
+    k = len(xs)
+    ptrs = (C.c_void_p * k)(*[x.data_ptr() for x in xs])
+    lds = (C.c_int64 * k)(*[x.stride(0) for x in xs])
+    with torch.cuda.device(xs[0].device):
+        check(lib().gr_layer_combine(ptrs, lds, k, ptr(w_dev), n, d, ptr(out), out.stride(0), stream_ptr()),
+              "gr_layer_combine")
+    return out
+
+
+class _LayerCombine(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, weights, *xs):
+        xs = [_rows(x) for x in xs]
+        if len(xs) > 8:
+            raise ValueError("at most 8 layer outputs")
+        w = None if weights is None else weights.contiguous()
+        ctx.n = len(xs)
+        ctx.save_for_backward(w, *xs)
+        return _combine_raw(xs, w)
+
+    @staticmethod
+    def backward(ctx, g):
+        w, *xs = ctx.saved_tensors
+        g = _rows(g)
+        n, dev = ctx.n, g.device
+        if w is None:                                   # mean: every input gets g / n (one kernel, shared result)
+            key = (str(dev), n)
+            inv = _INV_N.get(key)
+            if inv is None:
+                inv = _INV_N[key] = torch.full((1,), 1.0 / n, dtype=torch.float32, device=dev)
+            gx = _combine_raw([g], inv)
+            return (None,) + tuple(gx if ctx.needs_input_grad[1 + l] else None for l in range(n))
+        dxs = tuple(_combine_raw([g], w[l:l + 1]) if ctx.needs_input_grad[1 + l] else None for l in range(n))
+        dw = None
+        if ctx.needs_input_grad[0]:
+            l_ = lib()
+            ws_bytes = l_.gr_layer_combine_bwd_workspace_bytes()
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            dw8 = torch.empty(8, dtype=torch.float32, device=dev)
+            ptrs = (C.c_void_p * n)(*[x.data_ptr() for x in xs])
+            lds = (C.c_int64 * n)(*[x.stride(0) for x in xs])
+            with torch.cuda.device(dev):
+                check(l_.gr_layer_combine_dw(ptrs, lds, n, ptr(g), g.stride(0), g.shape[0], g.shape[1], ptr(dw8), ptr(ws),
+                                             ws_bytes, stream_ptr()), "gr_layer_combine_dw")
+            dw = dw8[:n]
+        return (dw,) + dxs
+
+
+def layer_combine(xs: Sequence[torch.Tensor], weights: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """sum_l weights[l] * xs[l] (device weights, e.g. softmax(layer_weights): model.py:204-207) or, with
+    ``weights=None``, torch.mean(torch.stack(xs), 0) (gat.py:287-288) — one kernel each way (gr_layer_combine)."""
+    return _LayerCombine.apply(weights, *xs)
+
+
+# ------------------------------------------------------------------------------------------------
 # Group-and-Shuffle: the composed per-layer map M_l = W_conn,l W_orth,l[:, perm]
 # ------------------------------------------------------------------------------------------------
 class _GsCompose(torch.autograd.Function):

@@ -20,7 +20,7 @@ import torch.nn.functional as F
 
 from .base import BaseRecommender
 from .graph_builder import as_csr
-from .layer_ops import gs_compose, new_dropout_seed, rowmap, spmm
+from .layer_ops import gs_compose, layer_combine, new_dropout_seed, rowmap, spmm
 
 
 def _block_orthogonal(skew_params) -> torch.Tensor:
@@ -151,7 +151,7 @@ class OrthogonalBundleGNN(BaseRecommender):
     def propagate(self, adj_matrix=None, edge_index=None) -> torch.Tensor:
         outs = self._layers(adj_matrix, residual=True)
         w = F.softmax(self.layer_weights, dim=0)
-        return sum([wi * e for wi, e in zip(w, outs)])
+        return layer_combine(outs, w)                         # sum([w_l * x_l]) of model.py:204-207, one kernel
 
     def forward(self, adj_matrix=None, edge_index=None) -> Tuple[torch.Tensor, torch.Tensor]:
         x = self.propagate(adj_matrix, edge_index)

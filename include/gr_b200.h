@@ -218,6 +218,18 @@ int gr_rowmap_bwd(const float *g, int64_t ldg, const float *out, int64_t ldo, co
                   int64_t ldd1, float *dx2, int64_t ldd2, float *dx3, int64_t ldd3, float *dresid, int64_t lddr,
                   float *dw, void *workspace, size_t workspace_bytes, void *stream);
 
+/* Combination of the L+1 layer outputs:  out = sum_l w_l x_l  with the weights in device memory (Group-and-Shuffle:
+ * softmax(layer_weights), src/models/orthogonal_bundle/model.py:204-207; products rounded separately and added left
+ * to right like the reference's python sum()), or with w_dev = NULL  out = (x_0 + x_1 + ...) / n_in  (GAT:
+ * torch.mean(torch.stack(..)), src/models/baselines/gat.py:287-288).  x_host / ld_host: HOST arrays of n_in <= 8
+ * device pointers / leading dimensions.  gr_layer_combine_dw: dw[l] = <g, x_l> for the weighted form (dw: device
+ * float[8]; deterministic two-stage reduction); dx_l = w_l g is gr_layer_combine with one input. */
+int gr_layer_combine(const float *const *x_host, const int64_t *ld_host, int32_t n_in, const float *w_dev,
+                     int64_t n_rows, int32_t d, float *out, int64_t ldo, void *stream);
+size_t gr_layer_combine_bwd_workspace_bytes(void);
+int gr_layer_combine_dw(const float *const *x_host, const int64_t *ld_host, int32_t n_in, const float *g, int64_t ldg,
+                        int64_t n_rows, int32_t d, float *dw, void *workspace, size_t workspace_bytes, void *stream);
+
 /* Group-and-Shuffle orthogonal maps of OrthogonalBundleGNN, composed per layer on the device:
  *     M_l = blockdiag(exp(P_k - P_k^T))[:, perm_conn_l]  @  blockdiag(exp(Q_k - Q_k^T))[:, perm_local_l]
  * replacing BundleConnectionLayer.forward (src/models/orthogonal_bundle/bundle_layer.py:56-73),

@@ -496,3 +496,27 @@ def test_cuda_graph_step_with_dropout_models(tiny, tmp_path):
             runs.append((loss, m.user_embedding.weight.detach().cpu().clone()))
         assert abs(runs[0][0] - runs[1][0]) <= 1e-6 * abs(runs[0][0])
         torch.testing.assert_close(runs[0][1], runs[1][1], rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize("n_in,weighted", [(4, True), (4, False), (1, True), (5, False), (8, True)])
+def test_layer_combine_vs_torch(n_in, weighted):
+    """gr_layer_combine / gr_layer_combine_dw (GAT: mean of the layer outputs; Group-and-Shuffle: softmax-weighted
+    sum) against torch: forward bit-equal to the reference's own expressions, gradients to 1e-6."""
+    from gnn_recommendations_b200.layer_ops import layer_combine
+    gen = torch.Generator().manual_seed(n_in)
+    base = torch.randn(1000, 64 * n_in, generator=gen).to(DEV)
+    xs = [base[:, 64 * l:64 * (l + 1)].detach().requires_grad_(True) for l in range(n_in)]     # strided views
+    w = torch.softmax(torch.randn(n_in, generator=gen), 0).to(DEV).requires_grad_(True) if weighted else None
+    out = layer_combine(xs, w)
+    ref = sum([wi * e for wi, e in zip(w, xs)]) if weighted else torch.mean(torch.stack(xs, dim=0), dim=0)
+    if weighted:
+        assert torch.equal(out, ref)                               # same products, same order of additions
+    else:                                                          # the CPU reference's order: ((x0+x1)+x2)+... / n
+        cpu = torch.mean(torch.stack([x.detach().cpu() for x in xs], dim=0), dim=0)
+        assert torch.equal(out.cpu(), cpu)
+    gout = torch.randn(1000, 64, generator=gen).to(DEV)
+    leaves = xs + ([w] if weighted else [])
+    got = torch.autograd.grad(out, leaves, gout)
+    want = torch.autograd.grad(ref, leaves, gout)
+    for a, b in zip(got, want):
+        close(a.cpu().numpy(), b.cpu().numpy(), rtol=2e-6)
