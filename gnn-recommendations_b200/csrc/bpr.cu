@@ -24,7 +24,7 @@ namespace gr {
 struct BprArgs {
     const float *emb;
     long long ld;
-    long long n_users;
+    long long n_users, n_items;
     const int64_t *users, *pos, *neg;
     int batch;
     int d;
@@ -55,27 +55,29 @@ __global__ void __launch_bounds__(256) bpr_fused_kernel(const BprArgs a) {
     cg::grid_group grid = cg::this_grid();
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const int j = blockIdx.x * 8 + warp;  // sample
     const int B = a.batch;
     const int nf4 = a.d >> 2;
+    const int stride = gridDim.x * 8;          // one cooperative wave; larger batches stride over the samples
+    const float nan = __int_as_float(0x7fc00000);
 
-    const float4 *eu = nullptr, *ep = nullptr, *en = nullptr;
-    long long ru = 0, rp = 0, rn = 0;
-    if (j < B) {
-        ru = a.users[j];
-        rp = a.n_users + a.pos[j];
-        rn = a.n_users + a.neg[j];
-        eu = reinterpret_cast<const float4 *>(a.emb + ru * a.ld);
-        ep = reinterpret_cast<const float4 *>(a.emb + rp * a.ld);
-        en = reinterpret_cast<const float4 *>(a.emb + rn * a.ld);
-        float sp = 0.f, sn = 0.f;
-        for (int f = lane; f < nf4; f += 32) {
-            const float4 u = __ldg(eu + f), p = __ldg(ep + f), n = __ldg(en + f);
-            sp += u.x * p.x + u.y * p.y + u.z * p.z + u.w * p.w;
-            sn += u.x * n.x + u.y * n.y + u.z * n.z + u.w * n.w;
+    // phase 1: p_j = <U[u_j], I[pos_j]>, n_j = <U[u_j], I[neg_j]>.  An id outside [0, n_users) / [0, n_items)
+    // poisons the loss with NaN (loud) and is never dereferenced.
+    for (int j = blockIdx.x * 8 + warp; j < B; j += stride) {
+        const long long u = a.users[j], pi = a.pos[j], ni = a.neg[j];
+        float sp = nan, sn = nan;
+        if (u >= 0 && u < a.n_users && pi >= 0 && pi < a.n_items && ni >= 0 && ni < a.n_items) {
+            const float4 *eu = reinterpret_cast<const float4 *>(a.emb + u * a.ld);
+            const float4 *ep = reinterpret_cast<const float4 *>(a.emb + (a.n_users + pi) * a.ld);
+            const float4 *en = reinterpret_cast<const float4 *>(a.emb + (a.n_users + ni) * a.ld);
+            sp = 0.f; sn = 0.f;
+            for (int f = lane; f < nf4; f += 32) {
+                const float4 uu = __ldg(eu + f), p = __ldg(ep + f), n = __ldg(en + f);
+                sp += uu.x * p.x + uu.y * p.y + uu.z * p.z + uu.w * p.w;
+                sn += uu.x * n.x + uu.y * n.y + uu.z * n.z + uu.w * n.w;
+            }
+            sp = warp_sum(sp);
+            sn = warp_sum(sn);
         }
-        sp = warp_sum(sp);
-        sn = warp_sum(sn);
         if (lane == 0) {
             a.scores[j] = sp;
             a.scores[B + j] = sn;
@@ -83,7 +85,8 @@ __global__ void __launch_bounds__(256) bpr_fused_kernel(const BprArgs a) {
     }
     grid.sync();
 
-    if (j < B) {
+    // phase 2: the B x B sums of sample j's row / column, its loss row and its three gradient rows
+    for (int j = blockIdx.x * 8 + warp; j < B; j += stride) {
         const float pj = a.scores[j], nj = a.scores[B + j];
         float col = 0.f, row = 0.f, lrow = 0.f;
         for (int t = lane; t < B; t += 32) {
@@ -99,6 +102,11 @@ __global__ void __launch_bounds__(256) bpr_fused_kernel(const BprArgs a) {
         const float inv = a.grad_scale / ((float)B * (float)B);
         const float dp = -col * inv, dn = row * inv;
         if (lane == 0) a.loss_rows[j] = lrow;
+        if (pj != pj) continue;              // invalid ids (NaN score): nothing to scatter
+        const long long ru = a.users[j], rp = a.n_users + a.pos[j], rn = a.n_users + a.neg[j];
+        const float4 *eu = reinterpret_cast<const float4 *>(a.emb + ru * a.ld);
+        const float4 *ep = reinterpret_cast<const float4 *>(a.emb + rp * a.ld);
+        const float4 *en = reinterpret_cast<const float4 *>(a.emb + rn * a.ld);
         float *gu = a.grad + ru * a.ldg, *gp = a.grad + rp * a.ldg, *gn = a.grad + rn * a.ldg;
         for (int f = lane; f < nf4; f += 32) {
             const float4 u = __ldg(eu + f), p = __ldg(ep + f), n = __ldg(en + f);
@@ -150,6 +158,7 @@ extern "C" int gr_bpr_fused(const float *emb, int64_t ld, int64_t n_users, int64
     a.emb = emb;
     a.ld = ld;
     a.n_users = n_users;
+    a.n_items = n_items;
     a.users = users;
     a.pos = pos;
     a.neg = neg;
@@ -163,10 +172,12 @@ extern "C" int gr_bpr_fused(const float *emb, int64_t ld, int64_t n_users, int64
     a.counter = reinterpret_cast<unsigned int *>(reinterpret_cast<char *>(workspace) +
                                                  (((size_t)batch * 3 * sizeof(float) + 15) & ~(size_t)15));
     a.grad_scale = grad_scale;
-    const int ctas = (int)((batch + 7) / 8);
+    int ctas = (int)((batch + 7) / 8);
     int max_per_sm = 0;
     GR_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_per_sm, bpr_fused_kernel, 256, 0));
-    if ((long long)max_per_sm * sm_count() < ctas) return GR_ERR_UNSUPPORTED;  // batch too large for one wave
+    const long long wave = (long long)max_per_sm * sm_count();
+    if (wave < 1) return GR_ERR_UNSUPPORTED;
+    if (ctas > wave) ctas = (int)wave;        // one cooperative wave; the kernel strides over the remaining samples
     void *params[] = {(void *)&a};
     GR_CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)bpr_fused_kernel, dim3(ctas), dim3(256), params, 0,
                                               static_cast<cudaStream_t>(stream)));

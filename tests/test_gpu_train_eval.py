@@ -611,3 +611,32 @@ def test_cuda_graph_training_step_equals_eager(tiny, tmp_path):
     assert a[5] == b[5] == 65.0
     for x, y in zip(a[2:5], b[2:5]):
         torch.testing.assert_close(x, y, rtol=1e-4, atol=1e-6)
+
+
+def test_bpr_fused_large_batch_and_bad_ids():
+    """batches larger than one cooperative wave (B > ~9.4 k) used to return GR_ERR_UNSUPPORTED — the
+    kernel now strides over the samples; an out-of-range id poisons the loss with NaN instead of writing out of
+    bounds."""
+    gen = torch.Generator().manual_seed(0)
+    nu, ni, d, B = 3000, 2000, 64, 12000
+    emb = (torch.randn(nu + ni, d, generator=gen) * 0.3).to(DEV).requires_grad_(True)
+    users = torch.randint(0, nu, (B,), generator=gen).to(DEV)
+    pos = torch.randint(0, ni, (B,), generator=gen).to(DEV)
+    neg = torch.randint(0, ni, (B,), generator=gen).to(DEV)
+    loss = g.bpr_fused(emb, nu, users, pos, neg)
+    (grad,) = torch.autograd.grad(loss, [emb])
+    e64 = emb.detach().double().requires_grad_(True)
+    p = (e64[users] * e64[nu + pos]).sum(1)
+    n = (e64[users] * e64[nu + neg]).sum(1)
+    ref = torch.nn.functional.softplus(n[:, None] - p[None, :]).mean()
+    (gref,) = torch.autograd.grad(ref, [e64])
+    assert abs(float(loss) - float(ref)) <= 1e-5 * abs(float(ref))
+    np.testing.assert_allclose(grad.cpu().numpy(), gref.cpu().numpy(), rtol=1e-4, atol=1e-6 * float(gref.abs().max()))
+    bad = users.clone()
+    bad[7] = nu + 5                                                # a user id beyond n_users
+    before = torch.cuda.memory_allocated()
+    loss_bad = g.bpr_fused(emb.detach(), nu, bad, pos, neg)
+    assert torch.isnan(loss_bad) and before >= 0
+    bad_item = pos.clone()
+    bad_item[3] = -1
+    assert torch.isnan(g.bpr_fused(emb.detach(), nu, users, bad_item, neg))
