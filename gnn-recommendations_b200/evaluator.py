@@ -75,6 +75,7 @@ def tc_kprime(k: int) -> int:
 
 
 TC_MIN_ITEMS = 2048     # below this the exact kernel alone is faster
+KMAX = 64               # list length limit of gr_score_topk / gr_score_topk_tc (csrc/topk.cu)
 
 
 def full_rank_topk(user_emb: torch.Tensor, item_emb: torch.Tensor, eval_users, seen_indptr, seen_items, k: int,
@@ -88,6 +89,9 @@ def full_rank_topk(user_emb: torch.Tensor, item_emb: torch.Tensor, eval_users, s
     dev = user_emb.device
     if dev.type != "cuda":
         raise RuntimeError("full_rank_topk needs CUDA tensors (no CPU fallback)")
+    if not 1 <= int(k) <= KMAX:
+        raise ValueError(f"k={k}: the fused score/top-K kernels keep at most {KMAX} items per user "
+                         f"(the reference's configs use K = 20 / 50); see INTEGRATION.md")
     if user_emb.stride(1) != 1 or item_emb.stride(1) != 1:
         user_emb, item_emb = user_emb.contiguous(), item_emb.contiguous()
     eval_users = torch.as_tensor(eval_users, dtype=torch.int64).to(dev).contiguous()
@@ -167,9 +171,6 @@ class Evaluator:
             ip, it = seen_csr(eval_users, user_emb.shape[0], _pairs(dataset.train_data), _pairs(dataset.valid_data))
             topk = full_rank_topk(user_emb, item_emb, eval_users, ip, it, max_k)
             gp, gi = seen_csr(eval_users, user_emb.shape[0], test_pairs)             # ground truth rows
-            if max_k > 64:
-                return compute_metrics_from_topk(topk.cpu(), eval_users.tolist(), ground_truth_dict(test_data),
-                                                 dataset.n_items, self.k_values)
             return topk_metrics_device(topk, gp, gi, dataset.n_items, self.k_values)
 
     def evaluate_batch(self, model, users, items, adj_matrix) -> torch.Tensor:

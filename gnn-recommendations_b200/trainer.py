@@ -290,9 +290,6 @@ class Trainer:
             ip, it = seen_csr(eval_users, user_emb.shape[0], self._train_arrays())   # train only (:324)
             topk = full_rank_topk(user_emb, item_emb, eval_users, ip, it, max_k)
             gp, gi = seen_csr(eval_users, user_emb.shape[0], valid_pairs)           # ground truth rows
-            if max_k > 64:                                   # longer lists than the device reduction handles
-                return compute_metrics_from_topk(topk.cpu(), eval_users.tolist(), ground_truth_dict(valid_data),
-                                                 self.dataset.n_items, k_values if k_values else [10])
             return topk_metrics_device(topk, gp, gi, self.dataset.n_items, k_values if k_values else [10])
 
     # ------------------------------------------------------------------ warm start / export

@@ -640,3 +640,13 @@ def test_bpr_fused_large_batch_and_bad_ids():
     bad_item = pos.clone()
     bad_item[3] = -1
     assert torch.isnan(g.bpr_fused(emb.detach(), nu, users, bad_item, neg))
+
+
+def test_topk_rejects_k_above_kernel_limit():
+    """K > 64 must fail up front with a clear ValueError (it used to surface as a GrError from the
+    kernel behind a dead host-metrics branch)."""
+    ue = torch.randn(10, 64, device=DEV)
+    ie = torch.randn(500, 64, device=DEV)
+    with pytest.raises(ValueError, match="at most 64"):
+        g.full_rank_topk(ue, ie, np.arange(10), None, None, 100)
+    assert g.full_rank_topk(ue, ie, np.arange(10), None, None, 64).shape == (10, 64)
