@@ -349,6 +349,8 @@ def run_b200(args):
     avg_kernel_ms = float(np.mean(kernel_ms))
     achieved = b_alg / (avg_kernel_ms * 1e-3) / 1e9
     traffic = _traffic(f"{args.workload}@{world}")
+    if isinstance(traffic, dict):          # dataset shapes carry {"dram_bytes", "lts_bytes", ...}; the line wants DRAM bytes
+        traffic = traffic.get("dram_bytes")
     roofline = {"bound": "hbm", "kernel": f"gr_spmm_csr_f32 (spmm_stream_rows<{d}> + spmm_long_rows<{d}>)",
                 "achieved": achieved, "peak": hbm_peak, "peak_source": peak_src, "unit": "GB/s",
                 "frac": achieved / hbm_peak, "traffic": traffic, "algorithmic_bytes_per_launch": b_alg,
