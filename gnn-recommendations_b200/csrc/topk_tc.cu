@@ -1,4 +1,4 @@
-// Tensor-core candidate pass for the full-ranking evaluation (tcgen05 / TMEM, sm_100a).
+// Tensor-core candidate pass for the full-ranking evaluation (tcgen05 / TMEM / TMA, sm_100a).
 //
 // The exact ranking (topk.cu) evaluates every user x item score as a k-sequential fp32 fmaf chain on
 // the FFMA pipe: 2*U*I*d flops, ~21 TFLOP/s.  fp32 has no tensor-core MMA; TF32 (10 mantissa bits)
@@ -12,52 +12,65 @@
 // exact kernel; results are therefore always bit-identical to the exact path.
 //
 // One CTA = 128 eval users (UMMA M = 128) against one item range (blockIdx.y; 1-4 ranges per user tile fill
-// the SMs evenly) in tiles of 128 items (UMMA N = 128):
-//   warps 0-3  producers : item tile fp32 rows -> shared memory in the K-major SWIZZLE_128B
-//                          canonical layout (32 tf32 per 128-byte row, 8-row atoms, 16-byte chunks
-//                          XOR-swizzled), fence.proxy.async, mbarrier arrive; one stage (two CTAs
-//                          per SM cover each other's load latency)
-//   warp  8    MMA       : one elected lane issues d/8 tcgen05.mma (K = 8 per instruction) per tile
-//                          into one of two 128-column TMEM accumulators, tcgen05.commit to mbarriers
-//   warps 4-7  epilogue  : tcgen05.ld 32 columns at a time; thread = TMEM lane = one user: seen-item
-//                          cursor, threshold filter, lane-parallel pushes into the user's K' min-heap
-//                          in shared memory
+// the SMs evenly) in tiles of 64 items (UMMA N = 64):
+//   warps 0-3            : load the user tile once (rows gathered through eval_users) into the K-major
+//                          SWIZZLE_128B canonical layout (32 tf32 per 128-byte row, 8-row atoms, 16-byte
+//                          chunks XOR-swizzled); then
+//   warp 0, one lane     : TMA producer — per item tile d/32 cp.async.bulk.tensor.2d boxes (32 floats x 64
+//                          rows, SWIZZLE_128B; rows past the catalogue are zero-filled by the hardware) into
+//                          a two-stage ring, completion by mbarrier complete_tx
+//                          (GR_TC_NO_TMA=1: the four warps copy LDG -> swizzled STS instead)
+//   warp 8, one lane     : MMA issuer — d/8 tcgen05.mma (K = 8 per instruction) per tile into one of four
+//                          64-column TMEM accumulators, tcgen05.commit to the stage / accumulator mbarriers
+//   warps 4-7  epilogue  : tcgen05.ld 32 columns at a time; thread = TMEM lane = one user.  Selection is
+//                          max-first: masked columns (seen items, catalogue tail) are set to -inf on the rare
+//                          chunks that have any, four 8-column FMNMX trees give the group maxima, and only a
+//                          group whose maximum beats the user's admission threshold is staged (8 values) and
+//                          walked — pushes into the user's K' min-heap in shared memory run lane-parallel.
 // Two CTAs are resident per SM when the heaps fit (d = 64: K' <= 32), so eight epilogue warps
 // share the four schedulers and one CTA's MMA overlaps the other's selection.
+#include <cuda.h>
 #include <math_constants.h>
 
 #include <cstdlib>
+#include <cstring>
 
 #include "gr_common.cuh"
 
 namespace gr {
 
 constexpr int TC_M = 128;       // users per CTA
-constexpr int TC_N = 128;       // items per tile
+constexpr int TC_N = 64;        // items per tile
 constexpr int TC_KB = 32;       // tf32 elements per 128-byte swizzle row
-constexpr int TC_STAGES = 1;     // one item-tile stage: two CTAs fit per SM and cover each other's bubbles
-constexpr int TC_THREADS = 288; // 4 producer + 4 epilogue + 1 MMA warps
+constexpr int TC_STAGES = 2;    // item-tile stages in shared memory
+constexpr int TC_ACC = 4;       // TMEM accumulators of TC_N columns each
+constexpr int TC_THREADS = 288; // warps 0-3: user tile, then TMA producer (one lane) or loaders; 4-7: epilogue; 8: MMA issuer
+constexpr int TC_GROUP = 8;     // columns per selection group
 constexpr int TC_KPRIME_MAX = 64;
+constexpr uint32_t TC_A_TILE = TC_M * 128;   // one k-block (32 tf32) of the user tile: 16 KB
+constexpr uint32_t TC_B_TILE = TC_N * 128;   // one k-block of an item tile: 8 KB
 
 struct TcArgs {
     const float *user_emb;
     long long ldu;
-    const float *item_emb;  // row 0 = item id item_lo
+    const float *item_emb;  // row i = item id i
     long long ldi;
     int d;
     const int64_t *eval_users;
     int n_eval;
-    long long item_lo, item_hi;
+    int n_items;
     const int64_t *seen_indptr;
     const int32_t *seen_items;
     int kprime;          // candidates kept per user
-    long long split_items;  // items per blockIdx.y (multiple of TC_N); gridDim.y item ranges fill the SMs evenly
+    int split_items;     // items per blockIdx.y (multiple of TC_N); gridDim.y item ranges fill the SMs evenly
     float *cand_scores;  // [n_eval][gridDim.y][kprime] approximate scores (unsorted)
     int *cand_ids;       // [n_eval][gridDim.y][kprime]
     int *cand_cnt;       // [n_eval][gridDim.y]
     int *error;          // device flag: 1 = the kernel could not run (re-scoring flags every row)
+    int use_tma;         // item tiles by cp.async.bulk.tensor (1) or by the four loader warps (0)
     int debug;           // GR_TC_DEBUG bits (experiments): 1 = epilogue skips selection, 2 = producers skip loads,
-                         // 4 = take the could-not-run path, bits 8.. = producer back-off in ns
+                         // 4 = take the could-not-run path, 8 = queues are dropped instead of drained,
+                         // 16 = filter only (no appends), bits 16.. = producer back-off in ns
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
@@ -67,6 +80,10 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// one arrival + `bytes` of pending TMA traffic: the phase completes when the copies have landed
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     asm volatile(
@@ -117,6 +134,15 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// one TMA box: coordinates (c0 = element along d, c1 = item row) of the tensor map -> shared memory;
+// the bytes are reported to `bar` (complete_tx)
+__device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *tmap, uint64_t *bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
     uint32_t r[32];
     asm volatile(
@@ -156,9 +182,9 @@ constexpr uint32_t kIdescTf32 = (1u << 4) | (2u << 7) | (2u << 10) | ((TC_N >> 3
 // position-major in shared memory (entry p of user m at [p * 128 + m], conflict-free for a warp).  The
 // root is the worst kept score = the admission threshold.  Ties are broken arbitrarily: the nomination
 // only has to guarantee "every rejected or evicted item has approximate score <= the final root".
-// Pushes run LANE-PARALLEL: the warp stages the 32 columns it just read from TMEM in shared memory and
-// every lane pops its own passing columns, so the warp executes max-over-lanes pushes per chunk
-// (~1-2) instead of one divergent push per (lane, column) event (~8 K per warp at 50 K items).
+// Pushes run LANE-PARALLEL: a lane whose 8-column group maximum beats its threshold stages the group in
+// shared memory and walks it, so the warp executes max-over-lanes pushes per group instead of one
+// divergent push per (lane, column) event.
 struct SelState {
     int cnt;
     float thr;
@@ -201,7 +227,43 @@ __device__ __forceinline__ SelState tc_heap_push(float *hs, int *hi, int m, int 
     return st;
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 2) topk_tc_candidates_kernel(const TcArgs a) {
+__device__ __forceinline__ float max8(const float *v) {
+    return fmaxf(fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3])), fmaxf(fmaxf(v[4], v[5]), fmaxf(v[6], v[7])));
+}
+
+// Columns that beat a user's (possibly stale) threshold are only APPENDED to the user's pending queue
+// (position-major like the heap: entry q of user m at [q * 128 + m]); the heap pushes — long divergent sift
+// loops — run when some lane's queue is nearly full: all lanes then pop their queues in lockstep, so a push
+// iteration serves every lane that has work instead of the one lane that happened to hit in this chunk
+// (one push per chunk with 1 of 32 lanes active was the dominant cost of the first version).  A stale
+// threshold only admits extra queue entries; each is re-checked against the current root when popped.
+constexpr int TC_PEND = 16;     // queue entries per user
+
+__device__ __forceinline__ void pend_append(uint32_t slot, float s, int id) {
+    asm volatile("st.shared.f32 [%0], %1;\n\tst.shared.b32 [%0+%3], %2;" ::"r"(slot), "f"(s), "r"(id), "n"(TC_PEND * TC_M * 4)
+                 : "memory");
+}
+
+__device__ __noinline__ SelState tc_drain(float *hs, int *hi, const float *ps, const int *pi, int m, int K, int cnt,
+                                          float thr, int np) {
+    for (int q = 0; __any_sync(0xffffffffu, q < np); ++q) {
+        if (q < np) {
+            const float sj = ps[q * TC_M + m];
+            if (sj > thr) {
+                const SelState st = tc_heap_push(hs, hi, m, K, cnt, sj, pi[q * TC_M + m]);
+                cnt = st.cnt;
+                thr = st.thr;
+            }
+        }
+    }
+    SelState out;
+    out.cnt = cnt;
+    out.thr = thr;
+    return out;
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 2) topk_tc_candidates_kernel(const TcArgs a,
+                                                                           const __grid_constant__ CUtensorMap tmap) {
     // SWIZZLE_128B operand tiles need 1024-byte alignment; the kernel has no static shared memory, so
     // the dynamic window starts at the CTA's (1 KB-granular) allocation.  Checked, not assumed.
     extern __shared__ __align__(1024) unsigned char smem_dyn[];
@@ -212,96 +274,116 @@ __global__ void __launch_bounds__(TC_THREADS, 2) topk_tc_candidates_kernel(const
     }
     const int d = a.d;
     const int nkb = d / TC_KB;                       // k-blocks of 32 tf32
-    const uint32_t tile_bytes = TC_M * 128;          // one k-block of a 128-row operand: 16 KB
     unsigned char *sA = smem_raw;                    // [nkb][128 rows][128 B]
-    unsigned char *sB = sA + (size_t)nkb * tile_bytes;            // [stages][nkb][128 rows][128 B]
-    float *ls = reinterpret_cast<float *>(sB + (size_t)TC_STAGES * nkb * tile_bytes);   // heap scores [kprime][128]
+    unsigned char *sB = sA + (size_t)nkb * TC_A_TILE;             // [stages][nkb][64 rows][128 B]
+    float *ls = reinterpret_cast<float *>(sB + (size_t)TC_STAGES * nkb * TC_B_TILE);     // heap scores [kprime][128]
     int *li = reinterpret_cast<int *>(ls + (size_t)a.kprime * TC_M);                      // heap ids    [kprime][128]
-    float *stage = reinterpret_cast<float *>(li + (size_t)a.kprime * TC_M);               // chunk staging [32][128]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(stage + 32 * TC_M);
-    uint64_t *b_full = bars, *b_empty = bars + 2, *t_full = bars + 4, *t_empty = bars + 6, *a_full = bars + 8;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 9);
+    float *pend_s = reinterpret_cast<float *>(li + (size_t)a.kprime * TC_M);              // pending scores [TC_PEND][128]
+    int *pend_i = reinterpret_cast<int *>(pend_s + TC_PEND * TC_M);                       // pending ids    [TC_PEND][128]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(pend_i + TC_PEND * TC_M);
+    uint64_t *b_full = bars, *b_empty = bars + TC_STAGES, *t_full = bars + 2 * TC_STAGES,
+             *t_empty = bars + 2 * TC_STAGES + TC_ACC, *a_full = bars + 2 * TC_STAGES + 2 * TC_ACC;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(a_full + 1);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const unsigned sleep_ns = (a.debug >> 8) ? (unsigned)(a.debug >> 8) : 200u;
+    const unsigned sleep_ns = (a.debug >> 16) ? (unsigned)(a.debug >> 16) : 200u;
     const int row0 = blockIdx.x * TC_M;
-    const long long item_lo = a.item_lo + (long long)blockIdx.y * a.split_items;
-    const long long item_hi = min(a.item_hi, item_lo + a.split_items);
-    const long long n_it = item_hi > item_lo ? item_hi - item_lo : 0;
-    const int n_tiles = (int)((n_it + TC_N - 1) / TC_N);
+    const int item_lo = (int)min((long long)a.n_items, (long long)blockIdx.y * a.split_items);
+    const int item_hi = (int)min((long long)a.n_items, (long long)item_lo + a.split_items);
+    const int n_it = item_hi - item_lo;
+    const int n_tiles = (n_it + TC_N - 1) / TC_N;
 
     if (tid == 0) {
         for (int s = 0; s < TC_STAGES; ++s) {
-            mbar_init(&b_full[s], 128);   // 128 producer threads
-            mbar_init(&b_empty[s], 1);    // tcgen05.commit
+            mbar_init(&b_full[s], a.use_tma ? 1 : 128);   // TMA: one arrive.expect_tx; else 128 loader threads
+            mbar_init(&b_empty[s], 1);                    // tcgen05.commit
         }
-        for (int s = 0; s < 2; ++s) {     // the TMEM accumulator is always double-buffered
+        for (int s = 0; s < TC_ACC; ++s) {
             mbar_init(&t_full[s], 1);     // tcgen05.commit
             mbar_init(&t_empty[s], 128);  // 128 epilogue threads
         }
         mbar_init(a_full, 128);
         fence_barrier_init();
     }
-    if (warp == 8) tmem_alloc(tmem_slot, 2 * TC_N);  // two 128-column fp32 accumulators
+    if (warp == 8) tmem_alloc(tmem_slot, TC_ACC * TC_N);  // four 64-column fp32 accumulators
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp < 4) {
-        // ===== producers =====
+        // ===== user tile, once (rows gathered through eval_users) =====
         const int f4_per_row = d / 4;
-        for (int idx = tid; idx < TC_M * f4_per_row; idx += 128) {   // user tile, once
+        for (int idx = tid; idx < TC_M * f4_per_row; idx += 128) {
             const int r = idx / f4_per_row, f = idx % f4_per_row;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (row0 + r < a.n_eval) v = __ldg(reinterpret_cast<const float4 *>(a.user_emb + a.eval_users[row0 + r] * a.ldu) + f);
-            *reinterpret_cast<float4 *>(sA + (size_t)(f >> 3) * tile_bytes + sw128_offset(r, f & 7)) = v;
+            *reinterpret_cast<float4 *>(sA + (size_t)(f >> 3) * TC_A_TILE + sw128_offset(r, f & 7)) = v;
         }
         fence_proxy_async();
         mbar_arrive(a_full);
-        for (int t = 0; t < n_tiles; ++t) {
-            const int s = t % TC_STAGES;
-            if (t >= TC_STAGES) mbar_wait_relaxed(&b_empty[s], ((t / TC_STAGES) - 1) & 1, sleep_ns);
-            unsigned char *dst = sB + (size_t)s * nkb * tile_bytes;
-            const long long i0 = item_lo + (long long)t * TC_N;
-            // 8 independent 16-byte loads in flight per thread, then their swizzled stores
-            for (int base = (a.debug & 2) && t >= TC_STAGES ? TC_N * f4_per_row : 0; base < TC_N * f4_per_row; base += 128 * 8) {
-                float4 v[8];
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const int idx = base + q * 128 + tid;
-                    const int r = idx / f4_per_row, f = idx % f4_per_row;
-                    v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (idx < TC_N * f4_per_row && i0 + r < item_hi)
-                        v[q] = __ldg(reinterpret_cast<const float4 *>(a.item_emb + (i0 + r - a.item_lo) * a.ldi) + f);
-                }
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const int idx = base + q * 128 + tid;
-                    const int r = idx / f4_per_row, f = idx % f4_per_row;
-                    if (idx < TC_N * f4_per_row)
-                        *reinterpret_cast<float4 *>(dst + (size_t)(f >> 3) * tile_bytes + sw128_offset(r, f & 7)) = v[q];
+        if (a.use_tma) {
+            // ===== TMA producer: one lane =====
+            if (warp == 0 && lane == 0) {
+                for (int t = 0; t < n_tiles; ++t) {
+                    const int s = t % TC_STAGES;
+                    if (t >= TC_STAGES) mbar_wait_relaxed(&b_empty[s], ((t / TC_STAGES) - 1) & 1, sleep_ns);
+                    unsigned char *dst = sB + (size_t)s * nkb * TC_B_TILE;
+                    if ((a.debug & 2) && t >= TC_STAGES) {
+                        mbar_arrive(&b_full[s]);
+                        continue;
+                    }
+                    mbar_arrive_expect_tx(&b_full[s], (uint32_t)nkb * TC_B_TILE);
+                    for (int kb = 0; kb < nkb; ++kb)
+                        tma_load_2d(dst + (size_t)kb * TC_B_TILE, &tmap, &b_full[s], kb * TC_KB, item_lo + t * TC_N);
                 }
             }
-            fence_proxy_async();
-            mbar_arrive(&b_full[s]);
+        } else {
+            // ===== loader warps: LDG -> swizzled STS =====
+            for (int t = 0; t < n_tiles; ++t) {
+                const int s = t % TC_STAGES;
+                if (t >= TC_STAGES) mbar_wait_relaxed(&b_empty[s], ((t / TC_STAGES) - 1) & 1, sleep_ns);
+                unsigned char *dst = sB + (size_t)s * nkb * TC_B_TILE;
+                const int i0 = item_lo + t * TC_N;
+                // 8 independent 16-byte loads in flight per thread, then their swizzled stores
+                for (int base = (a.debug & 2) && t >= TC_STAGES ? TC_N * f4_per_row : 0; base < TC_N * f4_per_row; base += 128 * 8) {
+                    float4 v[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const int idx = base + q * 128 + tid;
+                        const int r = idx / f4_per_row, f = idx % f4_per_row;
+                        v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (idx < TC_N * f4_per_row && i0 + r < item_hi)
+                            v[q] = __ldg(reinterpret_cast<const float4 *>(a.item_emb + (long long)(i0 + r) * a.ldi) + f);
+                    }
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const int idx = base + q * 128 + tid;
+                        const int r = idx / f4_per_row, f = idx % f4_per_row;
+                        if (idx < TC_N * f4_per_row)
+                            *reinterpret_cast<float4 *>(dst + (size_t)(f >> 3) * TC_B_TILE + sw128_offset(r, f & 7)) = v[q];
+                    }
+                }
+                fence_proxy_async();
+                mbar_arrive(&b_full[s]);
+            }
         }
     } else if (warp == 8) {
         // ===== MMA issuer =====
         if (lane == 0) {
             mbar_wait_relaxed(a_full, 0, sleep_ns);
             for (int t = 0; t < n_tiles; ++t) {
-                const int s = t % TC_STAGES, acc = t & 1;
+                const int s = t % TC_STAGES, acc = t % TC_ACC;
                 mbar_wait_relaxed(&b_full[s], (t / TC_STAGES) & 1, sleep_ns);
-                if (t >= 2) mbar_wait_relaxed(&t_empty[acc], ((t >> 1) - 1) & 1, sleep_ns);
+                if (t >= TC_ACC) mbar_wait_relaxed(&t_empty[acc], ((t / TC_ACC) - 1) & 1, sleep_ns);
                 tc_fence_after();
-                const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB + (size_t)s * nkb * tile_bytes);
+                const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB + (size_t)s * nkb * TC_B_TILE);
                 const uint32_t tmem_d = tmem_base + (uint32_t)acc * TC_N;
                 for (int kb = 0; kb < nkb; ++kb) {
 #pragma unroll
                     for (int k = 0; k < TC_KB / 8; ++k) {   // UMMA K = 8 tf32 = 32 bytes
-                        const uint64_t da = make_sw128_desc(a_base + kb * tile_bytes + k * 32);
-                        const uint64_t db = make_sw128_desc(b_base + kb * tile_bytes + k * 32);
+                        const uint64_t da = make_sw128_desc(a_base + kb * TC_A_TILE + k * 32);
+                        const uint64_t db = make_sw128_desc(b_base + kb * TC_B_TILE + k * 32);
                         umma_tf32(tmem_d, da, db, kIdescTf32, (kb | k) ? 1u : 0u);
                     }
                 }
@@ -314,8 +396,13 @@ __global__ void __launch_bounds__(TC_THREADS, 2) topk_tc_candidates_kernel(const
         const int m = (warp & 3) * 32 + lane;
         const bool user_ok = row0 + m < a.n_eval;
         const int K = a.kprime;
-        int cnt = 0;
-        float thr = -CUDART_INF_F;   // root of the heap once it is full
+        int cnt = 0;                 // heap entries
+        // next free entry of this user's pending queue, as a shared-space byte address (ids 8 KB further)
+        const uint32_t wp0 = smem_u32(pend_s + m), wp_limit = wp0 + (TC_PEND - TC_GROUP) * TC_M * 4;
+        uint32_t wp = wp0;
+        // admission threshold: root of the heap once it is full; a row beyond n_eval never admits anything
+        float thr = user_ok ? -CUDART_INF_F : CUDART_INF_F;
+        constexpr int kNoSeen = 0x7fffffff;
         int sc = 0, se = 0;
         if (user_ok && a.seen_indptr) {
             long long lo = a.seen_indptr[row0 + m], hi = a.seen_indptr[row0 + m + 1];
@@ -326,47 +413,66 @@ __global__ void __launch_bounds__(TC_THREADS, 2) topk_tc_candidates_kernel(const
             }
             sc = (int)lo;
         }
-        long long next_seen = sc < se ? (long long)a.seen_items[sc] : (1LL << 62);
+        int next_seen = sc < se ? a.seen_items[sc] : kNoSeen;     // absolute item id
         for (int t = 0; t < n_tiles; ++t) {
-            const int acc = t & 1;
-            mbar_wait(&t_full[acc], (t >> 1) & 1);
+            const int acc = t % TC_ACC;
+            mbar_wait(&t_full[acc], (t / TC_ACC) & 1);
             tc_fence_after();
-            const long long i0 = item_lo + (long long)t * TC_N;
+            const int i0 = item_lo + t * TC_N;
 #pragma unroll 1
             for (int c = 0; c < TC_N / 32; ++c) {
                 float v[32];
                 tmem_ld32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(acc * TC_N + c * 32), v);
                 if (a.debug & 1) continue;
-                const long long cbase = i0 + c * 32;
-                unsigned seen = 0;
+                const int cbase = i0 + c * 32;
+                // columns that must not be nominated: seen items of this user, padding beyond the range
+                unsigned kill = 0;
                 while (next_seen < cbase + 32) {          // next_seen is prefetched: no load on the common path
-                    if (next_seen >= cbase) seen |= 1u << (int)(next_seen - cbase);
+                    if (next_seen >= cbase) kill |= 1u << (next_seen - cbase);
                     ++sc;
-                    next_seen = sc < se ? (long long)a.seen_items[sc] : (1LL << 62);
+                    next_seen = sc < se ? a.seen_items[sc] : kNoSeen;
                 }
-                const long long room = item_hi - cbase;  // columns beyond the catalogue are padding
-                unsigned pass = 0;
+                const int room = item_hi - cbase;
+                if (room < 32) kill |= room <= 0 ? 0xffffffffu : ~((1u << room) - 1u);
+                if (kill) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) pass |= (unsigned)(v[j] > thr) << j;
-                pass &= user_ok ? ~seen : 0u;
-                if (room < 32) pass &= (room <= 0) ? 0u : ((1u << (int)room) - 1u);
-                if (!__any_sync(0xffffffffu, pass != 0)) continue;     // the warp stays converged here
+                    for (int j = 0; j < 32; ++j)
+                        if ((kill >> j) & 1u) v[j] = -CUDART_INF_F;
+                }
+                // max-first filter: one FMNMX tree per 8 columns, one compare per group
+                unsigned hit = 0;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) stage[j * TC_M + m] = v[j];   // own column of the staging tile
-                while (pass) {                                          // lanes pop their own passing columns
-                    const int j = __ffs(pass) - 1;
-                    pass &= pass - 1;
-                    const float sj = stage[j * TC_M + m];
-                    if (sj > thr) {
-                        const SelState st = tc_heap_push(ls, li, m, K, cnt, sj, (int)(cbase + j));
-                        cnt = st.cnt;
-                        thr = st.thr;
+                for (int gq = 0; gq < 32 / TC_GROUP; ++gq) hit |= (unsigned)(max8(v + gq * TC_GROUP) > thr) << gq;
+                if (!__any_sync(0xffffffffu, hit != 0)) continue;     // the warp stays converged here
+                if (a.debug & 16) continue;
+                // groups some lane passed: predicated appends to the pending queues (warp-uniform branch per group)
+#pragma unroll
+                for (int gq = 0; gq < 32 / TC_GROUP; ++gq) {
+                    if (__any_sync(0xffffffffu, (hit >> gq) & 1u)) {
+#pragma unroll
+                        for (int j = 0; j < TC_GROUP; ++j) {
+                            if (v[gq * TC_GROUP + j] > thr) {
+                                pend_append(wp, v[gq * TC_GROUP + j], cbase + gq * TC_GROUP + j);
+                                wp += TC_M * 4;
+                            }
+                        }
+                        if (__any_sync(0xffffffffu, wp > wp_limit)) {   // the next group may not fit
+                            if (!(a.debug & 8)) {
+                                const SelState st = tc_drain(ls, li, pend_s, pend_i, m, K, cnt, thr, (int)(wp - wp0) / (TC_M * 4));
+                                cnt = st.cnt;
+                                thr = st.thr;
+                            }
+                            wp = wp0;
+                        }
                     }
                 }
-                __syncwarp();
             }
             tc_fence_before();
             mbar_arrive(&t_empty[acc]);
+        }
+        {
+            const SelState st = tc_drain(ls, li, pend_s, pend_i, m, K, cnt, thr, (int)(wp - wp0) / (TC_M * 4));
+            cnt = st.cnt;
         }
         if (user_ok) {
             const size_t seg = (size_t)(row0 + m) * gridDim.y + blockIdx.y;
@@ -379,7 +485,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) topk_tc_candidates_kernel(const
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) tmem_dealloc(tmem_base, 2 * TC_N);
+    if (warp == 8) tmem_dealloc(tmem_base, TC_ACC * TC_N);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -510,8 +616,37 @@ __global__ void max_row_norm_kernel(const float *x, long long ld, int n, int d, 
 }
 
 static size_t tc_smem_bytes(int d, int kprime) {
-    const size_t tile = (size_t)TC_M * 128;
-    return (size_t)(d / TC_KB) * tile * (1 + TC_STAGES) + (size_t)kprime * TC_M * 8 + (size_t)32 * TC_M * 4 + 128;
+    return (size_t)(d / TC_KB) * ((size_t)TC_A_TILE + (size_t)TC_STAGES * TC_B_TILE) + (size_t)kprime * TC_M * 8 +
+           (size_t)TC_PEND * TC_M * 8 + 256;
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (libgr_b200.so does not link libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+// item table [n_items][d] fp32 (row stride ldi) as a 2-D tensor map with boxes of 32 floats x TC_N rows,
+// SWIZZLE_128B: the box lands in shared memory in exactly the K-major layout make_sw128_desc describes
+static bool make_item_tensor_map(CUtensorMap *tm, const float *item_emb, int64_t ldi, int64_t n_items, int d) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return false;
+    const cuuint64_t gdim[2] = {(cuuint64_t)d, (cuuint64_t)n_items};
+    const cuuint64_t gstride[1] = {(cuuint64_t)ldi * 4};
+    const cuuint32_t box[2] = {(cuuint32_t)TC_KB, (cuuint32_t)TC_N};
+    const cuuint32_t estride[2] = {1, 1};
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(item_emb), gdim, gstride, box, estride,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 constexpr size_t kSmemTwoCtas = (228 * 1024) / 2 - 1024;   // per CTA when two share an SM (1 KB reserved each)
 constexpr size_t kSmemOneCta = 227 * 1024;
@@ -571,7 +706,7 @@ extern "C" int gr_score_topk_tc(const float *user_emb, int64_t ldu, const float 
     const long long tiles_total = (n_items + TC_N - 1) / TC_N;
     int n_seg = tc_splits(n_eval, d, kprime);
     { const char *e = getenv("GR_TC_SPLITS"); if (e && atoi(e) > 0) n_seg = atoi(e) < 128 / kprime ? atoi(e) : 128 / kprime; }
-    if (n_seg > tiles_total / 8) n_seg = (int)(tiles_total / 8 > 0 ? tiles_total / 8 : 1);   // >= 1024 items per range
+    if (n_seg > tiles_total / 16) n_seg = (int)(tiles_total / 16 > 0 ? tiles_total / 16 : 1);   // >= 1024 items per range
     const long long split_items = ((tiles_total + n_seg - 1) / n_seg) * TC_N;
     n_seg = (int)((n_items + split_items - 1) / split_items);
     float *cand_scores = static_cast<float *>(workspace);
@@ -585,14 +720,19 @@ extern "C" int gr_score_topk_tc(const float *user_emb, int64_t ldu, const float 
 
     TcArgs a;
     a.user_emb = user_emb; a.ldu = ldu; a.item_emb = item_emb; a.ldi = ldi; a.d = d;
-    a.eval_users = eval_users; a.n_eval = (int)n_eval; a.item_lo = 0; a.item_hi = n_items;
+    a.eval_users = eval_users; a.n_eval = (int)n_eval; a.n_items = (int)n_items;
     a.seen_indptr = seen_indptr; a.seen_items = seen_items; a.kprime = kprime;
-    a.split_items = split_items;
+    a.split_items = (int)split_items;
     a.cand_scores = cand_scores; a.cand_ids = cand_ids; a.cand_cnt = cand_cnt; a.error = tc_error;
     { const char *e = getenv("GR_TC_DEBUG"); a.debug = e ? atoi(e) : 0; }
+    // item tiles by TMA unless GR_TC_NO_TMA=1 (or the driver has no cuTensorMapEncodeTiled): then four loader warps
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    { const char *e = getenv("GR_TC_NO_TMA"); a.use_tma = (e && atoi(e) != 0) ? 0 : 1; }
+    if (a.use_tma && !make_item_tensor_map(&tmap, item_emb, ldi, n_items, d)) a.use_tma = 0;
     const size_t smem = tc_smem_bytes(d, kprime);
     GR_CUDA_CHECK(cudaFuncSetAttribute(topk_tc_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    topk_tc_candidates_kernel<<<dim3((unsigned)((n_eval + TC_M - 1) / TC_M), (unsigned)n_seg), TC_THREADS, smem, s>>>(a);
+    topk_tc_candidates_kernel<<<dim3((unsigned)((n_eval + TC_M - 1) / TC_M), (unsigned)n_seg), TC_THREADS, smem, s>>>(a, tmap);
     GR_LAUNCH_CHECK();
 
     RescoreArgs r;

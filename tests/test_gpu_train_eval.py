@@ -457,6 +457,29 @@ def test_topk_tensor_core_kernel_failure_falls_back_to_exact(monkeypatch):
     assert stats["rows_reranked_exactly"] == 200 and torch.equal(got, want)
 
 
+@pytest.mark.parametrize("no_tma", [False, True])
+def test_topk_tensor_core_item_tiles_by_tma_and_by_loader_warps(no_tma, monkeypatch):
+    """The item tiles reach shared memory by cp.async.bulk.tensor (SWIZZLE_128B boxes, default) or by the loader
+    warps (GR_TC_NO_TMA=1): identical lists either way, from a row-strided item table (ld > d) whose catalogue
+    size is no multiple of the tile, with nearly every row proven by the nomination pass."""
+    if no_tma:
+        monkeypatch.setenv("GR_TC_NO_TMA", "1")
+    rng = np.random.default_rng(11)
+    nu, ni, d = 700, 10007, 64
+    ue = torch.from_numpy(rng.standard_normal((nu, d)).astype(np.float32)).to(DEV)
+    wide = torch.from_numpy(rng.standard_normal((ni, d + 32)).astype(np.float32)).to(DEV)
+    ie = wide[:, 16:16 + d]                                   # row stride 96 floats, 64-byte offset
+    eu = np.arange(nu)
+    lens = rng.integers(0, 60, nu)
+    ip = np.concatenate([[0], np.cumsum(lens)])
+    it = np.concatenate([np.sort(rng.choice(ni, n, replace=False)) for n in lens]).astype(np.int32)
+    want = g.full_rank_topk(ue, ie, eu, ip, it, 20, tensor_cores=False)
+    stats = {}
+    got = g.full_rank_topk(ue, ie, eu, ip, it, 20, tensor_cores=True, stats=stats)
+    assert torch.equal(got, want)
+    assert stats["tensor_cores"] and stats["rows_reranked_exactly"] <= nu // 20, stats
+
+
 def test_trainer_full_loop_vs_reference(tiny, tmp_path):
     """`Trainer.train()` (trainer.py:469-579): 2-epoch linear warm-up, cosine schedule, validation every
     epoch, early-stopping bookkeeping — 4 epochs of LightGCN from the same seeds as the reference run
