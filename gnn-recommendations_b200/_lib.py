@@ -33,6 +33,8 @@ SIGNATURES = {
     "gr_row_groups": (C.c_int, [_p, _i64, _i32, _i32, _p, _p]),
     "gr_spmm_csr_f32": (C.c_int, [_p, _p, _p, _p, _i32, _p, _i32, _p, _i32, _p, _p, _i32, _i32, _i64, _i32,
                                   _p, _i64, _p, _i64, _p, _i64, _p, _i64, _f32, _i32, _p, _i32, _i32, _i64, _i32, _p, _p]),
+    "gr_spmm_csr_map_f32": (C.c_int, [_p, _p, _p, _p, _i32, _p, _i32, _p, _i32, _p, _p, _i32, _i32, _i64, _i32,
+                                      _p, _i64, _p, _i64, _p, _i64, _p, _i64, _p, _i32, _f32, _f32, _p, _p, _p]),
     "gr_peer_scatter_rows": (C.c_int, [_p, _i64, _i64, _i32, _p, _i32, _i32, _i64, _i64, _p]),
     "gr_reduce_bcast_rows": (C.c_int, [_p, _i32, _i64, _p, _i32, _i64, _i64, _i64, _i64, _i32, _p, _i64, _p, _i64, _p,
                                        _i64, _f32, _i32, _p]),

@@ -15,6 +15,11 @@
 //     one feature per lane.  They run on a high-priority side stream and overlap the short-row kernel.
 //   * rows beyond 131 072 entries are cut into 65 536-entry segments whose partial chains are added
 //     in segment order (spmm_combine_parts) — deterministic, identical on 1 and N GPUs.
+// Dense-map epilogue (gr_spmm_csr_map_f32, d <= 64): the finished row t is multiplied by a d x d matrix held
+// in shared memory and combined with a residual row before it is written,
+//   out[r,:] = alpha * (t M) + beta * addend[r,:]      (y[r,:] = alpha * t, optional)
+// which is one Group-and-Shuffle layer (model.py:171-195: c = A x; (c W_conn) W_orth[:, perm]; residual) — and,
+// with M^T, its backward — in ONE pass: no second launch, no N x d round trip of c through HBM.
 // The epilogue of every kernel can also store the finished row into the layer buffers of the other
 // ranks (NVLink P2P stores or one NVSwitch multicast store): the all-gather of the row-partitioned
 // propagation is fused into the SpMM.
@@ -71,7 +76,22 @@ struct SpmmArgs {
     // entry; the last CTA of a launch zeroes both again.  (No library-global device state: two
     // propagations in flight on different streams use different words.)
     unsigned int *sched;
+    // dense-map epilogue (map != nullptr): out = map_alpha * (t @ map) + beta * addend, y = map_alpha * t;
+    // beta = map_beta * (*map_beta_dev if given).  map is [D][D] row-major; map_transposed applies map^T.
+    const float *map;
+    int map_transposed;
+    float map_alpha, map_beta;
+    const float *map_beta_dev;
 };
+
+// the d x d epilogue map into shared memory as Ms[i * D + j] = M[i][j] (or M[j][i]): out_j = sum_i t_i Ms[i][j]
+template <int D>
+__device__ __forceinline__ void load_map_smem(float *Ms, const SpmmArgs &a, int tid, int nthreads) {
+    for (int i = tid; i < D * D; i += nthreads) Ms[i] = a.map_transposed ? __ldg(a.map + (i % D) * D + i / D) : __ldg(a.map + i);
+}
+__device__ __forceinline__ float map_beta_of(const SpmmArgs &a) {
+    return a.map_beta * (a.map_beta_dev ? __ldg(a.map_beta_dev) : 1.f);
+}
 
 // kernel template parameter PEERS: how the finished row also leaves the GPU
 constexpr int kPeersNone = 0;       // not at all
@@ -209,11 +229,22 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) spmm_warp_rows(const SpmmAr
 // and the addend row are prefetched at the previous boundary.  Rows with >= long_thr entries
 // belong to the long-row kernel: the stream jumps over them.
 // ---------------------------------------------------------------------------------------------
-template <int D, int PEERS>
+template <int D, int PEERS, bool MAP = false>
 __global__ void __launch_bounds__(kWarpsPerCta * 32) spmm_stream_rows(const SpmmArgs a) {
     using C = RowCfg<D>;
     constexpr int LPR = C::LPR, VPL = C::VPL, SPW = C::RPW, UNROLL = C::UNROLL;
     constexpr unsigned kFull = 0xffffffffu;
+    static_assert(!MAP || (VPL == 1 && PEERS == kPeersNone), "dense-map epilogue: d <= 128, single GPU");
+    // dense-map epilogue: the map and one staging row per sub-warp in shared memory
+    extern __shared__ __align__(16) unsigned char stream_smem[];
+    float4 *Ms4 = reinterpret_cast<float4 *>(stream_smem);                          // [D][D/4]
+    float4 *srow4 = Ms4 + (MAP ? D * (D / 4) : 0);                                   // [warps * SPW][D/4]
+    float map_beta = 0.f;
+    if constexpr (MAP) {
+        load_map_smem<D>(reinterpret_cast<float *>(Ms4), a, threadIdx.x, kWarpsPerCta * 32);
+        map_beta = map_beta_of(a);
+        __syncthreads();
+    }
 
     const uint64_t pol_s = policy_evict_first(), pol_g = policy_evict_last();
     const int lane = threadIdx.x & 31;
@@ -234,6 +265,28 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) spmm_stream_rows(const Spmm
         }
     };
     auto flush = [&](int row) {
+        if constexpr (MAP) {
+            // t (one float4 per lane of the sub-warp) -> shared memory, then lane gl forms columns 4gl..4gl+3 of t M
+            const unsigned sub = (LPR == 32) ? kFull : (((1u << LPR) - 1u) << ((lane / LPR) * LPR));
+            float4 *mine = srow4 + (warp * SPW + lane / LPR) * (D / 4);
+            mine[gl] = acc[0];
+            __syncwarp(sub);
+            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 2
+            for (int i4 = 0; i4 < D / 4; ++i4) {
+                const float4 tt = mine[i4];
+                fma4(o, tt.x, Ms4[(4 * i4 + 0) * (D / 4) + gl]);
+                fma4(o, tt.y, Ms4[(4 * i4 + 1) * (D / 4) + gl]);
+                fma4(o, tt.z, Ms4[(4 * i4 + 2) * (D / 4) + gl]);
+                fma4(o, tt.w, Ms4[(4 * i4 + 3) * (D / 4) + gl]);
+            }
+            __syncwarp(sub);
+            if (a.y) st_stream_f4(a.y + (long long)row * a.ldy4 + gl, scale4(acc[0], a.map_alpha, GR_SCALE_MUL));
+            o = scale4(o, a.map_alpha, GR_SCALE_MUL);
+            if (a.addend) fma4(o, map_beta, add_cur[0]);
+            st_stream_f4(a.out + (long long)row * a.ldo4 + gl, o);
+            acc[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
 #pragma unroll
         for (int j = 0; j < VPL; ++j) {
             const int off = gl + j * LPR;
@@ -255,6 +308,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) spmm_stream_rows(const Spmm
                 st_stream_f4(a.out + (long long)row * a.ldo4 + off, scale4(o, a.scale, a.scale_mode));
             }
             acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         }
     };
     // move to row r+1 (its end offset comes from the prefetched stop_next); jump over long rows
@@ -632,7 +686,7 @@ struct LongCfgBar {
     static_assert(STAGES - 1 <= IDX_AHEAD && STAGES + IDX_AHEAD + 1 <= IDX_RING, "index ring too small");
 };
 
-template <int D, int PEERS>
+template <int D, int PEERS, bool MAP = false>
 __global__ void __launch_bounds__(LongCfgBar<D>::THREADS, 1) spmm_long_rows_bar(const SpmmArgs a) {
     using L = LongCfgBar<D>;
     constexpr int STAGES = L::STAGES, CH = L::CHUNK, F4 = D / 4, CONS = L::CONS, PROD = L::PROD;
@@ -655,6 +709,14 @@ __global__ void __launch_bounds__(LongCfgBar<D>::THREADS, 1) spmm_long_rows_bar(
     // persistent CTAs: rows are handed out in row_order (longest first) through a ticket counter,
     // so the hottest row starts first and no CTA queues work behind it.
     int &s_ticket = *reinterpret_cast<int *>(smem_raw + L::SMEM);  // one int after the rings
+    // dense-map epilogue: the map and one staging row after the ticket word
+    float *Ms = reinterpret_cast<float *>(smem_raw + L::SMEM + 16);   // [D][D]
+    float *srow = Ms + (MAP ? D * D : 0);                             // [D]
+    float map_beta = 0.f;
+    if constexpr (MAP) {
+        load_map_smem<D>(Ms, a, threadIdx.x, L::THREADS);             // visible after the first barrier below
+        map_beta = map_beta_of(a);
+    }
     for (;;) {
     if (threadIdx.x == 0) s_ticket = (int)atomicAdd(a.sched, 1u);
     __syncthreads();
@@ -751,7 +813,23 @@ __global__ void __launch_bounds__(LongCfgBar<D>::THREADS, 1) spmm_long_rows_bar(
     }
     cp_async_wait<0>();
 
-    if (is_cons && part >= 0) {
+    if constexpr (MAP) {
+        // the row is spread over the consumer warps (one feature per lane): through shared memory, then thread f
+        // forms column f of t M.  `part` is uniform over the CTA, so the barrier is not divergent.
+        const int f = warp * 32 + lane;
+        if (is_cons && part >= 0) a.part_buf[(long long)part * D + f] = acc;
+        if (is_cons && part < 0) srow[f] = acc;
+        __syncthreads();
+        if (is_cons && part < 0) {
+            float o = 0.f;
+#pragma unroll 8
+            for (int i = 0; i < D; ++i) o = __fmaf_rn(srow[i], Ms[i * D + f], o);
+            if (a.y) reinterpret_cast<float *>(a.y + (long long)r * a.ldy4)[f] = __fmul_rn(acc, a.map_alpha);
+            o = __fmul_rn(o, a.map_alpha);
+            if (a.addend) o = __fmaf_rn(map_beta, reinterpret_cast<const float *>(a.addend + (long long)r * a.lda4)[f], o);
+            reinterpret_cast<float *>(a.out + (long long)r * a.ldo4)[f] = o;
+        }
+    } else if (is_cons && part >= 0) {
         a.part_buf[(long long)part * D + warp * 32 + lane] = acc;
     } else if (is_cons) {
         const int f = warp * 32 + lane;
@@ -790,6 +868,7 @@ __global__ void __launch_bounds__(LongCfgBar<D>::THREADS, 1) spmm_long_rows_bar(
 
 // Split rows: total = ((p0 + p1) + p2) + ... in segment order, then the usual epilogue.
 __global__ void spmm_combine_parts(const SpmmArgs a, int d) {
+    __shared__ float srow[256];
     const int sidx = blockIdx.x;
     const int r = a.split_rows[sidx];
     const int first = a.split_rows[a.n_split + sidx];
@@ -797,6 +876,10 @@ __global__ void spmm_combine_parts(const SpmmArgs a, int d) {
     for (int f = threadIdx.x; f < d; f += blockDim.x) {
         float t = a.part_buf[(long long)first * d + f];
         for (int k = 1; k < n; ++k) t = __fadd_rn(t, a.part_buf[(long long)(first + k) * d + f]);
+        if (a.map) {                // dense-map epilogue below (d <= 256)
+            srow[f] = t;
+            continue;
+        }
         if (a.y) reinterpret_cast<float *>(a.y + (long long)r * a.ldy4)[f] = t;
         if (a.peer_multicast) {
             st_multimem_f1(reinterpret_cast<float *>(a.peer_y[0] + (a.peer_row_off + r) * a.ldy4) + f, t);
@@ -813,6 +896,19 @@ __global__ void spmm_combine_parts(const SpmmArgs a, int d) {
             reinterpret_cast<float *>(a.out + (long long)r * a.ldo4)[f] = apply_scale(o, a.scale, a.scale_mode);
         }
     }
+    if (a.map) {
+        __syncthreads();
+        const float beta = map_beta_of(a);
+        for (int f = threadIdx.x; f < d; f += blockDim.x) {
+            float o = 0.f;
+            for (int i = 0; i < d; ++i)
+                o = __fmaf_rn(srow[i], a.map_transposed ? __ldg(a.map + f * d + i) : __ldg(a.map + i * d + f), o);
+            if (a.y) reinterpret_cast<float *>(a.y + (long long)r * a.ldy4)[f] = __fmul_rn(srow[f], a.map_alpha);
+            o = __fmul_rn(o, a.map_alpha);
+            if (a.addend) o = __fmaf_rn(beta, reinterpret_cast<const float *>(a.addend + (long long)r * a.lda4)[f], o);
+            reinterpret_cast<float *>(a.out + (long long)r * a.ldo4)[f] = o;
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -822,6 +918,7 @@ struct SideStream {
     cudaStream_t stream = nullptr;
     cudaEvent_t fork = nullptr, join = nullptr;
     bool smem_attr_set[4] = {false, false, false, false};
+    bool smem_attr_set_map[4] = {false, false, false, false};
 };
 
 // One high-priority side stream (+ fork/join events) per (device, caller stream): the long-row kernel of a
@@ -868,6 +965,15 @@ static int launch(const SpmmArgs &base, int n_long, long long n_rows, int slot, 
             GR_CUDA_CHECK(cudaFuncSetAttribute(k_mc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
             side->smem_attr_set[slot] = true;
         }
+        // dense-map epilogue (d <= 64: the barrier pipeline): the map and a staging row follow the rings
+        constexpr size_t kSmemMap = kSmem + (size_t)D * D * 4 + (size_t)D * 4;
+        if constexpr (kBar) {
+            if (base.map && !side->smem_attr_set_map[slot]) {
+                GR_CUDA_CHECK(cudaFuncSetAttribute(spmm_long_rows_bar<D, kPeersNone, true>,
+                                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMap));
+                side->smem_attr_set_map[slot] = true;
+            }
+        }
         // GR_LONG_SERIAL=1: long rows first on the caller's stream instead of concurrently on the side stream
         static const bool serial_long = [] { const char *e = getenv("GR_LONG_SERIAL"); return e && atoi(e) != 0; }();
         cudaStream_t ls = serial_long ? stream : side->stream;
@@ -882,7 +988,9 @@ static int launch(const SpmmArgs &base, int n_long, long long n_rows, int slot, 
         int long_ctas = sm_count();
         if (long_ctas > n_work) long_ctas = n_work;
         if (long_ctas < 1) long_ctas = 1;
-        if (la.n_peers > 0 && la.peer_multicast)
+        if (la.map) {
+            if constexpr (kBar) spmm_long_rows_bar<D, kPeersNone, true><<<long_ctas, kThreads, kSmemMap, ls>>>(la);
+        } else if (la.n_peers > 0 && la.peer_multicast)
             k_mc<<<long_ctas, kThreads, kSmem, ls>>>(la);
         else if (la.n_peers > 0)
             k_p2p<<<long_ctas, kThreads, kSmem, ls>>>(la);
@@ -904,7 +1012,12 @@ static int launch(const SpmmArgs &base, int n_long, long long n_rows, int slot, 
         const long long per_cta = (long long)kWarpsPerCta * C::RPW;
         const long long ctas = (base.n_groups + per_cta - 1) / per_cta;
         if (ctas > 0) {
-            if (base.n_peers > 0 && base.peer_multicast)
+            if (base.map) {
+                if constexpr (D <= 64) {
+                    constexpr size_t kMapSmem = (size_t)D * D * 4 + (size_t)kWarpsPerCta * C::RPW * D * 4;
+                    spmm_stream_rows<D, kPeersNone, true><<<(unsigned)ctas, kWarpsPerCta * 32, kMapSmem, stream>>>(wa);
+                }
+            } else if (base.n_peers > 0 && base.peer_multicast)
                 spmm_stream_rows<D, kPeersMulticast><<<(unsigned)ctas, kWarpsPerCta * 32, 0, stream>>>(wa);
             else if (base.n_peers > 0)
                 spmm_stream_rows<D, kPeersP2P><<<(unsigned)ctas, kWarpsPerCta * 32, 0, stream>>>(wa);
@@ -974,15 +1087,16 @@ extern "C" int gr_peer_scatter_rows(const float *src, int64_t lds, int64_t n_row
     return GR_OK;
 }
 
-extern "C" int gr_spmm_csr_f32(const int32_t *indptr, const int32_t *indices, const float *vals,
-                               const int32_t *row_order, int32_t n_long, const int32_t *long_items,
-                               int32_t n_long_items, const int32_t *split_rows, int32_t n_split, float *part_buf,
-                               const int32_t *group_ptr,
-                               int32_t n_groups, int32_t long_threshold, int64_t n_rows, int32_t d, const float *x,
-                               int64_t ldx, float *y, int64_t ldy, const float *addend, int64_t lda, float *out,
-                               int64_t ldo, float scale, int32_t scale_mode, float *const *peer_y_host,
-                               int32_t n_peers, int32_t peer_multicast, int64_t peer_row_offset, int32_t peer_route_block,
-                               uint32_t *sched_ws, void *stream) {
+static int spmm_entry(const int32_t *indptr, const int32_t *indices, const float *vals,
+                      const int32_t *row_order, int32_t n_long, const int32_t *long_items,
+                      int32_t n_long_items, const int32_t *split_rows, int32_t n_split, float *part_buf,
+                      const int32_t *group_ptr,
+                      int32_t n_groups, int32_t long_threshold, int64_t n_rows, int32_t d, const float *x,
+                      int64_t ldx, float *y, int64_t ldy, const float *addend, int64_t lda, float *out,
+                      int64_t ldo, float scale, int32_t scale_mode, float *const *peer_y_host,
+                      int32_t n_peers, int32_t peer_multicast, int64_t peer_row_offset, int32_t peer_route_block,
+                      const float *map, int32_t map_transposed, float map_alpha, float map_beta,
+                      const float *map_beta_dev, uint32_t *sched_ws, void *stream) {
     using namespace gr;
     if (n_rows == 0) return GR_OK;
     if (row_order && n_long > 0 && !sched_ws) return GR_ERR_INVALID;      // long-row scheduler needs its 2 words
@@ -1030,6 +1144,15 @@ extern "C" int gr_spmm_csr_f32(const int32_t *indptr, const int32_t *indices, co
     if (a.route_block > 0 && (a.peer_multicast || n_peers < 1 || (n_rows + a.route_block - 1) / a.route_block > n_peers))
         return GR_ERR_INVALID;
     a.sched = sched_ws;
+    a.map = map;
+    a.map_transposed = map_transposed ? 1 : 0;
+    a.map_alpha = map_alpha;
+    a.map_beta = map_beta;
+    a.map_beta_dev = map_beta_dev;
+    if (map) {   // dense-map epilogue: d <= 64, streaming schedule, single GPU, result in `out`
+        if (d > 64 || !group_ptr || n_peers != 0) return GR_ERR_UNSUPPORTED;
+        if (!out || !aligned16(map)) return GR_ERR_INVALID;
+    }
     for (int p = 0; p < kMaxPeers; ++p) {
         a.peer_y[p] = p < n_peers ? reinterpret_cast<float4 *>(peer_y_host[p]) : nullptr;
         if (p < n_peers && (!peer_y_host[p] || !aligned16(peer_y_host[p]))) return GR_ERR_INVALID;
@@ -1043,4 +1166,32 @@ extern "C" int gr_spmm_csr_f32(const int32_t *indptr, const int32_t *indices, co
         case 256: return launch<256>(a, n_long, n_rows, 3, s);
         default: return GR_ERR_UNSUPPORTED;
     }
+}
+
+extern "C" int gr_spmm_csr_f32(const int32_t *indptr, const int32_t *indices, const float *vals,
+                               const int32_t *row_order, int32_t n_long, const int32_t *long_items,
+                               int32_t n_long_items, const int32_t *split_rows, int32_t n_split, float *part_buf,
+                               const int32_t *group_ptr,
+                               int32_t n_groups, int32_t long_threshold, int64_t n_rows, int32_t d, const float *x,
+                               int64_t ldx, float *y, int64_t ldy, const float *addend, int64_t lda, float *out,
+                               int64_t ldo, float scale, int32_t scale_mode, float *const *peer_y_host,
+                               int32_t n_peers, int32_t peer_multicast, int64_t peer_row_offset, int32_t peer_route_block,
+                               uint32_t *sched_ws, void *stream) {
+    return spmm_entry(indptr, indices, vals, row_order, n_long, long_items, n_long_items, split_rows, n_split, part_buf,
+                      group_ptr, n_groups, long_threshold, n_rows, d, x, ldx, y, ldy, addend, lda, out, ldo, scale,
+                      scale_mode, peer_y_host, n_peers, peer_multicast, peer_row_offset, peer_route_block, nullptr, 0,
+                      1.f, 0.f, nullptr, sched_ws, stream);
+}
+
+extern "C" int gr_spmm_csr_map_f32(const int32_t *indptr, const int32_t *indices, const float *vals,
+                                   const int32_t *row_order, int32_t n_long, const int32_t *long_items,
+                                   int32_t n_long_items, const int32_t *split_rows, int32_t n_split, float *part_buf,
+                                   const int32_t *group_ptr, int32_t n_groups, int32_t long_threshold, int64_t n_rows,
+                                   int32_t d, const float *x, int64_t ldx, float *y, int64_t ldy, const float *addend,
+                                   int64_t lda, float *out, int64_t ldo, const float *map, int32_t map_transposed,
+                                   float alpha, float beta, const float *beta_dev, uint32_t *sched_ws, void *stream) {
+    if (!map) return GR_ERR_INVALID;
+    return spmm_entry(indptr, indices, vals, row_order, n_long, long_items, n_long_items, split_rows, n_split, part_buf,
+                      group_ptr, n_groups, long_threshold, n_rows, d, x, ldx, y, ldy, addend, lda, out, ldo, 1.f,
+                      GR_SCALE_NONE, nullptr, 0, 0, 0, 0, map, map_transposed, alpha, beta, beta_dev, sched_ws, stream);
 }

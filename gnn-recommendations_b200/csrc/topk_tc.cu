@@ -13,16 +13,16 @@
 //
 // One CTA = 128 eval users (UMMA M = 128) against one item range (blockIdx.y; 1-4 ranges per user tile fill
 // the SMs evenly) in tiles of 64 items (UMMA N = 64):
-//   warps 0-3            : load the user tile once (rows gathered through eval_users) into the K-major
+//   warps 0-1            : load the user tile once (rows gathered through eval_users) into the K-major
 //                          SWIZZLE_128B canonical layout (32 tf32 per 128-byte row, 8-row atoms, 16-byte
 //                          chunks XOR-swizzled); then
 //   warp 0, one lane     : TMA producer — per item tile d/32 cp.async.bulk.tensor.2d boxes (32 floats x 64
 //                          rows, SWIZZLE_128B; rows past the catalogue are zero-filled by the hardware) into
 //                          a two-stage ring, completion by mbarrier complete_tx
-//                          (GR_TC_NO_TMA=1: the four warps copy LDG -> swizzled STS instead)
-//   warp 8, one lane     : MMA issuer — d/8 tcgen05.mma (K = 8 per instruction) per tile into one of four
+//   warp 1, one lane     : MMA issuer — d/8 tcgen05.mma (K = 8 per instruction) per tile into one of four
 //                          64-column TMEM accumulators, tcgen05.commit to the stage / accumulator mbarriers
-//   warps 4-7  epilogue  : tcgen05.ld 32 columns at a time; thread = TMEM lane = one user.  Selection is
+//   warps 2-5  epilogue  : tcgen05.ld 32 columns at a time into two register sets (the load of the next chunk
+//                          is in flight while one is selected); thread = TMEM lane = one user.  Selection is
 //                          max-first: masked columns (seen items, catalogue tail) are set to -inf on the rare
 //                          chunks that have any, four 8-column FMNMX trees give the group maxima, and only a
 //                          group whose maximum beats the user's admission threshold is staged (8 values) and
@@ -44,7 +44,7 @@ constexpr int TC_N = 64;        // items per tile
 constexpr int TC_KB = 32;       // tf32 elements per 128-byte swizzle row
 constexpr int TC_STAGES = 2;    // item-tile stages in shared memory
 constexpr int TC_ACC = 4;       // TMEM accumulators of TC_N columns each
-constexpr int TC_THREADS = 288; // warps 0-3: user tile, then TMA producer (one lane) or loaders; 4-7: epilogue; 8: MMA issuer
+constexpr int TC_THREADS = 192; // warps 0-1: user tile, then TMA producer (warp 0) / MMA issuer (warp 1), one lane each; 2-5: epilogue
 constexpr int TC_GROUP = 8;     // columns per selection group
 constexpr int TC_KPRIME_MAX = 64;
 constexpr uint32_t TC_A_TILE = TC_M * 128;   // one k-block (32 tf32) of the user tile: 16 KB
@@ -67,7 +67,6 @@ struct TcArgs {
     int *cand_ids;       // [n_eval][gridDim.y][kprime]
     int *cand_cnt;       // [n_eval][gridDim.y]
     int *error;          // device flag: 1 = the kernel could not run (re-scoring flags every row)
-    int use_tma;         // item tiles by cp.async.bulk.tensor (1) or by the four loader warps (0)
     int debug;           // GR_TC_DEBUG bits (experiments): 1 = epilogue skips selection, 2 = producers skip loads,
                          // 4 = take the could-not-run path, 8 = queues are dropped instead of drained,
                          // 16 = filter only (no appends), bits 16.. = producer back-off in ns
@@ -96,17 +95,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
-// waiting role that is NOT on the critical path (producers, MMA issuer): back off between polls so the
-// spin does not take issue slots from the epilogue warp sharing the scheduler
-__device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, uint32_t parity, unsigned sleep_ns = 200) {
+// waiting role that is NOT on the critical path (TMA producer, MMA issuer): a non-blocking test and a plain
+// nanosleep between polls.  (try_wait with a suspend hint compiles to NANOSLEEP.SYNCS, which every mbarrier
+// event of the CTA wakes — with 128 epilogue arrivals per tile the two single-lane roles polled every ~25 ns
+// and took a third of the issue slots of the schedulers they share with two epilogue warps.)
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, uint32_t parity, unsigned sleep_ns = 100) {
     uint32_t done = 0;
     while (true) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done)
-            : "r"(smem_u32(bar)), "r"(parity), "r"(2000u)
+            : "r"(smem_u32(bar)), "r"(parity)
             : "memory");
         if (done) break;
         __nanosleep(sleep_ns);
@@ -143,20 +144,27 @@ __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *t
         "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
-    uint32_t r[32];
+// 32 columns of this warp's 32 TMEM lanes into r[]; the registers are valid only after tmem_ld_wait(r)
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, float (&r)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
         "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7]), "=f"(r[8]),
+          "=f"(r[9]), "=f"(r[10]), "=f"(r[11]), "=f"(r[12]), "=f"(r[13]), "=f"(r[14]), "=f"(r[15]), "=f"(r[16]),
+          "=f"(r[17]), "=f"(r[18]), "=f"(r[19]), "=f"(r[20]), "=f"(r[21]), "=f"(r[22]), "=f"(r[23]), "=f"(r[24]),
+          "=f"(r[25]), "=f"(r[26]), "=f"(r[27]), "=f"(r[28]), "=f"(r[29]), "=f"(r[30]), "=f"(r[31])
         : "r"(taddr)
         : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+// tcgen05.wait::ld; the registers of the load are in/out operands so that no use of them is scheduled above it
+__device__ __forceinline__ void tmem_ld_wait(float (&r)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+f"(r[0]), "+f"(r[1]), "+f"(r[2]), "+f"(r[3]), "+f"(r[4]), "+f"(r[5]), "+f"(r[6]), "+f"(r[7]),
+                   "+f"(r[8]), "+f"(r[9]), "+f"(r[10]), "+f"(r[11]), "+f"(r[12]), "+f"(r[13]), "+f"(r[14]), "+f"(r[15]),
+                   "+f"(r[16]), "+f"(r[17]), "+f"(r[18]), "+f"(r[19]), "+f"(r[20]), "+f"(r[21]), "+f"(r[22]), "+f"(r[23]),
+                   "+f"(r[24]), "+f"(r[25]), "+f"(r[26]), "+f"(r[27]), "+f"(r[28]), "+f"(r[29]), "+f"(r[30]), "+f"(r[31])
+                 :
+                 : "memory");
 }
 
 // K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address
@@ -286,7 +294,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) topk_tc_candidates_kernel(const
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(a_full + 1);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const unsigned sleep_ns = (a.debug >> 16) ? (unsigned)(a.debug >> 16) : 200u;
+    const unsigned sleep_ns = (a.debug >> 16) ? (unsigned)(a.debug >> 16) : 100u;
     const int row0 = blockIdx.x * TC_M;
     const int item_lo = (int)min((long long)a.n_items, (long long)blockIdx.y * a.split_items);
     const int item_hi = (int)min((long long)a.n_items, (long long)item_lo + a.split_items);
@@ -295,26 +303,26 @@ __global__ void __launch_bounds__(TC_THREADS, 2) topk_tc_candidates_kernel(const
 
     if (tid == 0) {
         for (int s = 0; s < TC_STAGES; ++s) {
-            mbar_init(&b_full[s], a.use_tma ? 1 : 128);   // TMA: one arrive.expect_tx; else 128 loader threads
-            mbar_init(&b_empty[s], 1);                    // tcgen05.commit
+            mbar_init(&b_full[s], 1);     // one arrive.expect_tx by the TMA producer
+            mbar_init(&b_empty[s], 1);    // tcgen05.commit
         }
         for (int s = 0; s < TC_ACC; ++s) {
             mbar_init(&t_full[s], 1);     // tcgen05.commit
-            mbar_init(&t_empty[s], 128);  // 128 epilogue threads
+            mbar_init(&t_empty[s], 4);    // one arrival per epilogue warp
         }
-        mbar_init(a_full, 128);
+        mbar_init(a_full, 64);            // the two loader warps of the user tile
         fence_barrier_init();
     }
-    if (warp == 8) tmem_alloc(tmem_slot, TC_ACC * TC_N);  // four 64-column fp32 accumulators
+    if (warp == 1) tmem_alloc(tmem_slot, TC_ACC * TC_N);  // four 64-column fp32 accumulators
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp < 4) {
+    if (warp < 2) {
         // ===== user tile, once (rows gathered through eval_users) =====
         const int f4_per_row = d / 4;
-        for (int idx = tid; idx < TC_M * f4_per_row; idx += 128) {
+        for (int idx = tid; idx < TC_M * f4_per_row; idx += 64) {
             const int r = idx / f4_per_row, f = idx % f4_per_row;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (row0 + r < a.n_eval) v = __ldg(reinterpret_cast<const float4 *>(a.user_emb + a.eval_users[row0 + r] * a.ldu) + f);
@@ -322,55 +330,22 @@ __global__ void __launch_bounds__(TC_THREADS, 2) topk_tc_candidates_kernel(const
         }
         fence_proxy_async();
         mbar_arrive(a_full);
-        if (a.use_tma) {
-            // ===== TMA producer: one lane =====
-            if (warp == 0 && lane == 0) {
-                for (int t = 0; t < n_tiles; ++t) {
-                    const int s = t % TC_STAGES;
-                    if (t >= TC_STAGES) mbar_wait_relaxed(&b_empty[s], ((t / TC_STAGES) - 1) & 1, sleep_ns);
-                    unsigned char *dst = sB + (size_t)s * nkb * TC_B_TILE;
-                    if ((a.debug & 2) && t >= TC_STAGES) {
-                        mbar_arrive(&b_full[s]);
-                        continue;
-                    }
-                    mbar_arrive_expect_tx(&b_full[s], (uint32_t)nkb * TC_B_TILE);
-                    for (int kb = 0; kb < nkb; ++kb)
-                        tma_load_2d(dst + (size_t)kb * TC_B_TILE, &tmap, &b_full[s], kb * TC_KB, item_lo + t * TC_N);
-                }
-            }
-        } else {
-            // ===== loader warps: LDG -> swizzled STS =====
+        if (warp == 0 && lane == 0) {
+            // ===== TMA producer =====
             for (int t = 0; t < n_tiles; ++t) {
                 const int s = t % TC_STAGES;
                 if (t >= TC_STAGES) mbar_wait_relaxed(&b_empty[s], ((t / TC_STAGES) - 1) & 1, sleep_ns);
                 unsigned char *dst = sB + (size_t)s * nkb * TC_B_TILE;
-                const int i0 = item_lo + t * TC_N;
-                // 8 independent 16-byte loads in flight per thread, then their swizzled stores
-                for (int base = (a.debug & 2) && t >= TC_STAGES ? TC_N * f4_per_row : 0; base < TC_N * f4_per_row; base += 128 * 8) {
-                    float4 v[8];
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const int idx = base + q * 128 + tid;
-                        const int r = idx / f4_per_row, f = idx % f4_per_row;
-                        v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (idx < TC_N * f4_per_row && i0 + r < item_hi)
-                            v[q] = __ldg(reinterpret_cast<const float4 *>(a.item_emb + (long long)(i0 + r) * a.ldi) + f);
-                    }
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const int idx = base + q * 128 + tid;
-                        const int r = idx / f4_per_row, f = idx % f4_per_row;
-                        if (idx < TC_N * f4_per_row)
-                            *reinterpret_cast<float4 *>(dst + (size_t)(f >> 3) * TC_B_TILE + sw128_offset(r, f & 7)) = v[q];
-                    }
+                if ((a.debug & 2) && t >= TC_STAGES) {
+                    mbar_arrive(&b_full[s]);
+                    continue;
                 }
-                fence_proxy_async();
-                mbar_arrive(&b_full[s]);
+                mbar_arrive_expect_tx(&b_full[s], (uint32_t)nkb * TC_B_TILE);
+                for (int kb = 0; kb < nkb; ++kb)
+                    tma_load_2d(dst + (size_t)kb * TC_B_TILE, &tmap, &b_full[s], kb * TC_KB, item_lo + t * TC_N);
             }
-        }
-    } else if (warp == 8) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
+        } else if (warp == 1 && lane == 0) {
+            // ===== MMA issuer =====
             mbar_wait_relaxed(a_full, 0, sleep_ns);
             for (int t = 0; t < n_tiles; ++t) {
                 const int s = t % TC_STAGES, acc = t % TC_ACC;
@@ -392,8 +367,10 @@ __global__ void __launch_bounds__(TC_THREADS, 2) topk_tc_candidates_kernel(const
             }
         }
     } else {
-        // ===== epilogue: thread = TMEM lane = one user row =====
-        const int m = (warp & 3) * 32 + lane;
+        // ===== epilogue (warps 2-5): thread = TMEM lane = one user row; warp w reads TMEM lanes 32 (w % 4).. =====
+        const int quarter = warp & 3;
+        const int m = quarter * 32 + lane;
+        const uint32_t tmem_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
         const bool user_ok = row0 + m < a.n_eval;
         const int K = a.kprime;
         int cnt = 0;                 // heap entries
@@ -414,61 +391,82 @@ __global__ void __launch_bounds__(TC_THREADS, 2) topk_tc_candidates_kernel(const
             sc = (int)lo;
         }
         int next_seen = sc < se ? a.seen_items[sc] : kNoSeen;     // absolute item id
-        for (int t = 0; t < n_tiles; ++t) {
-            const int acc = t % TC_ACC;
-            mbar_wait(&t_full[acc], (t / TC_ACC) & 1);
-            tc_fence_after();
-            const int i0 = item_lo + t * TC_N;
-#pragma unroll 1
-            for (int c = 0; c < TC_N / 32; ++c) {
-                float v[32];
-                tmem_ld32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(acc * TC_N + c * 32), v);
-                if (a.debug & 1) continue;
-                const int cbase = i0 + c * 32;
-                // columns that must not be nominated: seen items of this user, padding beyond the range
-                unsigned kill = 0;
-                while (next_seen < cbase + 32) {          // next_seen is prefetched: no load on the common path
-                    if (next_seen >= cbase) kill |= 1u << (next_seen - cbase);
-                    ++sc;
-                    next_seen = sc < se ? a.seen_items[sc] : kNoSeen;
-                }
-                const int room = item_hi - cbase;
-                if (room < 32) kill |= room <= 0 ? 0xffffffffu : ~((1u << room) - 1u);
-                if (kill) {
+
+        // selection over one 32-column chunk held in registers (scores of items cbase .. cbase + 31)
+        auto select = [&](float (&v)[32], const int cbase) {
+            if (a.debug & 1) return;
+            // columns that must not be nominated: seen items of this user, padding beyond the range
+            unsigned kill = 0;
+            while (next_seen < cbase + 32) {          // next_seen is prefetched: no load on the common path
+                if (next_seen >= cbase) kill |= 1u << (next_seen - cbase);
+                ++sc;
+                next_seen = sc < se ? a.seen_items[sc] : kNoSeen;
+            }
+            const int room = item_hi - cbase;
+            if (room < 32) kill |= room <= 0 ? 0xffffffffu : ~((1u << room) - 1u);
+            if (kill) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if ((kill >> j) & 1u) v[j] = -CUDART_INF_F;
-                }
-                // max-first filter: one FMNMX tree per 8 columns, one compare per group
-                unsigned hit = 0;
+                for (int j = 0; j < 32; ++j)
+                    if ((kill >> j) & 1u) v[j] = -CUDART_INF_F;
+            }
+            // max-first filter: one FMNMX tree per 8 columns, one compare per group
+            unsigned hit = 0;
 #pragma unroll
-                for (int gq = 0; gq < 32 / TC_GROUP; ++gq) hit |= (unsigned)(max8(v + gq * TC_GROUP) > thr) << gq;
-                if (!__any_sync(0xffffffffu, hit != 0)) continue;     // the warp stays converged here
-                if (a.debug & 16) continue;
-                // groups some lane passed: predicated appends to the pending queues (warp-uniform branch per group)
+            for (int gq = 0; gq < 32 / TC_GROUP; ++gq) hit |= (unsigned)(max8(v + gq * TC_GROUP) > thr) << gq;
+            if (!__any_sync(0xffffffffu, hit != 0)) return;       // the warp stays converged here
+            if (a.debug & 16) return;
+            // groups some lane passed: predicated appends to the pending queues (warp-uniform branch per group)
 #pragma unroll
-                for (int gq = 0; gq < 32 / TC_GROUP; ++gq) {
-                    if (__any_sync(0xffffffffu, (hit >> gq) & 1u)) {
+            for (int gq = 0; gq < 32 / TC_GROUP; ++gq) {
+                if (__any_sync(0xffffffffu, (hit >> gq) & 1u)) {
 #pragma unroll
-                        for (int j = 0; j < TC_GROUP; ++j) {
-                            if (v[gq * TC_GROUP + j] > thr) {
-                                pend_append(wp, v[gq * TC_GROUP + j], cbase + gq * TC_GROUP + j);
-                                wp += TC_M * 4;
-                            }
+                    for (int j = 0; j < TC_GROUP; ++j) {
+                        if (v[gq * TC_GROUP + j] > thr) {
+                            pend_append(wp, v[gq * TC_GROUP + j], cbase + gq * TC_GROUP + j);
+                            wp += TC_M * 4;
                         }
-                        if (__any_sync(0xffffffffu, wp > wp_limit)) {   // the next group may not fit
-                            if (!(a.debug & 8)) {
-                                const SelState st = tc_drain(ls, li, pend_s, pend_i, m, K, cnt, thr, (int)(wp - wp0) / (TC_M * 4));
-                                cnt = st.cnt;
-                                thr = st.thr;
-                            }
-                            wp = wp0;
+                    }
+                    if (__any_sync(0xffffffffu, wp > wp_limit)) {   // the next group may not fit
+                        if (!(a.debug & 8)) {
+                            const SelState st = tc_drain(ls, li, pend_s, pend_i, m, K, cnt, thr, (int)(wp - wp0) / (TC_M * 4));
+                            cnt = st.cnt;
+                            thr = st.thr;
                         }
+                        wp = wp0;
                     }
                 }
             }
+        };
+
+        // Two register sets: while one chunk is being selected, the tcgen05.ld of the next one is in flight
+        // (TMEM latency was exposed per chunk with only two epilogue warps per scheduler).
+        float va[32], vb[32];
+        auto release = [&](int acc) {          // this warp has read everything it needs from accumulator `acc`
             tc_fence_before();
-            mbar_arrive(&t_empty[acc]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&t_empty[acc]);
+        };
+        if (n_tiles > 0) {
+            mbar_wait(&t_full[0], 0);
+            tc_fence_after();
+            tmem_ld32_issue(tmem_row, va);
+            tmem_ld_wait(va);
+        }
+        for (int t = 0; t < n_tiles; ++t) {
+            const int acc = t % TC_ACC;
+            const int i0 = item_lo + t * TC_N;
+            tmem_ld32_issue(tmem_row + (uint32_t)(acc * TC_N + 32), vb);       // second half of tile t
+            select(va, i0);
+            tmem_ld_wait(vb);
+            release(acc);                                                       // every read of tile t has landed
+            if (t + 1 < n_tiles) {
+                const int nacc = (t + 1) % TC_ACC;
+                mbar_wait(&t_full[nacc], ((t + 1) / TC_ACC) & 1);
+                tc_fence_after();
+                tmem_ld32_issue(tmem_row + (uint32_t)(nacc * TC_N), va);       // first half of tile t + 1
+            }
+            select(vb, i0 + 32);
+            if (t + 1 < n_tiles) tmem_ld_wait(va);
         }
         {
             const SelState st = tc_drain(ls, li, pend_s, pend_i, m, K, cnt, thr, (int)(wp - wp0) / (TC_M * 4));
@@ -485,7 +483,10 @@ __global__ void __launch_bounds__(TC_THREADS, 2) topk_tc_candidates_kernel(const
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) tmem_dealloc(tmem_base, TC_ACC * TC_N);
+    if (warp == 1) {
+        __syncwarp();
+        tmem_dealloc(tmem_base, TC_ACC * TC_N);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -684,6 +685,7 @@ extern "C" size_t gr_topk_tc_workspace_bytes(int64_t n_eval, int32_t kprime) {
 }
 
 extern "C" int gr_topk_tc_supported(int32_t d, int32_t kprime) {
+    if (!encode_tiled_fn()) return 0;      // the driver has no cuTensorMapEncodeTiled: exact kernel only
     return (d > 0 && d % TC_KB == 0 && kprime > 0 && kprime <= TC_KPRIME_MAX && tc_smem_bytes(d, kprime) <= kSmemOneCta) ? 1 : 0;
 }
 
@@ -725,11 +727,9 @@ extern "C" int gr_score_topk_tc(const float *user_emb, int64_t ldu, const float 
     a.split_items = (int)split_items;
     a.cand_scores = cand_scores; a.cand_ids = cand_ids; a.cand_cnt = cand_cnt; a.error = tc_error;
     { const char *e = getenv("GR_TC_DEBUG"); a.debug = e ? atoi(e) : 0; }
-    // item tiles by TMA unless GR_TC_NO_TMA=1 (or the driver has no cuTensorMapEncodeTiled): then four loader warps
     CUtensorMap tmap;
     memset(&tmap, 0, sizeof(tmap));
-    { const char *e = getenv("GR_TC_NO_TMA"); a.use_tma = (e && atoi(e) != 0) ? 0 : 1; }
-    if (a.use_tma && !make_item_tensor_map(&tmap, item_emb, ldi, n_items, d)) a.use_tma = 0;
+    if (!make_item_tensor_map(&tmap, item_emb, ldi, n_items, d)) return GR_ERR_UNSUPPORTED;
     const size_t smem = tc_smem_bytes(d, kprime);
     GR_CUDA_CHECK(cudaFuncSetAttribute(topk_tc_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     topk_tc_candidates_kernel<<<dim3((unsigned)((n_eval + TC_M - 1) / TC_M), (unsigned)n_seg), TC_THREADS, smem, s>>>(a, tmap);

@@ -404,6 +404,40 @@ class NormAdjCSR:
         return y, out
 
 
+    def spmm_map(self, x: torch.Tensor, m: torch.Tensor, alpha: float = 1.0, beta: float = 0.0,
+                 addend: Optional[torch.Tensor] = None, beta_dev: Optional[torch.Tensor] = None,
+                 transposed: bool = False, want_y: bool = False,
+                 out: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+        """out = alpha * ((Â x) @ M) + beta * addend  (M^T with ``transposed``), y = alpha * (Â x) if ``want_y``:
+        the sparse product and the dense d x d map in one kernel (gr_spmm_csr_map_f32).  -> (out, y)."""
+        if not self.supports_map(int(x.shape[1])):
+            raise ValueError("spmm_map needs d <= 64 and the streaming schedule")
+        if x.dtype != torch.float32 or x.dim() != 2 or x.stride(1) != 1 or x.shape[0] != self.n_cols:
+            raise ValueError("x must be a row-major float32 matrix with one row per adjacency column")
+        d = int(x.shape[1])
+        if tuple(m.shape) != (d, d) or not m.is_contiguous() or m.dtype != torch.float32:
+            raise ValueError("the map must be a contiguous float32 d x d matrix")
+        y = torch.empty((self.n_rows, d), dtype=torch.float32, device=self.device) if want_y else None
+        if out is None:
+            out = torch.empty((self.n_rows, d), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            self.launches += 1 + (1 if (self.n_long > 0 and self.row_order is not None) else 0) + \
+                (1 if self.n_split > 0 else 0)
+            check(lib().gr_spmm_csr_map_f32(
+                ptr(self.indptr), ptr(self.indices), ptr(self.vals), ptr(self.row_order), self.n_long,
+                ptr(self.long_items), self.n_long_items, ptr(self.split_rows), self.n_split, ptr(self._parts(d)),
+                ptr(self.group_ptr), self.n_groups, self.long_threshold, self.n_rows,
+                d, ptr(x), x.stride(0), ptr(y), y.stride(0) if y is not None else 0,
+                ptr(addend), addend.stride(0) if addend is not None else 0, ptr(out), out.stride(0),
+                ptr(m), int(bool(transposed)), float(alpha), float(beta), ptr(beta_dev),
+                ptr(self._sched_words()), stream_ptr()), "gr_spmm_csr_map_f32")
+        return out, y
+
+    def supports_map(self, d: int) -> bool:
+        """gr_spmm_csr_map_f32 covers d = 32 / 64 on a matrix that carries the streaming schedule."""
+        return d in (32, 64) and self.group_ptr is not None
+
+
 def degree_lut(max_deg: int, power: float) -> np.ndarray:
     """``np.power(max(deg,1).astype(float32), power)`` for deg = 0..max_deg — the host numpy is
     the source of Â's values in the reference (graph_builder.py:114-119, 130)."""

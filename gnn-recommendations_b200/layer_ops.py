@@ -116,8 +116,9 @@ def _rowmap_raw(x1, wa, ba, x2, x3, wb, bb, resid, alpha, beta, act, slope, drop
 
 
 def _rowmap_bwd_raw(g, out, x1, wa, x2, x3, wb, resid, alpha, beta, act, slope, drop_p, drop_seed, need_dx, need_dx2,
-                    need_dx3, need_dresid, need_dw):
-    """-> (dx1, dx2, dx3, dresid, dw) — dw is the flat [nw*d_in*d_out + d_out] buffer of gr_rowmap_bwd."""
+                    need_dx3, need_dresid, need_dw, dw_out=None):
+    """-> (dx1, dx2, dx3, dresid, dw) — dw is the flat [nw*d_in*d_out + d_out] buffer of gr_rowmap_bwd
+    (``dw_out``: write it there instead of a new tensor)."""
     seed, seed_dev = _seed_parts(drop_seed)
     n, d_in = x1.shape
     d_out = wa.shape[1]
@@ -129,7 +130,7 @@ def _rowmap_bwd_raw(g, out, x1, wa, x2, x3, wb, resid, alpha, beta, act, slope, 
     dx3 = torch.empty((n, d_in), dtype=torch.float32, device=dev) if (need_dx3 and has_b) else None
     dres = torch.empty((n, d_out), dtype=torch.float32, device=dev) if need_dresid else None
     total = (2 if has_b else 1) * d_in * d_out + d_out
-    dw = torch.empty(total, dtype=torch.float32, device=dev) if need_dw else None
+    dw = (dw_out if dw_out is not None else torch.empty(total, dtype=torch.float32, device=dev)) if need_dw else None
     ws_bytes = l.gr_rowmap_bwd_workspace_bytes(n, d_in, d_out, int(has_b))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
@@ -294,6 +295,128 @@ def gs_compose(skew: torch.Tensor, perm_c: Optional[torch.Tensor], perm_g: torch
     int64 -> M [L, d, d] with M_l = blockdiag(exp(P - P^T))[:, perm_c] @ blockdiag(exp(Q - Q^T))[:, perm_g]
     (bundle_layer.py:59-73, group_shuffle_layer.py:88-129, model.py:176); differentiable w.r.t. skew."""
     return _GsCompose.apply(skew, None if perm_c is None else perm_c.contiguous(), perm_g.contiguous())
+
+
+class _SpmmMap(torch.autograd.Function):
+    """out = alpha (Â x) M' + beta R with M' = M or M^T (gr_spmm_csr_map_f32), differentiable w.r.t. x, M and R.
+    Backward: dx = alpha (Â^T g) M'^T (the same fused kernel), dM' = (alpha Â x)^T g (gr_rowmap_bwd's
+    weight-gradient kernels on the stored aggregate), dR = beta g (gr_layer_combine)."""
+
+    @staticmethod
+    def forward(ctx, x, m, resid, csr, alpha, beta, transposed):
+        x, m, resid = _rows(x), m.contiguous(), _rows(resid)
+        keep_c = ctx.needs_input_grad[1]
+        out, c = csr.spmm_map(x, m, alpha, beta, addend=resid, transposed=transposed, want_y=keep_c)
+        ctx.csr, ctx.cfg = csr, (float(alpha), float(beta), bool(transposed), resid is not None)
+        ctx.save_for_backward(m, c)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        m, c = ctx.saved_tensors
+        alpha, beta, transposed, has_res = ctx.cfg
+        g = _rows(g)
+        dev, d = g.device, int(g.shape[1])
+        dx = dm = dres = None
+        if ctx.needs_input_grad[0]:
+            dx, _ = ctx.csr.transpose().spmm_map(g, m, alpha, 0.0, transposed=not transposed)
+        if ctx.needs_input_grad[1]:
+            dw = torch.empty(d * d + d, dtype=torch.float32, device=dev)
+            _rowmap_bwd_raw(g, None, c, m, None, None, None, None, 1.0, 0.0, ACT_NONE, 0.0, 0.0, 0,
+                            False, False, False, False, True, dw_out=dw)
+            dm = dw[:d * d].view(d, d)                   # (alpha Â x)^T g = dL/dM'
+            if transposed:
+                dm = dm.t()
+        if has_res and ctx.needs_input_grad[2]:
+            key = (str(dev), 1, beta)
+            wb = _GS_X0_WEIGHTS.get(key)
+            if wb is None:
+                wb = _GS_X0_WEIGHTS[key] = torch.tensor([beta], dtype=torch.float32, device=dev)
+            dres = _combine_raw([g], wb)
+        return dx, dm, dres, None, None, None, None
+
+
+def spmm_map(csr: NormAdjCSR, x: torch.Tensor, m: torch.Tensor, alpha: float = 1.0, beta: float = 0.0,
+             resid: Optional[torch.Tensor] = None, transposed: bool = False) -> torch.Tensor:
+    """alpha (Â x) M + beta resid  (M^T with ``transposed``) in one kernel, with autograd; needs csr.supports_map(d)."""
+    return _SpmmMap.apply(x, m, resid, csr, float(alpha), float(beta), bool(transposed))
+
+
+class _GsPropagate(torch.autograd.Function):
+    """The whole Group-and-Shuffle propagation (model.py:164-207) as ONE autograd node:
+
+        x_{l+1} = alpha (Â x_l) M_l + beta x_0      (l = 0 .. L-1; alpha = 1 - residual_alpha, beta = residual_alpha)
+        out     = sum_l w_l x_l
+
+    Forward: one gr_spmm_csr_map_f32 per layer (sparse product, dense map and residual in a single kernel; it also
+    leaves c_l = alpha Â x_l for the weight gradient when a backward pass will follow) + gr_layer_combine.
+    Backward, written out by hand so that no elementwise torch kernel is left between the layers:
+        gx_L = w_L G;   for l = L .. 1:   dM_l = c_{l-1}^T gx_l   (gr_rowmap_bwd, weight-gradient part)
+                                          gx_{l-1} = w_{l-1} G + alpha (Â^T gx_l) M_l^T   (the same fused kernel)
+        dx_0 = gx_0 + beta (gx_1 + .. + gx_L)  (gr_layer_combine),   dw_l = <G, x_l>  (gr_layer_combine_dw)."""
+
+    @staticmethod
+    def forward(ctx, x0, ms, w, csr, alpha, beta):
+        x0, ms, w = _rows(x0), ms.contiguous(), w.contiguous()
+        n_layers = int(ms.shape[0])
+        keep = any(ctx.needs_input_grad[:3])
+        xs, cs, x = [x0], [], x0
+        for l in range(n_layers):
+            x, c = csr.spmm_map(x, ms[l], alpha, beta, addend=x0, want_y=keep)
+            xs.append(x)
+            cs.append(c)
+        ctx.csr, ctx.cfg = csr, (float(alpha), float(beta), n_layers)
+        if keep:
+            ctx.save_for_backward(ms, w, *xs, *cs)
+        return _combine_raw(xs, w)
+
+    @staticmethod
+    def backward(ctx, G):
+        ms, w, *rest = ctx.saved_tensors
+        alpha, beta, n_layers = ctx.cfg
+        xs, cs = rest[:n_layers + 1], rest[n_layers + 1:]
+        G = _rows(G)
+        dev, d = G.device, int(G.shape[1])
+        csr_t = ctx.csr.transpose()
+        dms = torch.empty((n_layers, d * d + d), dtype=torch.float32, device=dev)     # [dM_l | column sums (unused)]
+        gxs = [None] * (n_layers + 1)
+        gxs[n_layers] = _combine_raw([G], w[n_layers:n_layers + 1])
+        for l in range(n_layers, 0, -1):
+            g = gxs[l]
+            _rowmap_bwd_raw(g, None, cs[l - 1], ms[l - 1], None, None, None, None, 1.0, 0.0, ACT_NONE, 0.0, 0.0, 0,
+                            False, False, False, False, True, dw_out=dms[l - 1])
+            gxs[l - 1], _ = csr_t.spmm_map(g, ms[l - 1], alpha, 1.0, addend=G, beta_dev=w[l - 1:l], transposed=True)
+        key = (str(dev), n_layers, beta)
+        wx0 = _GS_X0_WEIGHTS.get(key)
+        if wx0 is None:
+            wx0 = _GS_X0_WEIGHTS[key] = torch.tensor([1.0] + [beta] * n_layers, dtype=torch.float32, device=dev)
+        dx0 = _combine_raw(gxs, wx0)
+        l_ = lib()
+        ws_bytes = l_.gr_layer_combine_bwd_workspace_bytes()
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        dw8 = torch.empty(8, dtype=torch.float32, device=dev)
+        n = n_layers + 1
+        ptrs = (C.c_void_p * n)(*[x.data_ptr() for x in xs])
+        lds = (C.c_int64 * n)(*[x.stride(0) for x in xs])
+        with torch.cuda.device(dev):
+            check(l_.gr_layer_combine_dw(ptrs, lds, n, ptr(G), G.stride(0), G.shape[0], d, ptr(dw8), ptr(ws), ws_bytes,
+                                         stream_ptr()), "gr_layer_combine_dw")
+        return dx0, dms[:, :d * d].view(n_layers, d, d), dw8[:n], None, None, None
+
+
+_GS_X0_WEIGHTS = {}
+
+
+def gs_propagate(csr: NormAdjCSR, x0: torch.Tensor, ms: torch.Tensor, w: torch.Tensor, alpha: float,
+                 beta: float) -> torch.Tensor:
+    """sum_l w[l] x_l with x_{l+1} = alpha (Â x_l) ms[l] + beta x_0 — the Group-and-Shuffle propagation with the
+    dense map fused into the SpMM epilogue (gr_spmm_csr_map_f32), forward and backward.  Needs
+    ``csr.supports_map(d)`` and at most 7 layers."""
+    return _GsPropagate.apply(x0, ms, w, csr, float(alpha), float(beta))
+
+
+def gs_propagate_supported(csr: NormAdjCSR, d: int, n_layers: int) -> bool:
+    return csr.supports_map(d) and n_layers + 1 <= 8
 
 
 # ------------------------------------------------------------------------------------------------

@@ -5,11 +5,13 @@ Per layer the reference computes  c = Â x ; t = c @ W_conn ; g = (t @ W_orth)[:
 x = (1-a) g + a x0.  The two 64x64 maps and the column permutation compose into one matrix
 M = W_conn (W_orth[:, perm]) built on the device by gr_gs_compose (block matrix exponentials +
 composition in two launches for all layers; backward gr_gs_compose_bwd through the adjoint Frechet
-derivative of exp — the reference runs 48 matrix_exp calls per forward), so a layer is one SpMM
-kernel plus one rowmap kernel (dense map + residual fused; backward gr_rowmap_bwd); the layer
-outputs are combined with softmax(layer_weights).  State-dict keys, constructor signature and
-RNG order match the reference.  The edge-list mode (use_edge_index=True, off by default,
-model.py:64) is not part of the hot path and raises NotImplementedError."""
+derivative of exp — the reference runs 48 matrix_exp calls per forward), and a layer is ONE kernel:
+gr_spmm_csr_map_f32 applies M and the residual in the SpMM epilogue while the aggregated row is still on
+the SM (layer_ops.gs_propagate, forward and backward; d <= 64, no layer dropout).  Otherwise — dropout
+> 0 in train mode, other widths — a layer is the SpMM kernel plus the rowmap kernel (backward
+gr_rowmap_bwd).  The layer outputs are combined with softmax(layer_weights).  State-dict keys, constructor signature and
+RNG order match the reference.  The edge-list mode (use_edge_index=True, off by default, model.py:64;
+parallel_transport.py:5-52) runs on the same kernels over a CSR of the edge list (_layers_edge_index)."""
 from __future__ import annotations
 
 from typing import Dict, List, Optional, Tuple
@@ -20,7 +22,9 @@ import torch.nn.functional as F
 
 from .base import BaseRecommender
 from .graph_builder import as_csr
-from .layer_ops import gs_compose, layer_combine, new_dropout_seed, rowmap, spmm
+from .graph_builder import NormAdjCSR
+from .layer_ops import (gs_compose, gs_propagate, gs_propagate_supported, layer_combine, new_dropout_seed, rowmap,
+                        spmm, spmm_map)
 
 
 def _block_orthogonal(skew_params) -> torch.Tensor:
@@ -126,10 +130,61 @@ class OrthogonalBundleGNN(BaseRecommender):
         perm_g = torch.stack([layer.perm for layer in self.local_transform_layers])
         return gs_compose(skew, perm_c, perm_g)
 
-    def _layers(self, adj_matrix, residual: bool) -> List[torch.Tensor]:
+    def _edge_csr(self, edge_index: torch.Tensor) -> NormAdjCSR:
+        """The edge list of the edge-list mode as a CSR: row = destination, one entry of value 1 per edge, in edge
+        order (a stable sort by destination), so the SpMM's storage-order chain adds the source rows in the order
+        ``index_add_`` does (parallel_transport.py:49-50, model.py:218-222).  Cached per edge_index tensor."""
+        key = (edge_index.data_ptr(), tuple(edge_index.shape), str(edge_index.device))
+        hit = getattr(self, "_edge_cache", None)
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        dev = self.user_embedding.weight.device
+        ei = edge_index.to(dev)
+        n = self.n_users + self.n_items
+        order = torch.sort(ei[1], stable=True).indices                      # plumbing: once per edge list
+        coo = torch.sparse_coo_tensor(torch.stack([ei[1][order], ei[0][order]]),
+                                      torch.ones(ei.shape[1], dtype=torch.float32, device=dev), (n, n))
+        csr = NormAdjCSR.from_torch_coo(coo)
+        self._edge_cache = (key, csr)
+        return csr
+
+    def _layers_edge_index(self, edge_index, residual: bool) -> List[torch.Tensor]:
+        """use_edge_index=True (model.py:159-181 with parallel_transport.py:5-52): per layer
+        x_j <- sum over edges (i -> j) of W_conn x_i, i.e. (E x) W_conn^T with E the edge-count matrix — the fused
+        SpMM + map kernel with the TRANSPOSED connection matrix — then the local Group-and-Shuffle map and the
+        residual (rowmap kernel).  Without parallel transport the first step is the plain sum E x (model.py:218-222)."""
+        if edge_index is None:
+            raise ValueError("edge_index must be provided when use_edge_index=True")
+        csr = self._edge_csr(edge_index)
+        x0 = torch.cat([self.user_embedding.weight, self.item_embedding.weight], dim=0)
+        nb, bs, L = self.embedding_dim // self.block_size, self.block_size, self.n_layers
+        loc = gs_compose(torch.stack([p for layer in self.local_transform_layers for p in layer.skew_params])
+                         .view(L, 1, nb, bs, bs), None, torch.stack([layer.perm for layer in self.local_transform_layers]))
+        conn = None
+        if self.use_parallel_transport:
+            conn = gs_compose(torch.stack([p for layer in self.connection_layers for p in layer.skew_params])
+                              .view(L, 1, nb, bs, bs), None,
+                              torch.stack([layer.shuffle_perm for layer in self.connection_layers]))
+        x, outs, a = x0, [x0], self.residual_alpha
+        fused = csr.supports_map(self.embedding_dim)
+        for l in range(L):
+            if conn is None:
+                t = spmm(csr, x)
+            elif fused:
+                t = spmm_map(csr, x, conn[l], transposed=True)
+            else:
+                t = rowmap(spmm(csr, x), conn[l].t().contiguous())
+            if residual:
+                p = self.dropout if (self.training and self.dropout_layer is not None) else 0.0
+                x = rowmap(t, loc[l], resid=x0, alpha=1.0 - a, beta=a, drop_p=p, drop_seed=new_dropout_seed() if p else 0)
+            else:
+                x = rowmap(t, loc[l])
+            outs.append(x)
+        return outs
+
+    def _layers(self, adj_matrix, residual: bool, edge_index=None) -> List[torch.Tensor]:
         if self.use_edge_index:
-            raise NotImplementedError("edge_index mode (model.py:218-222) is outside the B200 hot path; "
-                                      "use the adjacency-matrix mode (the reference default)")
+            return self._layers_edge_index(edge_index, residual)
         if adj_matrix is None:
             raise ValueError("adj_matrix must be provided when use_edge_index=False")
         csr = as_csr(adj_matrix)
@@ -149,8 +204,16 @@ class OrthogonalBundleGNN(BaseRecommender):
         return outs
 
     def propagate(self, adj_matrix=None, edge_index=None) -> torch.Tensor:
-        outs = self._layers(adj_matrix, residual=True)
         w = F.softmax(self.layer_weights, dim=0)
+        drop = self.dropout if (self.training and self.dropout_layer is not None) else 0.0
+        if not self.use_edge_index and adj_matrix is not None and drop == 0.0:
+            csr = as_csr(adj_matrix)
+            if gs_propagate_supported(csr, self.embedding_dim, self.n_layers):
+                # every layer = ONE kernel: sparse product, composed 64x64 map and residual in the SpMM epilogue
+                x0 = torch.cat([self.user_embedding.weight, self.item_embedding.weight], dim=0)
+                a = self.residual_alpha
+                return gs_propagate(csr, x0, self._layer_matrices(), w, 1.0 - a, a)
+        outs = self._layers(adj_matrix, residual=True, edge_index=edge_index)
         return layer_combine(outs, w)                         # sum([w_l * x_l]) of model.py:204-207, one kernel
 
     def forward(self, adj_matrix=None, edge_index=None) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -167,7 +230,7 @@ class OrthogonalBundleGNN(BaseRecommender):
     def get_layer_embeddings(self, adj_matrix=None, edge_index=None) -> List[torch.Tensor]:
         """model.py:306-356: per-layer outputs WITHOUT the residual (analysis helper)."""
         with torch.no_grad():
-            return [o.clone() for o in self._layers(adj_matrix, residual=False)]
+            return [o.clone() for o in self._layers(adj_matrix, residual=False, edge_index=edge_index)]
 
     def get_orthogonality_errors(self) -> torch.Tensor:
         return torch.stack([l.get_orthogonality_error() for l in self.local_transform_layers])

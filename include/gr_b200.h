@@ -141,6 +141,25 @@ int gr_spmm_csr_f32(const int32_t *indptr, const int32_t *indices, const float *
                     int32_t peer_multicast, int64_t peer_row_offset, int32_t peer_route_block, uint32_t *sched_ws,
                     void *stream);
 
+/* SpMM with a dense-map epilogue: one Group-and-Shuffle layer in one pass (replaces, for
+ * orthogonal_bundle/model.py:171-195, `torch.sparse.mm` + the `@ W_conn`, `@ W_orth`, `[:, perm]` products + the
+ * residual; W_conn W_orth[:, perm] is pre-composed into `map` by gr_gs_compose):
+ *     t = A x (the same storage-order fmaf chain as gr_spmm_csr_f32)
+ *     out[r,:] = alpha * (t[r,:] @ map) + beta * addend[r,:]        y[r,:] = alpha * t[r,:]   (y optional)
+ * `map` = d x d row-major fp32 in device memory (map_transposed != 0: map^T is applied — the backward of the
+ * layer is the same call on the transposed adjacency with map^T); beta is multiplied by *beta_dev when that
+ * device scalar is given (a softmax layer weight that lives on the device).  The finished row never leaves the
+ * SM between the sparse product and the map: no second launch, no N x d round trip.  d <= 64, streaming
+ * schedule (group_ptr) required, single GPU; otherwise GR_ERR_UNSUPPORTED (the caller then runs
+ * gr_spmm_csr_f32 + gr_rowmap_f32).  Schedule / sched_ws arguments as for gr_spmm_csr_f32. */
+int gr_spmm_csr_map_f32(const int32_t *indptr, const int32_t *indices, const float *vals,
+                        const int32_t *row_order, int32_t n_long, const int32_t *long_items,
+                        int32_t n_long_items, const int32_t *split_rows, int32_t n_split, float *part_buf,
+                        const int32_t *group_ptr, int32_t n_groups, int32_t long_threshold, int64_t n_rows,
+                        int32_t d, const float *x, int64_t ldx, float *y, int64_t ldy, const float *addend,
+                        int64_t lda, float *out, int64_t ldo, const float *map, int32_t map_transposed,
+                        float alpha, float beta, const float *beta_dev, uint32_t *sched_ws, void *stream);
+
 /* Fused compute + all-gather for the row-partitioned multi-GPU propagation (no reference
  * counterpart).  `peer_y_host` (HOST array of n_peers <= 8 DEVICE pointers, one per rank of the
  * box including this one, e.g. torch symmetric-memory buffer_ptrs) names every rank's gathered

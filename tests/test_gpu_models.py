@@ -451,6 +451,41 @@ def test_full_size_model_families_vs_oracle(case):
         assert abs(a - b) <= 1e-4 * max(abs(a), abs(b), 1e-12), (case, r, c, a, b)
 
 
+def test_gs_fused_propagation_equals_layerwise_path(tiny, csr):
+    """OrthogonalBundleGNN.propagate with the dense map fused into the SpMM epilogue (gs_propagate: one kernel per
+    layer, hand-written backward) against the layer-wise path (SpMM + rowmap kernels under autograd): same
+    embeddings and the same gradient for every parameter, to fp32 rounding."""
+    from gnn_recommendations_b200.layer_ops import gs_propagate_supported, layer_combine
+    nu, ni = int(tiny["n_users"]), int(tiny["n_items"])
+    torch.manual_seed(5)
+    model = g.OrthogonalBundleGNN(nu, ni, 64, 3, 8, 0.1, 0.0, 0.3).to(DEV)
+    with torch.no_grad():
+        model.layer_weights.copy_(torch.tensor([0.3, -0.2, 0.5, 0.1]))
+        model.user_embedding.weight.mul_(30.0)
+        model.item_embedding.weight.mul_(30.0)
+    assert gs_propagate_supported(csr, 64, 3)
+    probe = torch.randn(nu + ni, 64, generator=torch.Generator().manual_seed(1)).to(DEV)
+
+    def run(fused):
+        model.zero_grad()
+        if fused:
+            out = model.propagate(csr)
+        else:
+            outs = model._layers(csr, residual=True)
+            out = layer_combine(outs, torch.softmax(model.layer_weights, dim=0))
+        (out * probe).sum().backward()
+        return out.detach().clone(), {k: p.grad.detach().clone() for k, p in model.named_parameters()}
+
+    out_f, grads_f = run(True)
+    out_l, grads_l = run(False)
+    assert float((out_f - out_l).abs().max()) <= 2e-6 * float(out_l.abs().max())
+    for k, gl in grads_l.items():
+        gf = grads_f[k]
+        assert gf is not None, k
+        tol = 1e-5 * float(gl.abs().max()) + 1e-9
+        assert float((gf - gl).abs().max()) <= tol, (k, float((gf - gl).abs().max()), float(gl.abs().max()))
+
+
 def test_dropout_seed_from_device_memory_equals_host_seed(tiny):
     """CUDA-graph replays refresh the dropout seed in DEVICE memory (layer_ops.DropSeed.dev): the kernels must
     draw the mask of host seed (value + device word), forward and backward, for the rowmap epilogue and the GAT

@@ -313,6 +313,50 @@ def test_spmm_split_rows_deterministic_segment_sums():
         assert np.array_equal(bits(out.cpu().numpy()), bits((add.numpy() + got) / np.float32(4.0)))
 
 
+@pytest.mark.parametrize("d", [32, 64])
+def test_spmm_dense_map_epilogue_short_long_and_split_rows(d):
+    """gr_spmm_csr_map_f32: out = alpha (A x) M + beta R and y = alpha (A x) from ONE kernel, on a graph with
+    short rows, long rows (CTA-cooperative kernel) and split rows (combine pass): the aggregate is the exact
+    fmaf chain of the plain SpMM (y bit-equal to alpha * t), the mapped row equals a float64 evaluation of
+    t M to fp32 accuracy; M^T, the device-resident beta factor and the no-residual form are covered."""
+    rng = np.random.default_rng(21 + d)
+    nu, ni = 6000, 50
+    # item 0: every user (split row); item 1: 1 500 users (long row, not split); the rest random (short rows)
+    u = np.concatenate([np.arange(nu), np.arange(1500), rng.integers(0, nu, 20000)])
+    i = np.concatenate([np.zeros(nu, dtype=np.int64), np.ones(1500, dtype=np.int64), rng.integers(2, ni, 20000)])
+    csr = g.NormAdjCSR.from_pairs(u, i, nu, ni, device=DEV)
+    csr.split_threshold, csr.split_segment = 2048, 1000
+    csr._schedule()
+    assert csr.n_split >= 1 and csr.n_long > csr.n_split and csr.supports_map(d)
+    n = nu + ni
+    gen = torch.Generator().manual_seed(d)
+    x = torch.randn(n, d, generator=gen).to(DEV)
+    m = (torch.randn(d, d, generator=gen) / np.sqrt(d)).to(DEV)
+    r = torch.randn(n, d, generator=gen).to(DEV)
+    t, _ = csr.spmm(x)
+    t64 = t.double()
+    alpha, beta = 0.9, 0.1
+    out, y = csr.spmm_map(x, m, alpha, beta, addend=r, want_y=True)
+    assert np.array_equal(bits(y.cpu().numpy()), bits((t * np.float32(alpha)).cpu().numpy()))
+    want = alpha * (t64 @ m.double()) + beta * r.double()
+    scale = float(want.abs().max())
+    assert float((out.double() - want).abs().max()) <= 2e-6 * scale
+    # transposed map, beta read from device memory (0.1 * 0.5), no y
+    bdev = torch.tensor([0.5], device=DEV)
+    out_t, y_t = csr.spmm_map(x, m, alpha, beta, addend=r, beta_dev=bdev, transposed=True)
+    assert y_t is None
+    want_t = alpha * (t64 @ m.double().T) + beta * 0.5 * r.double()
+    assert float((out_t.double() - want_t).abs().max()) <= 2e-6 * float(want_t.abs().max())
+    # no residual
+    out_n, _ = csr.spmm_map(x, m, 1.0, 0.0)
+    assert float((out_n.double() - t64 @ m.double()).abs().max()) <= 2e-6 * float((t64 @ m.double()).abs().max())
+    # deterministic
+    out2, _ = csr.spmm_map(x, m, alpha, beta, addend=r)
+    assert torch.equal(out, out2)
+    with pytest.raises(ValueError):
+        csr.spmm_map(torch.randn(n, 128, device=DEV), torch.eye(128, device=DEV))
+
+
 # ----------------------------------------------------------------------------- BASELINE configs[1..3] at full size
 @pytest.mark.parametrize("shape", ["C2", "C3", "C4"])
 def test_full_size_dataset_shapes_vs_oracle(shape):

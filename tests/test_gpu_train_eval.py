@@ -457,13 +457,10 @@ def test_topk_tensor_core_kernel_failure_falls_back_to_exact(monkeypatch):
     assert stats["rows_reranked_exactly"] == 200 and torch.equal(got, want)
 
 
-@pytest.mark.parametrize("no_tma", [False, True])
-def test_topk_tensor_core_item_tiles_by_tma_and_by_loader_warps(no_tma, monkeypatch):
-    """The item tiles reach shared memory by cp.async.bulk.tensor (SWIZZLE_128B boxes, default) or by the loader
-    warps (GR_TC_NO_TMA=1): identical lists either way, from a row-strided item table (ld > d) whose catalogue
-    size is no multiple of the tile, with nearly every row proven by the nomination pass."""
-    if no_tma:
-        monkeypatch.setenv("GR_TC_NO_TMA", "1")
+def test_topk_tensor_core_item_tiles_by_tma_from_a_strided_table():
+    """The item tiles reach shared memory by cp.async.bulk.tensor (SWIZZLE_128B boxes): a row-strided item table
+    (ld > d) whose catalogue size is no multiple of the tile (the hardware zero-fills the tail rows) gives the
+    exact kernel's lists, with nearly every row proven by the nomination pass."""
     rng = np.random.default_rng(11)
     nu, ni, d = 700, 10007, 64
     ue = torch.from_numpy(rng.standard_normal((nu, d)).astype(np.float32)).to(DEV)
