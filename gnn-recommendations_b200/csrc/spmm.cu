@@ -229,17 +229,28 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) spmm_warp_rows(const SpmmAr
 // and the addend row are prefetched at the previous boundary.  Rows with >= long_thr entries
 // belong to the long-row kernel: the stream jumps over them.
 // ---------------------------------------------------------------------------------------------
+// MAP variant (dense-map epilogue): a finished row is not mapped at once — one row against the d x d map re-reads
+// the whole map from shared memory (16 KB per row: measured 2x slower than the separate rowmap kernel) and is a
+// 64-deep dependent fmaf chain in the middle of the gather stream.  The sub-warp STASHES the row in shared memory
+// instead and the map is applied to four stashed rows at a time (4 rows x 4 columns per lane: every map element
+// read from shared memory feeds four rows, sixteen independent chains per lane), at the converged point of the
+// warp's batch loop so that both sub-warps run the dense loop together.
+constexpr int kMapRows = 4;     // rows per sub-warp stash
+
 template <int D, int PEERS, bool MAP = false>
-__global__ void __launch_bounds__(kWarpsPerCta * 32) spmm_stream_rows(const SpmmArgs a) {
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 3) spmm_stream_rows(const SpmmArgs a) {
     using C = RowCfg<D>;
     constexpr int LPR = C::LPR, VPL = C::VPL, SPW = C::RPW, UNROLL = C::UNROLL;
     constexpr unsigned kFull = 0xffffffffu;
     static_assert(!MAP || (VPL == 1 && PEERS == kPeersNone), "dense-map epilogue: d <= 128, single GPU");
-    // dense-map epilogue: the map and one staging row per sub-warp in shared memory
+    constexpr int F4 = D / 4;
+    // dense-map epilogue: the map, kMapRows stashed rows per sub-warp and their row ids in shared memory
     extern __shared__ __align__(16) unsigned char stream_smem[];
-    float4 *Ms4 = reinterpret_cast<float4 *>(stream_smem);                          // [D][D/4]
-    float4 *srow4 = Ms4 + (MAP ? D * (D / 4) : 0);                                   // [warps * SPW][D/4]
+    float4 *Ms4 = reinterpret_cast<float4 *>(stream_smem);                          // [D][F4]
+    float4 *stash4 = Ms4 + (MAP ? D * F4 : 0);                                       // [warps * SPW][kMapRows][F4]
+    int *stash_row = reinterpret_cast<int *>(stash4 + (MAP ? kWarpsPerCta * SPW * kMapRows * F4 : 0));
     float map_beta = 0.f;
+    int scount = 0;                                                                  // rows in this sub-warp's stash
     if constexpr (MAP) {
         load_map_smem<D>(reinterpret_cast<float *>(Ms4), a, threadIdx.x, kWarpsPerCta * 32);
         map_beta = map_beta_of(a);
@@ -259,32 +270,58 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) spmm_stream_rows(const Spmm
     for (int j = 0; j < VPL; ++j) acc[j] = add_cur[j] = make_float4(0.f, 0.f, 0.f, 0.f);
 
     auto load_addend = [&](int row) {
-        if (a.addend) {
+        if constexpr (!MAP) {          // (the dense-map epilogue reads the residual rows when it writes a batch)
+            if (a.addend) {
 #pragma unroll
-            for (int j = 0; j < VPL; ++j) add_cur[j] = __ldg(a.addend + (long long)row * a.lda4 + gl + j * LPR);
+                for (int j = 0; j < VPL; ++j) add_cur[j] = __ldg(a.addend + (long long)row * a.lda4 + gl + j * LPR);
+            }
+        }
+    };
+    // dense-map epilogue: out = alpha (t M) + beta R for the rows of this sub-warp's stash; lane gl forms
+    // columns 4 gl .. 4 gl + 3 of all of them
+    auto map_stash = [&]() {
+        if constexpr (MAP) {
+            const unsigned sub = (LPR == 32) ? kFull : (((1u << LPR) - 1u) << ((lane / LPR) * LPR));
+            const int sw = warp * SPW + lane / LPR;
+            const float4 *st = stash4 + sw * kMapRows * F4;
+            __syncwarp(sub);                         // the stashed rows (written by the other lanes) are visible
+            float4 o[kMapRows];
+#pragma unroll
+            for (int q = 0; q < kMapRows; ++q) o[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+            for (int i4 = 0; i4 < F4; ++i4) {
+                const float4 m0 = Ms4[(4 * i4 + 0) * F4 + gl], m1 = Ms4[(4 * i4 + 1) * F4 + gl];
+                const float4 m2 = Ms4[(4 * i4 + 2) * F4 + gl], m3 = Ms4[(4 * i4 + 3) * F4 + gl];
+#pragma unroll
+                for (int q = 0; q < kMapRows; ++q) {
+                    const float4 tt = st[q * F4 + i4];
+                    fma4(o[q], tt.x, m0);
+                    fma4(o[q], tt.y, m1);
+                    fma4(o[q], tt.z, m2);
+                    fma4(o[q], tt.w, m3);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < kMapRows; ++q) {
+                if (q < scount) {
+                    const int row = stash_row[sw * kMapRows + q];
+                    float4 res = scale4(o[q], a.map_alpha, GR_SCALE_MUL);
+                    if (a.addend) fma4(res, map_beta, __ldg(a.addend + (long long)row * a.lda4 + gl));
+                    st_stream_f4(a.out + (long long)row * a.ldo4 + gl, res);
+                }
+            }
+            __syncwarp(sub);                         // before the stash is written again
+            scount = 0;
         }
     };
     auto flush = [&](int row) {
         if constexpr (MAP) {
-            // t (one float4 per lane of the sub-warp) -> shared memory, then lane gl forms columns 4gl..4gl+3 of t M
-            const unsigned sub = (LPR == 32) ? kFull : (((1u << LPR) - 1u) << ((lane / LPR) * LPR));
-            float4 *mine = srow4 + (warp * SPW + lane / LPR) * (D / 4);
-            mine[gl] = acc[0];
-            __syncwarp(sub);
-            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 2
-            for (int i4 = 0; i4 < D / 4; ++i4) {
-                const float4 tt = mine[i4];
-                fma4(o, tt.x, Ms4[(4 * i4 + 0) * (D / 4) + gl]);
-                fma4(o, tt.y, Ms4[(4 * i4 + 1) * (D / 4) + gl]);
-                fma4(o, tt.z, Ms4[(4 * i4 + 2) * (D / 4) + gl]);
-                fma4(o, tt.w, Ms4[(4 * i4 + 3) * (D / 4) + gl]);
-            }
-            __syncwarp(sub);
+            if (scount == kMapRows) map_stash();     // rare: several rows ended inside one batch of entries
+            const int sw = warp * SPW + lane / LPR;
+            stash4[(sw * kMapRows + scount) * F4 + gl] = acc[0];
+            if (gl == 0) stash_row[sw * kMapRows + scount] = row;
+            ++scount;
             if (a.y) st_stream_f4(a.y + (long long)row * a.ldy4 + gl, scale4(acc[0], a.map_alpha, GR_SCALE_MUL));
-            o = scale4(o, a.map_alpha, GR_SCALE_MUL);
-            if (a.addend) fma4(o, map_beta, add_cur[0]);
-            st_stream_f4(a.out + (long long)row * a.ldo4 + gl, o);
             acc[0] = make_float4(0.f, 0.f, 0.f, 0.f);
         } else {
 #pragma unroll
@@ -407,6 +444,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) spmm_stream_rows(const Spmm
                 }
                 u0 = lim;
             }
+            if constexpr (MAP) {     // the sub-warps are converged again: map the stashes that are (nearly) full
+                if (__any_sync(kFull, scount >= kMapRows - 1)) map_stash();
+            }
         }
         if (dead_until > kc + LPR && kc < stream_end) {  // jump over a long row: reload the chunk registers
             kc = dead_until;
@@ -426,6 +466,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) spmm_stream_rows(const Spmm
     while (r < r_end) {
         flush(r);
         next_row();
+    }
+    if constexpr (MAP) {
+        if (__any_sync(kFull, scount > 0)) map_stash();
     }
 }
 
@@ -709,14 +752,11 @@ __global__ void __launch_bounds__(LongCfgBar<D>::THREADS, 1) spmm_long_rows_bar(
     // persistent CTAs: rows are handed out in row_order (longest first) through a ticket counter,
     // so the hottest row starts first and no CTA queues work behind it.
     int &s_ticket = *reinterpret_cast<int *>(smem_raw + L::SMEM);  // one int after the rings
-    // dense-map epilogue: the map and one staging row after the ticket word
-    float *Ms = reinterpret_cast<float *>(smem_raw + L::SMEM + 16);   // [D][D]
-    float *srow = Ms + (MAP ? D * D : 0);                             // [D]
+    // dense-map epilogue: one staging row after the ticket word; the map itself is read through L1 (a few hundred
+    // long rows per launch — 16 KB of shared memory here would cost the streaming kernel a resident CTA)
+    float *srow = reinterpret_cast<float *>(smem_raw + L::SMEM + 16);   // [D]
     float map_beta = 0.f;
-    if constexpr (MAP) {
-        load_map_smem<D>(Ms, a, threadIdx.x, L::THREADS);             // visible after the first barrier below
-        map_beta = map_beta_of(a);
-    }
+    if constexpr (MAP) map_beta = map_beta_of(a);
     for (;;) {
     if (threadIdx.x == 0) s_ticket = (int)atomicAdd(a.sched, 1u);
     __syncthreads();
@@ -823,7 +863,8 @@ __global__ void __launch_bounds__(LongCfgBar<D>::THREADS, 1) spmm_long_rows_bar(
         if (is_cons && part < 0) {
             float o = 0.f;
 #pragma unroll 8
-            for (int i = 0; i < D; ++i) o = __fmaf_rn(srow[i], Ms[i * D + f], o);
+            for (int i = 0; i < D; ++i)
+                o = __fmaf_rn(srow[i], a.map_transposed ? __ldg(a.map + f * D + i) : __ldg(a.map + i * D + f), o);
             if (a.y) reinterpret_cast<float *>(a.y + (long long)r * a.ldy4)[f] = __fmul_rn(acc, a.map_alpha);
             o = __fmul_rn(o, a.map_alpha);
             if (a.addend) o = __fmaf_rn(map_beta, reinterpret_cast<const float *>(a.addend + (long long)r * a.lda4)[f], o);
@@ -965,8 +1006,8 @@ static int launch(const SpmmArgs &base, int n_long, long long n_rows, int slot, 
             GR_CUDA_CHECK(cudaFuncSetAttribute(k_mc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
             side->smem_attr_set[slot] = true;
         }
-        // dense-map epilogue (d <= 64: the barrier pipeline): the map and a staging row follow the rings
-        constexpr size_t kSmemMap = kSmem + (size_t)D * D * 4 + (size_t)D * 4;
+        // dense-map epilogue (d <= 64: the barrier pipeline): a staging row follows the rings
+        constexpr size_t kSmemMap = kSmem + (size_t)D * 4;
         if constexpr (kBar) {
             if (base.map && !side->smem_attr_set_map[slot]) {
                 GR_CUDA_CHECK(cudaFuncSetAttribute(spmm_long_rows_bar<D, kPeersNone, true>,
@@ -1014,7 +1055,7 @@ static int launch(const SpmmArgs &base, int n_long, long long n_rows, int slot, 
         if (ctas > 0) {
             if (base.map) {
                 if constexpr (D <= 64) {
-                    constexpr size_t kMapSmem = (size_t)D * D * 4 + (size_t)kWarpsPerCta * C::RPW * D * 4;
+                    constexpr size_t kMapSmem = (size_t)D * D * 4 + (size_t)kWarpsPerCta * C::RPW * kMapRows * (D * 4 + 4);
                     spmm_stream_rows<D, kPeersNone, true><<<(unsigned)ctas, kWarpsPerCta * 32, kMapSmem, stream>>>(wa);
                 }
             } else if (base.n_peers > 0 && base.peer_multicast)

@@ -21,13 +21,14 @@
 //                          a two-stage ring, completion by mbarrier complete_tx
 //   warp 1, one lane     : MMA issuer — d/8 tcgen05.mma (K = 8 per instruction) per tile into one of four
 //                          64-column TMEM accumulators, tcgen05.commit to the stage / accumulator mbarriers
-//   warps 2-5  epilogue  : tcgen05.ld 32 columns at a time into two register sets (the load of the next chunk
-//                          is in flight while one is selected); thread = TMEM lane = one user.  Selection is
+//   warps 2-5  epilogue  : tcgen05.ld of a whole 64-column tile into registers (the accumulator is released at
+//                          once); thread = TMEM lane = one user.  Selection is
 //                          max-first: masked columns (seen items, catalogue tail) are set to -inf on the rare
-//                          chunks that have any, four 8-column FMNMX trees give the group maxima, and only a
+//                          tiles that have any, eight 8-column FMNMX trees give the group maxima, and only a
 //                          group whose maximum beats the user's admission threshold is staged (8 values) and
-//                          walked — pushes into the user's K' min-heap in shared memory run lane-parallel.
-// Two CTAs are resident per SM when the heaps fit (d = 64: K' <= 32), so eight epilogue warps
+//                          appended to the user's pending queue; the queues are drained in lock-step into the
+//                          users' candidate sets (unsorted K' entries + tracked minimum) in shared memory.
+// Two CTAs are resident per SM when the candidate sets fit (d = 64: K' <= 32), so eight epilogue warps
 // share the four schedulers and one CTA's MMA overlaps the other's selection.
 #include <cuda.h>
 #include <math_constants.h>
@@ -186,52 +187,54 @@ __device__ __forceinline__ uint32_t sw128_offset(int row, int c16) {
 // instruction descriptor: D = F32, A = B = TF32, both K-major, N at bits [17,23) (N>>3), M at [24,29) (M>>4)
 constexpr uint32_t kIdescTf32 = (1u << 4) | (2u << 7) | (2u << 10) | ((TC_N >> 3) << 17) | ((TC_M >> 4) << 24);
 
-// Per-user candidate set = binary MIN-heap on the approximate score of the K' best seen so far,
-// position-major in shared memory (entry p of user m at [p * 128 + m], conflict-free for a warp).  The
-// root is the worst kept score = the admission threshold.  Ties are broken arbitrarily: the nomination
-// only has to guarantee "every rejected or evicted item has approximate score <= the final root".
-// Pushes run LANE-PARALLEL: a lane whose 8-column group maximum beats its threshold stages the group in
-// shared memory and walks it, so the warp executes max-over-lanes pushes per group instead of one
-// divergent push per (lane, column) event.
+// Per-user candidate set = the K' best approximate scores seen so far as an UNSORTED array, position-major in
+// shared memory (entry p of user m at [p * 128 + m], conflict-free for a warp), plus — in registers — the worst
+// kept score (the admission threshold) and its position.  A new entry overwrites the worst one and the minimum is
+// recomputed by a scan: K' independent shared-memory loads and a compare/select tree, ~100 cycles of dependent
+// latency and the SAME instruction stream for every lane.  (The first versions kept a binary heap: fewer
+// instructions per insertion, but a sift-down is five dependent load -> compare -> store rounds with data-dependent
+// trip counts, ~3x the latency, and the lock-step drain of a warp is bound by exactly that latency.)
+// Ties are broken arbitrarily: the nomination only has to guarantee "every rejected or evicted item has
+// approximate score <= the final threshold".
 struct SelState {
     int cnt;
     float thr;
+    int minpos;
 };
 
-__device__ __forceinline__ SelState tc_heap_push(float *hs, int *hi, int m, int K, int cnt, float s, int id) {
-    if (cnt < K) {                       // filling: append and sift up
-        int i = cnt++;
-        while (i > 0) {
-            const int par = (i - 1) >> 1;
-            const float ps = hs[par * TC_M + m];
-            if (!(s < ps)) break;                    // the parent must be the worse one
-            hs[i * TC_M + m] = ps;
-            hi[i * TC_M + m] = hi[par * TC_M + m];
-            i = par;
-        }
-        hs[i * TC_M + m] = s;
-        hi[i * TC_M + m] = id;
-    } else {                             // full: the new entry replaces the root, sift down
-        int i = 0;
-        while (true) {
-            int c = 2 * i + 1;
-            if (c >= K) break;
-            float cs = hs[c * TC_M + m];
-            if (c + 1 < K) {
-                const float rs = hs[(c + 1) * TC_M + m];
-                if (rs < cs) { ++c; cs = rs; }
-            }
-            if (!(cs < s)) break;
-            hs[i * TC_M + m] = cs;
-            hi[i * TC_M + m] = hi[c * TC_M + m];
-            i = c;
-        }
-        hs[i * TC_M + m] = s;
-        hi[i * TC_M + m] = id;
-    }
+__device__ __forceinline__ SelState tc_set_insert(float *hs, int *hi, int m, int K, int cnt, int minpos, float s, int id) {
+    const int pos = cnt < K ? cnt : minpos;       // filling: append; full: replace the worst entry
+    hs[pos * TC_M + m] = s;
+    hi[pos * TC_M + m] = id;
     SelState st;
-    st.cnt = cnt;
-    st.thr = (cnt == K) ? hs[m] : -CUDART_INF_F;     // root score once the heap is full
+    st.cnt = cnt < K ? cnt + 1 : cnt;
+    st.thr = -CUDART_INF_F;
+    st.minpos = 0;
+    if (st.cnt == K) {                            // (K is a multiple of 8)
+        float mn = CUDART_INF_F;
+        int mp = 0;
+        for (int p0 = 0; p0 < K; p0 += 8) {
+            float e[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) e[j] = hs[(p0 + j) * TC_M + m];
+            // (value, position) minimum tree over the eight entries
+            const bool l01 = e[1] < e[0], l23 = e[3] < e[2], l45 = e[5] < e[4], l67 = e[7] < e[6];
+            const float v01 = l01 ? e[1] : e[0], v23 = l23 ? e[3] : e[2], v45 = l45 ? e[5] : e[4], v67 = l67 ? e[7] : e[6];
+            const int p01 = l01 ? 1 : 0, p23 = l23 ? 3 : 2, p45 = l45 ? 5 : 4, p67 = l67 ? 7 : 6;
+            const bool la = v23 < v01, lb = v67 < v45;
+            const float va = la ? v23 : v01, vb = lb ? v67 : v45;
+            const int pa = la ? p23 : p01, pb = lb ? p67 : p45;
+            const bool lc = vb < va;
+            const float vc = lc ? vb : va;
+            const int pc = lc ? pb : pa;
+            if (vc < mn) {
+                mn = vc;
+                mp = p0 + pc;
+            }
+        }
+        st.thr = mn;
+        st.minpos = mp;
+    }
     return st;
 }
 
@@ -240,8 +243,8 @@ __device__ __forceinline__ float max8(const float *v) {
 }
 
 // Columns that beat a user's (possibly stale) threshold are only APPENDED to the user's pending queue
-// (position-major like the heap: entry q of user m at [q * 128 + m]); the heap pushes — long divergent sift
-// loops — run when some lane's queue is nearly full: all lanes then pop their queues in lockstep, so a push
+// (position-major like the candidate set: entry q of user m at [q * 128 + m]); the insertions run when some
+// lane's queue is nearly full: all lanes then pop their queues in lockstep, so a push
 // iteration serves every lane that has work instead of the one lane that happened to hit in this chunk
 // (one push per chunk with 1 of 32 lanes active was the dominant cost of the first version).  A stale
 // threshold only admits extra queue entries; each is re-checked against the current root when popped.
@@ -253,20 +256,22 @@ __device__ __forceinline__ void pend_append(uint32_t slot, float s, int id) {
 }
 
 __device__ __noinline__ SelState tc_drain(float *hs, int *hi, const float *ps, const int *pi, int m, int K, int cnt,
-                                          float thr, int np) {
+                                          float thr, int minpos, int np) {
     for (int q = 0; __any_sync(0xffffffffu, q < np); ++q) {
         if (q < np) {
             const float sj = ps[q * TC_M + m];
             if (sj > thr) {
-                const SelState st = tc_heap_push(hs, hi, m, K, cnt, sj, pi[q * TC_M + m]);
+                const SelState st = tc_set_insert(hs, hi, m, K, cnt, minpos, sj, pi[q * TC_M + m]);
                 cnt = st.cnt;
                 thr = st.thr;
+                minpos = st.minpos;
             }
         }
     }
     SelState out;
     out.cnt = cnt;
     out.thr = thr;
+    out.minpos = minpos;
     return out;
 }
 
@@ -284,8 +289,8 @@ __global__ void __launch_bounds__(TC_THREADS, 2) topk_tc_candidates_kernel(const
     const int nkb = d / TC_KB;                       // k-blocks of 32 tf32
     unsigned char *sA = smem_raw;                    // [nkb][128 rows][128 B]
     unsigned char *sB = sA + (size_t)nkb * TC_A_TILE;             // [stages][nkb][64 rows][128 B]
-    float *ls = reinterpret_cast<float *>(sB + (size_t)TC_STAGES * nkb * TC_B_TILE);     // heap scores [kprime][128]
-    int *li = reinterpret_cast<int *>(ls + (size_t)a.kprime * TC_M);                      // heap ids    [kprime][128]
+    float *ls = reinterpret_cast<float *>(sB + (size_t)TC_STAGES * nkb * TC_B_TILE);     // kept scores [kprime][128]
+    int *li = reinterpret_cast<int *>(ls + (size_t)a.kprime * TC_M);                      // kept ids    [kprime][128]
     float *pend_s = reinterpret_cast<float *>(li + (size_t)a.kprime * TC_M);              // pending scores [TC_PEND][128]
     int *pend_i = reinterpret_cast<int *>(pend_s + TC_PEND * TC_M);                       // pending ids    [TC_PEND][128]
     uint64_t *bars = reinterpret_cast<uint64_t *>(pend_i + TC_PEND * TC_M);
@@ -373,11 +378,11 @@ __global__ void __launch_bounds__(TC_THREADS, 2) topk_tc_candidates_kernel(const
         const uint32_t tmem_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
         const bool user_ok = row0 + m < a.n_eval;
         const int K = a.kprime;
-        int cnt = 0;                 // heap entries
+        int cnt = 0, minpos = 0;     // kept candidates, position of the worst one
         // next free entry of this user's pending queue, as a shared-space byte address (ids 8 KB further)
         const uint32_t wp0 = smem_u32(pend_s + m), wp_limit = wp0 + (TC_PEND - TC_GROUP) * TC_M * 4;
         uint32_t wp = wp0;
-        // admission threshold: root of the heap once it is full; a row beyond n_eval never admits anything
+        // admission threshold: the worst kept score once the set is full; a row beyond n_eval never admits anything
         float thr = user_ok ? -CUDART_INF_F : CUDART_INF_F;
         constexpr int kNoSeen = 0x7fffffff;
         int sc = 0, se = 0;
@@ -392,32 +397,41 @@ __global__ void __launch_bounds__(TC_THREADS, 2) topk_tc_candidates_kernel(const
         }
         int next_seen = sc < se ? a.seen_items[sc] : kNoSeen;     // absolute item id
 
-        // selection over one 32-column chunk held in registers (scores of items cbase .. cbase + 31)
-        auto select = [&](float (&v)[32], const int cbase) {
+        // selection over one 64-column tile held in registers (scores of items cbase .. cbase + 63).  The whole tile
+        // is one straight-line block up to the group branches, so the eight FMNMX trees overlap (two epilogue warps
+        // per scheduler cannot hide dependent-issue latency by themselves: "wait" was the top stall reason).
+        auto select = [&](float (&v)[TC_N], const int cbase) {
             if (a.debug & 1) return;
             // columns that must not be nominated: seen items of this user, padding beyond the range
-            unsigned kill = 0;
-            while (next_seen < cbase + 32) {          // next_seen is prefetched: no load on the common path
-                if (next_seen >= cbase) kill |= 1u << (next_seen - cbase);
+            unsigned kill0 = 0, kill1 = 0;
+            while (next_seen < cbase + TC_N) {        // next_seen is prefetched: no load on the common path
+                const int o = next_seen - cbase;
+                if (o >= 32) kill1 |= 1u << (o - 32);
+                else if (o >= 0) kill0 |= 1u << o;
                 ++sc;
                 next_seen = sc < se ? a.seen_items[sc] : kNoSeen;
             }
             const int room = item_hi - cbase;
-            if (room < 32) kill |= room <= 0 ? 0xffffffffu : ~((1u << room) - 1u);
-            if (kill) {
+            if (room < TC_N) {
+                kill0 |= room <= 0 ? 0xffffffffu : (room >= 32 ? 0u : ~((1u << room) - 1u));
+                kill1 |= room <= 32 ? 0xffffffffu : ~((1u << (room - 32)) - 1u);
+            }
+            if (kill0 | kill1) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if ((kill >> j) & 1u) v[j] = -CUDART_INF_F;
+                for (int j = 0; j < 32; ++j) {
+                    if ((kill0 >> j) & 1u) v[j] = -CUDART_INF_F;
+                    if ((kill1 >> j) & 1u) v[32 + j] = -CUDART_INF_F;
+                }
             }
             // max-first filter: one FMNMX tree per 8 columns, one compare per group
             unsigned hit = 0;
 #pragma unroll
-            for (int gq = 0; gq < 32 / TC_GROUP; ++gq) hit |= (unsigned)(max8(v + gq * TC_GROUP) > thr) << gq;
+            for (int gq = 0; gq < TC_N / TC_GROUP; ++gq) hit |= (unsigned)(max8(v + gq * TC_GROUP) > thr) << gq;
             if (!__any_sync(0xffffffffu, hit != 0)) return;       // the warp stays converged here
             if (a.debug & 16) return;
             // groups some lane passed: predicated appends to the pending queues (warp-uniform branch per group)
 #pragma unroll
-            for (int gq = 0; gq < 32 / TC_GROUP; ++gq) {
+            for (int gq = 0; gq < TC_N / TC_GROUP; ++gq) {
                 if (__any_sync(0xffffffffu, (hit >> gq) & 1u)) {
 #pragma unroll
                     for (int j = 0; j < TC_GROUP; ++j) {
@@ -428,9 +442,10 @@ __global__ void __launch_bounds__(TC_THREADS, 2) topk_tc_candidates_kernel(const
                     }
                     if (__any_sync(0xffffffffu, wp > wp_limit)) {   // the next group may not fit
                         if (!(a.debug & 8)) {
-                            const SelState st = tc_drain(ls, li, pend_s, pend_i, m, K, cnt, thr, (int)(wp - wp0) / (TC_M * 4));
+                            const SelState st = tc_drain(ls, li, pend_s, pend_i, m, K, cnt, thr, minpos, (int)(wp - wp0) / (TC_M * 4));
                             cnt = st.cnt;
                             thr = st.thr;
+                            minpos = st.minpos;
                         }
                         wp = wp0;
                     }
@@ -438,38 +453,23 @@ __global__ void __launch_bounds__(TC_THREADS, 2) topk_tc_candidates_kernel(const
             }
         };
 
-        // Two register sets: while one chunk is being selected, the tcgen05.ld of the next one is in flight
-        // (TMEM latency was exposed per chunk with only two epilogue warps per scheduler).
-        float va[32], vb[32];
-        auto release = [&](int acc) {          // this warp has read everything it needs from accumulator `acc`
+        float v[TC_N];
+        for (int t = 0; t < n_tiles; ++t) {
+            const int acc = t % TC_ACC;
+            mbar_wait(&t_full[acc], (t / TC_ACC) & 1);
+            tc_fence_after();
+            tmem_ld32_issue(tmem_row + (uint32_t)(acc * TC_N), *reinterpret_cast<float(*)[32]>(v));
+            tmem_ld32_issue(tmem_row + (uint32_t)(acc * TC_N + 32), *reinterpret_cast<float(*)[32]>(v + 32));
+            tmem_ld_wait(*reinterpret_cast<float(*)[32]>(v));
+            tmem_ld_wait(*reinterpret_cast<float(*)[32]>(v + 32));
+            // the accumulator is free as soon as the tile is in registers: the MMA of tile t + 4 can start
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&t_empty[acc]);
-        };
-        if (n_tiles > 0) {
-            mbar_wait(&t_full[0], 0);
-            tc_fence_after();
-            tmem_ld32_issue(tmem_row, va);
-            tmem_ld_wait(va);
-        }
-        for (int t = 0; t < n_tiles; ++t) {
-            const int acc = t % TC_ACC;
-            const int i0 = item_lo + t * TC_N;
-            tmem_ld32_issue(tmem_row + (uint32_t)(acc * TC_N + 32), vb);       // second half of tile t
-            select(va, i0);
-            tmem_ld_wait(vb);
-            release(acc);                                                       // every read of tile t has landed
-            if (t + 1 < n_tiles) {
-                const int nacc = (t + 1) % TC_ACC;
-                mbar_wait(&t_full[nacc], ((t + 1) / TC_ACC) & 1);
-                tc_fence_after();
-                tmem_ld32_issue(tmem_row + (uint32_t)(nacc * TC_N), va);       // first half of tile t + 1
-            }
-            select(vb, i0 + 32);
-            if (t + 1 < n_tiles) tmem_ld_wait(va);
+            select(v, item_lo + t * TC_N);
         }
         {
-            const SelState st = tc_drain(ls, li, pend_s, pend_i, m, K, cnt, thr, (int)(wp - wp0) / (TC_M * 4));
+            const SelState st = tc_drain(ls, li, pend_s, pend_i, m, K, cnt, thr, minpos, (int)(wp - wp0) / (TC_M * 4));
             cnt = st.cnt;
         }
         if (user_ok) {
@@ -686,7 +686,8 @@ extern "C" size_t gr_topk_tc_workspace_bytes(int64_t n_eval, int32_t kprime) {
 
 extern "C" int gr_topk_tc_supported(int32_t d, int32_t kprime) {
     if (!encode_tiled_fn()) return 0;      // the driver has no cuTensorMapEncodeTiled: exact kernel only
-    return (d > 0 && d % TC_KB == 0 && kprime > 0 && kprime <= TC_KPRIME_MAX && tc_smem_bytes(d, kprime) <= kSmemOneCta) ? 1 : 0;
+    return (d > 0 && d % TC_KB == 0 && kprime > 0 && kprime % 8 == 0 && kprime <= TC_KPRIME_MAX &&
+            tc_smem_bytes(d, kprime) <= kSmemOneCta) ? 1 : 0;
 }
 
 extern "C" int gr_score_topk_tc(const float *user_emb, int64_t ldu, const float *item_emb, int64_t ldi, int32_t d,

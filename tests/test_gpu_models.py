@@ -486,6 +486,38 @@ def test_gs_fused_propagation_equals_layerwise_path(tiny, csr):
         assert float((gf - gl).abs().max()) <= tol, (k, float((gf - gl).abs().max()), float(gl.abs().max()))
 
 
+@pytest.mark.parametrize("tag,transport", [("pt", True), ("nopt", False)])
+def test_gs_edge_list_mode_vs_reference(tiny, tag, transport):
+    """use_edge_index=True (model.py:159-222, parallel_transport.py:5-52): embeddings, per-layer embeddings and all
+    parameter gradients against the unmodified reference run on the same edge list (tests/golden/gs_edge.npz,
+    make_golden_gs_edge.py); the edge sums are unnormalised, so values reach 1e3 — embeddings to relative 1e-5,
+    gradients inside three times the error band of the reference's own fp32 run around its float64 run."""
+    import os
+    z = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "gs_edge.npz")))
+    nu, ni = int(tiny["n_users"]), int(tiny["n_items"])
+    model = load(g.OrthogonalBundleGNN(nu, ni, 64, 3, 8, 0.1, 0.0, 0.01, use_parallel_transport=transport,
+                                       use_edge_index=True), tiny, "gs")
+    ei = torch.from_numpy(z["edge_index"]).to(DEV)
+    with pytest.raises(ValueError):
+        model(edge_index=None)
+    ue, ie = model(edge_index=ei)
+    close(ue.detach().cpu().numpy(), z[f"{tag}/out_user"])
+    close(ie.detach().cpu().numpy(), z[f"{tag}/out_item"])
+    layers = torch.stack(model.get_layer_embeddings(edge_index=ei)).cpu().numpy()
+    for l in range(layers.shape[0]):
+        close(layers[l], z[f"{tag}/layers"][l])
+    loss = (ue * torch.from_numpy(z["probe_u"]).to(DEV)).sum() + (ie * torch.from_numpy(z["probe_i"]).to(DEV)).sum()
+    assert abs(float(loss) - float(z[f"{tag}/loss"])) <= 1e-4 * abs(float(z[f"{tag}/loss"]))
+    model.zero_grad()
+    loss.backward()
+    for k, prm in model.named_parameters():
+        assert prm.grad is not None, k
+        exact = z[f"{tag}/grad64/{k}"]                      # the reference in float64
+        ref_err = np.abs(z[f"{tag}/grad/{k}"].astype(np.float64) - exact).max()      # its own fp32 error
+        our_err = np.abs(prm.grad.cpu().numpy().astype(np.float64) - exact).max()
+        assert our_err <= max(3.0 * ref_err, 1e-5 * np.abs(exact).max()), (k, our_err, ref_err, np.abs(exact).max())
+
+
 def test_dropout_seed_from_device_memory_equals_host_seed(tiny):
     """CUDA-graph replays refresh the dropout seed in DEVICE memory (layer_ops.DropSeed.dev): the kernels must
     draw the mask of host seed (value + device word), forward and backward, for the rowmap epilogue and the GAT
