@@ -237,8 +237,46 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) spmm_warp_rows(const SpmmAr
 // warp's batch loop so that both sub-warps run the dense loop together.
 constexpr int kMapRows = 4;     // rows per sub-warp stash
 
+// out = alpha (t M) + beta R for the `count` (<= kMapRows) rows of one sub-warp's stash; lane gl forms columns
+// 4 gl .. 4 gl + 3 of all of them.  Deliberately NOT inlined: inlined, its sixteen accumulators raised the register
+// pressure of the gather loop until ptxas spilled the gathered rows themselves (STL / LDL in the hot loop, the
+// kernel 2.5x slower); as a call the caller's state is saved once per batch of rows instead.
+template <int D>
+__device__ __noinline__ void map_stash_rows(const float4 *Ms4, const float4 *st, const int *rows, int count, int gl,
+                                            unsigned sub, float4 *out, long long ldo4, const float4 *addend,
+                                            long long lda4, float alpha, float beta) {
+    constexpr int F4 = D / 4;
+    __syncwarp(sub);                         // the stashed rows (written by the other lanes) are visible
+    float4 o[kMapRows];
+#pragma unroll
+    for (int q = 0; q < kMapRows; ++q) o[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 2
+    for (int i4 = 0; i4 < F4; ++i4) {
+        const float4 m0 = Ms4[(4 * i4 + 0) * F4 + gl], m1 = Ms4[(4 * i4 + 1) * F4 + gl];
+        const float4 m2 = Ms4[(4 * i4 + 2) * F4 + gl], m3 = Ms4[(4 * i4 + 3) * F4 + gl];
+#pragma unroll
+        for (int q = 0; q < kMapRows; ++q) {
+            const float4 tt = st[q * F4 + i4];
+            fma4(o[q], tt.x, m0);
+            fma4(o[q], tt.y, m1);
+            fma4(o[q], tt.z, m2);
+            fma4(o[q], tt.w, m3);
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < kMapRows; ++q) {
+        if (q < count) {
+            const int row = rows[q];
+            float4 res = scale4(o[q], alpha, GR_SCALE_MUL);
+            if (addend) fma4(res, beta, __ldg(addend + (long long)row * lda4 + gl));
+            st_stream_f4(out + (long long)row * ldo4 + gl, res);
+        }
+    }
+    __syncwarp(sub);                         // before the stash is written again
+}
+
 template <int D, int PEERS, bool MAP = false>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 3) spmm_stream_rows(const SpmmArgs a) {
+__global__ void __launch_bounds__(kWarpsPerCta * 32, MAP ? 2 : 3) spmm_stream_rows(const SpmmArgs a) {
     using C = RowCfg<D>;
     constexpr int LPR = C::LPR, VPL = C::VPL, SPW = C::RPW, UNROLL = C::UNROLL;
     constexpr unsigned kFull = 0xffffffffu;
@@ -277,40 +315,13 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 3) spmm_stream_rows(const S
             }
         }
     };
-    // dense-map epilogue: out = alpha (t M) + beta R for the rows of this sub-warp's stash; lane gl forms
-    // columns 4 gl .. 4 gl + 3 of all of them
+    // dense-map epilogue of this sub-warp's stash (a call, not inlined: see map_stash_rows)
     auto map_stash = [&]() {
         if constexpr (MAP) {
             const unsigned sub = (LPR == 32) ? kFull : (((1u << LPR) - 1u) << ((lane / LPR) * LPR));
             const int sw = warp * SPW + lane / LPR;
-            const float4 *st = stash4 + sw * kMapRows * F4;
-            __syncwarp(sub);                         // the stashed rows (written by the other lanes) are visible
-            float4 o[kMapRows];
-#pragma unroll
-            for (int q = 0; q < kMapRows; ++q) o[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 1
-            for (int i4 = 0; i4 < F4; ++i4) {
-                const float4 m0 = Ms4[(4 * i4 + 0) * F4 + gl], m1 = Ms4[(4 * i4 + 1) * F4 + gl];
-                const float4 m2 = Ms4[(4 * i4 + 2) * F4 + gl], m3 = Ms4[(4 * i4 + 3) * F4 + gl];
-#pragma unroll
-                for (int q = 0; q < kMapRows; ++q) {
-                    const float4 tt = st[q * F4 + i4];
-                    fma4(o[q], tt.x, m0);
-                    fma4(o[q], tt.y, m1);
-                    fma4(o[q], tt.z, m2);
-                    fma4(o[q], tt.w, m3);
-                }
-            }
-#pragma unroll
-            for (int q = 0; q < kMapRows; ++q) {
-                if (q < scount) {
-                    const int row = stash_row[sw * kMapRows + q];
-                    float4 res = scale4(o[q], a.map_alpha, GR_SCALE_MUL);
-                    if (a.addend) fma4(res, map_beta, __ldg(a.addend + (long long)row * a.lda4 + gl));
-                    st_stream_f4(a.out + (long long)row * a.ldo4 + gl, res);
-                }
-            }
-            __syncwarp(sub);                         // before the stash is written again
+            map_stash_rows<D>(Ms4, stash4 + sw * kMapRows * F4, stash_row + sw * kMapRows, scount, gl, sub, a.out, a.ldo4,
+                              a.addend, a.lda4, a.map_alpha, map_beta);
             scount = 0;
         }
     };

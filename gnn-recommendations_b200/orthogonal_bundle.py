@@ -5,11 +5,12 @@ Per layer the reference computes  c = Â x ; t = c @ W_conn ; g = (t @ W_orth)[:
 x = (1-a) g + a x0.  The two 64x64 maps and the column permutation compose into one matrix
 M = W_conn (W_orth[:, perm]) built on the device by gr_gs_compose (block matrix exponentials +
 composition in two launches for all layers; backward gr_gs_compose_bwd through the adjoint Frechet
-derivative of exp — the reference runs 48 matrix_exp calls per forward), and a layer is ONE kernel:
-gr_spmm_csr_map_f32 applies M and the residual in the SpMM epilogue while the aggregated row is still on
-the SM (layer_ops.gs_propagate, forward and backward; d <= 64, no layer dropout).  Otherwise — dropout
-> 0 in train mode, other widths — a layer is the SpMM kernel plus the rowmap kernel (backward
-gr_rowmap_bwd).  The layer outputs are combined with softmax(layer_weights).  State-dict keys, constructor signature and
+derivative of exp — the reference runs 48 matrix_exp calls per forward), so a layer is the SpMM kernel
+plus the rowmap kernel (dense map + residual fused; backward gr_rowmap_bwd).  With GR_GS_FUSED=1 a layer is
+ONE kernel instead: gr_spmm_csr_map_f32 applies M and the residual in the SpMM epilogue
+(layer_ops.gs_propagate, forward and backward; d <= 64, no layer dropout) — implemented and parity-tested,
+but measured slower than the two-kernel layer on B200 (see _gs_fused_enabled), hence opt-in.  The layer
+outputs are combined with softmax(layer_weights).  State-dict keys, constructor signature and
 RNG order match the reference.  The edge-list mode (use_edge_index=True, off by default, model.py:64;
 parallel_transport.py:5-52) runs on the same kernels over a CSR of the edge list (_layers_edge_index)."""
 from __future__ import annotations
@@ -25,6 +26,17 @@ from .graph_builder import as_csr
 from .graph_builder import NormAdjCSR
 from .layer_ops import (gs_compose, gs_propagate, gs_propagate_supported, layer_combine, new_dropout_seed, rowmap,
                         spmm, spmm_map)
+
+
+def _gs_fused_enabled() -> bool:
+    """GR_GS_FUSED=1 selects the fused layer kernel (gr_spmm_csr_map_f32: sparse product, composed map and
+    residual in one launch, layer_ops.gs_propagate).  Default: the layer-wise path (SpMM kernel + rowmap kernel).
+    Measured on B200 at the Gowalla shape the fused kernel is SLOWER (forward 0.82 ms against 0.57 ms): the
+    register-tiled dense map needs ~45 more registers than the gather loop, and at 126 registers per thread only
+    one streaming CTA fits beside the long-row kernel's CTA on an SM (two waves instead of one); capped at 80
+    registers ptxas spills the gathered rows in the hot loop (Group-and-Shuffle)."""
+    import os
+    return os.environ.get("GR_GS_FUSED", "0") == "1"
 
 
 def _block_orthogonal(skew_params) -> torch.Tensor:
@@ -206,7 +218,7 @@ class OrthogonalBundleGNN(BaseRecommender):
     def propagate(self, adj_matrix=None, edge_index=None) -> torch.Tensor:
         w = F.softmax(self.layer_weights, dim=0)
         drop = self.dropout if (self.training and self.dropout_layer is not None) else 0.0
-        if not self.use_edge_index and adj_matrix is not None and drop == 0.0:
+        if not self.use_edge_index and adj_matrix is not None and drop == 0.0 and _gs_fused_enabled():
             csr = as_csr(adj_matrix)
             if gs_propagate_supported(csr, self.embedding_dim, self.n_layers):
                 # every layer = ONE kernel: sparse product, composed 64x64 map and residual in the SpMM epilogue

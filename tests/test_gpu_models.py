@@ -94,8 +94,8 @@ def test_gs_layer_embeddings_and_metrics(tiny, csr):
     assert len(layers) == 4 and layers[1].shape == (500, 64)
     met = m.get_orthogonality_metrics()
     assert float(met["local_fro_max"]) < 1e-4 and float(met["conn_fro_max"]) < 1e-4
-    with pytest.raises(NotImplementedError):
-        g.OrthogonalBundleGNN(5, 5, use_edge_index=True).to(DEV)(None, torch.zeros(2, 3, dtype=torch.long))
+    with pytest.raises(ValueError):          # edge-list mode without an edge list (model.py:136-138)
+        g.OrthogonalBundleGNN(5, 5, use_edge_index=True).to(DEV)(None, None)
 
 
 def test_rowmap_kernel_vs_torch():
@@ -451,7 +451,7 @@ def test_full_size_model_families_vs_oracle(case):
         assert abs(a - b) <= 1e-4 * max(abs(a), abs(b), 1e-12), (case, r, c, a, b)
 
 
-def test_gs_fused_propagation_equals_layerwise_path(tiny, csr):
+def test_gs_fused_propagation_equals_layerwise_path(tiny, csr, monkeypatch):
     """OrthogonalBundleGNN.propagate with the dense map fused into the SpMM epilogue (gs_propagate: one kernel per
     layer, hand-written backward) against the layer-wise path (SpMM + rowmap kernels under autograd): same
     embeddings and the same gradient for every parameter, to fp32 rounding."""
@@ -464,6 +464,7 @@ def test_gs_fused_propagation_equals_layerwise_path(tiny, csr):
         model.user_embedding.weight.mul_(30.0)
         model.item_embedding.weight.mul_(30.0)
     assert gs_propagate_supported(csr, 64, 3)
+    monkeypatch.setenv("GR_GS_FUSED", "1")           # propagate() takes the fused kernel only when asked to
     probe = torch.randn(nu + ni, 64, generator=torch.Generator().manual_seed(1)).to(DEV)
 
     def run(fused):
