@@ -568,6 +568,69 @@ class BipartitePartition:
         return a_u, a_i
 
 
+def build_user_owner_csrs(part: "BipartitePartition", rank: int, user, item, device="cuda",
+                          long_threshold: Optional[int] = None, item_degree_allreduce=None):
+    """Partitioned graph build of the user-owner layout (SURVEY.md §8e "graph build": partition the pairs by owner,
+    local sort / segment, one all-reduce of degrees): (A_u, A_i) of ``part.local_csrs(full, rank)`` straight from
+    the (user, item) pairs WITHOUT the full matrix — bit for bit the same entries, order and values.
+
+    A rank only touches the pairs of the users it owns (u % G == rank): the library's pair builder
+    (radix sort + dedupe: gr_build_csr_pattern) makes the pattern of the local bipartite block
+    [users_local + items] x [users_local + items]; a user's degree is its local pair count, an item's degree is the
+    SUM over ranks of its local pair counts — ``item_degree_allreduce(t)`` (in place on an int64 [n_items] device
+    tensor; ``torch.distributed.all_reduce`` in a job, omitted for one rank) is the only collective.  The values
+    are the reference's left-to-right product (dis[r] * mult) * dis[c] (graph_builder.py:126) from the same
+    degree look-up table as the single-GPU build."""
+    from .graph_builder import _require_cuda, degree_lut
+
+    device = _require_cuda(device)
+    G, U, I = part.world_size, part.n_users, part.n_items
+    user = torch.as_tensor(user, dtype=torch.int64).to(device)
+    item = torch.as_tensor(item, dtype=torch.int64).to(device)
+    if user.numel() != item.numel():
+        raise ValueError("user and item must have the same length")
+    if user.numel() and (int(user.min()) < 0 or int(user.max()) >= U or int(item.min()) < 0 or int(item.max()) >= I):
+        raise ValueError("user/item id out of range")
+    mine = (user % G) == rank
+    nul = part.n_users_local(rank)
+    loc = NormAdjCSR.from_pairs((user[mine] // G).contiguous(), item[mine].contiguous(), nul, I,
+                                normalization="none", device=device)          # vals = multiplicities
+    ip = loc.indptr.long()
+    counts = ip[1:] - ip[:-1]                          # entries per row (distinct neighbours) of the local block
+    # degrees count every pair, duplicates included (the row sums of the reference's summed-duplicate matrix)
+    deg_u = loc.deg[:nul].long()
+    deg_i = loc.deg[nul:].long().clone()
+    if item_degree_allreduce is not None:
+        item_degree_allreduce(deg_i)
+    max_deg = int(max(int(deg_u.max()) if nul else 0, int(deg_i.max()) if I else 0))
+    lut = torch.from_numpy(degree_lut(max_deg, -0.5)).to(device)
+    dis_u, dis_i = lut[deg_u], lut[deg_i]
+    kw = {} if long_threshold is None else {"long_threshold": int(long_threshold)}
+    # ---- A_u: the user rows; columns nul + item -> item
+    n_u = int(ip[nul].item())
+    cols_u = (loc.indices[:n_u] - nul).contiguous()
+    rows_u = torch.repeat_interleave(torch.arange(nul, device=device), counts[:nul])
+    vals_u = ((dis_u[rows_u] * loc.vals[:n_u]) * dis_i[cols_u.long()]).contiguous()
+    a_u = NormAdjCSR(loc.indptr[:nul + 1].clone(), cols_u, vals_u, nul, part.items_padded, **kw)
+    # ---- A_i: the item rows restricted to this rank's users (columns = local user row), padded to the common
+    # height and ROTATED to start at the next rank's block (see local_csrs)
+    cols_i = loc.indices[n_u:]
+    own = counts[nul:]
+    rows_i = torch.repeat_interleave(torch.arange(I, device=device), own)
+    vals_i = (dis_i[rows_i] * loc.vals[n_u:]) * dis_u[cols_i.long()]
+    iptr = torch.zeros(part.items_padded + 1, dtype=torch.int64, device=device)
+    torch.cumsum(own, 0, out=iptr[1:I + 1])
+    iptr[I + 1:] = iptr[I]
+    shift = part.item_shift(rank)
+    cut = int(iptr[shift].item())
+    cnt = iptr[1:] - iptr[:-1]
+    rptr = torch.zeros_like(iptr)
+    torch.cumsum(torch.cat([cnt[shift:], cnt[:shift]]), 0, out=rptr[1:])
+    a_i = NormAdjCSR(rptr.to(torch.int32), torch.cat([cols_i[cut:], cols_i[:cut]]).contiguous(),
+                     torch.cat([vals_i[cut:], vals_i[:cut]]).contiguous(), part.items_padded, nul, **kw)
+    return a_u, a_i
+
+
 class ItemExchange:
     """Peer-mapped buffers of the 1.5-D propagation: two full item tables T[2] [items_padded, d] (layer parity)
     and one partial buffer P [items_padded, d] per rank, allocated with torch's symmetric-memory allocator so every

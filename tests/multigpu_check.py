@@ -84,6 +84,13 @@ def main():
                                                lightgcn_propagate_user_owner)
     bp = BipartitePartition(nu, ni, world)
     a_u, a_i = bp.local_csrs(full, rank)
+    # partitioned build: the same two matrices straight from this rank's pairs + one all-reduce of the item degrees
+    from gnn_recommendations_b200.dist import build_user_owner_csrs
+    b_u, b_i = build_user_owner_csrs(bp, rank, *sp["train"], device=dev, long_threshold=full.long_threshold,
+                                     item_degree_allreduce=dist.all_reduce)
+    ok_build = all(torch.equal(x.indptr, y.indptr) and torch.equal(x.indices, y.indices) and
+                   torch.equal(x.vals.view(torch.int32), y.vals.view(torch.int32)) for x, y in ((b_u, a_u), (b_i, a_i)))
+    a_u, a_i = b_u, b_i                                  # everything below runs on the partition-built matrices
     iex = ItemExchange(bp, d, dev)
     lo_b, hi_b = bp.item_range(rank)
     xi_blk = torch.zeros((bp.item_block, d), device=dev)
@@ -113,13 +120,15 @@ def main():
     if hi_b > lo_b:
         ok_uo_train = ok_uo_train and bool(torch.allclose(uo.items.detach()[: hi_b - lo_b], w2.detach()[nu + lo_b: nu + hi_b],
                                                           rtol=1e-4, atol=2e-6))
-    flags = torch.tensor([int(ok_prop), int(ok_topk), int(ok_fused), int(ok_train), int(ok_uo), int(ok_uo_train)], device=dev)
+    flags = torch.tensor([int(ok_prop), int(ok_topk), int(ok_fused), int(ok_train), int(ok_uo), int(ok_uo_train),
+                          int(ok_build)], device=dev)
     dist.all_reduce(flags, op=dist.ReduceOp.MIN)
     if rank == 0:
         print(f"multigpu_check shape={shape} world={world} rows/rank={[part.n_local(r) for r in range(world)]} "
               f"propagation_bit_identical={bool(flags[0])} topk_bit_identical={bool(flags[1])} "
               f"fused_peer_exchange_bit_identical={bool(flags[2])} sharded_training_matches={bool(flags[3])} "
               f"user_owner_propagation_within_1e-5={bool(flags[4])} user_owner_training_matches={bool(flags[5])} "
+              f"user_owner_partitioned_build_bit_identical={bool(flags[6])} "
               f"train_step_ms: sharded {1e3 * t_sh / n_steps:.3f} / user-owner {1e3 * t_uo / 10:.3f} vs 1 GPU "
               f"{1e3 * t_1 / n_steps:.3f}", flush=True)
     dist.destroy_process_group()

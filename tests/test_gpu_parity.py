@@ -418,6 +418,36 @@ def test_partitioned_graph_build_equals_rows_of_the_full_build(shape, world, sel
         assert (got.n_rows, got.n_cols) == (want.n_rows, want.n_cols)
 
 
+@pytest.mark.parametrize("shape,world", [("tiny", 2), ("tiny", 3), ("C1", 4), ("C1", 8)])
+def test_user_owner_partitioned_build_equals_cuts_of_the_full_build(shape, world):
+    """build_user_owner_csrs: each rank's (A_u, A_i) from the pairs of ITS users + the all-reduced item degrees ==
+    BipartitePartition.local_csrs(full matrix) bit for bit (pattern, order, values), duplicate pairs included.
+    The all-reduce is emulated on one GPU by summing the ranks' item-degree shares."""
+    from gnn_recommendations_b200.dist import BipartitePartition, build_user_owner_csrs
+    from gnn_recommendations_b200.synthetic import synth_split
+    sp = synth_split(shape, 42)
+    nu, ni = sp["n_users"], sp["n_items"]
+    tu, ti = sp["train"]
+    tu, ti = np.concatenate([tu, tu[:50]]), np.concatenate([ti, ti[:50]])      # duplicates are summed
+    full = g.NormAdjCSR.from_pairs(tu, ti, nu, ni, device=DEV)
+    part = BipartitePartition(nu, ni, world)
+    # pass 1: every rank's share of the item degrees (what the all-reduce would add up)
+    shares = []
+    for rank in range(world):
+        build_user_owner_csrs(part, rank, tu, ti, device=DEV, item_degree_allreduce=lambda t: shares.append(t.clone()))
+    total = torch.stack(shares).sum(0)
+    assert torch.equal(total.to(torch.int32), full.deg[nu:])
+    for rank in range(world):
+        want_u, want_i = part.local_csrs(full, rank)
+        got_u, got_i = build_user_owner_csrs(part, rank, tu, ti, device=DEV, long_threshold=full.long_threshold,
+                                             item_degree_allreduce=lambda t: t.copy_(total))
+        for got, want, name in ((got_u, want_u, "A_u"), (got_i, want_i, "A_i")):
+            assert (got.n_rows, got.n_cols) == (want.n_rows, want.n_cols), (name, rank)
+            assert torch.equal(got.indptr, want.indptr), (shape, world, rank, name)
+            assert torch.equal(got.indices, want.indices), (shape, world, rank, name)
+            assert torch.equal(got.vals.view(torch.int32), want.vals.view(torch.int32)), (shape, world, rank, name)
+
+
 def test_spmm_two_streams_concurrently_share_no_state():
     """The C-ABI keeps no device-side state (the long-row ticket counters were __device__ globals):
     two propagations with long rows in flight on two streams — each with its own scheduler words and side
