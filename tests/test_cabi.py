@@ -94,3 +94,23 @@ def test_all_models_same_seed_same_parameters_as_reference():
         assert list(sa) == list(sb), cls.__name__
         for k in sa:
             assert torch.equal(sa[k], sb[k]), (cls.__name__, k)
+
+
+def test_integration_md_ctypes_stub_matches_the_bound_signature():
+    """The ctypes stub INTEGRATION.md shows a maintainer must name as many arguments as the header declares for
+    gr_spmm_csr_f32 (it went stale once when the peer-route and scheduler-workspace arguments were added)."""
+    from gnn_recommendations_b200 import _lib
+    text = open(os.path.join(REPO, "INTEGRATION.md"), encoding="utf-8").read()
+    start = text.index("_gr.gr_spmm_csr_f32.argtypes = ") + len("_gr.gr_spmm_csr_f32.argtypes = ")
+    expr = re.sub(r"#[^\n]*", "", text[start:text.index("def sparse_mm", start)])
+    argtypes = eval(expr, {"ctypes": ctypes})
+    assert len(argtypes) == len(_lib.SIGNATURES["gr_spmm_csr_f32"][1])
+    c0 = text.index("rc = _gr.gr_spmm_csr_f32(") + len("rc = _gr.gr_spmm_csr_f32(")
+    call = re.sub(r"#[^\n]*", "", text[c0:text.index("if rc:", c0)])
+    call = call[:call.rindex(")")]
+    depth, n_args = 0, 1
+    for ch in call:
+        depth += ch in "(["
+        depth -= ch in ")]"
+        n_args += (ch == "," and depth == 0)
+    assert n_args == len(argtypes), (n_args, len(argtypes))
