@@ -8,7 +8,7 @@ include/gr_b200.h); there is no CPU fallback.
 from . import _lib  # noqa: F401
 from .base import BaseRecommender  # noqa: F401
 from .graph_builder import (NormAdjCSR, as_csr, build_bipartite_graph, convert_to_torch_sparse,  # noqa: F401
-                            normalize_adjacency_matrix)
+                            normalize_adjacency_matrix, sm_copy)
 from .lightgcn import LightGCN, lightgcn_propagate  # noqa: F401
 from .ngcf import NGCF, NGCFLayer  # noqa: F401
 from .gat import GAT, GATLayer  # noqa: F401

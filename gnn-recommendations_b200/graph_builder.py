@@ -438,6 +438,36 @@ class NormAdjCSR:
         return d in (32, 64) and self.group_ptr is not None
 
 
+def sm_copy(dst: torch.Tensor, src: torch.Tensor, ctas: int = 32) -> None:
+    """dst <- src by a small SM kernel (gr_peer_copy_multi) on the current stream, between device memory and PINNED
+    host memory in either direction (pinned allocations are device-addressable under unified addressing: the kernel
+    stores to / loads from the host buffer over PCIe).  Why not cudaMemcpyAsync: beside an HBM-saturating SpMM the
+    copy engines are starved (measured at C5: the 12.8 GB embedding download ran at ~22 GB/s while a propagation
+    was running, 57 GB/s alone), whereas a few dozen resident copy CTAs compete for HBM like any other SM traffic.
+    Both tensors contiguous, same byte size; a tail that is no multiple of 16 bytes goes through copy_."""
+    if not (dst.is_contiguous() and src.is_contiguous()):
+        raise ValueError("sm_copy needs contiguous tensors")
+    n = src.numel() * src.element_size()
+    if n != dst.numel() * dst.element_size():
+        raise ValueError("sm_copy: size mismatch")
+    for t in (dst, src):
+        if t.device.type != "cuda" and not t.is_pinned():
+            raise ValueError("sm_copy: host tensors must be pinned")
+    main = n & ~15
+    dev = dst.device if dst.device.type == "cuda" else src.device
+    if dev.type != "cuda":
+        raise ValueError("sm_copy: one side must be a CUDA tensor")
+    if main:
+        import ctypes
+        dsts = (ctypes.c_void_p * 1)(dst.data_ptr())
+        srcs = (ctypes.c_void_p * 1)(src.data_ptr())
+        sizes = (ctypes.c_size_t * 1)(main)
+        with torch.cuda.device(dev):
+            check(lib().gr_peer_copy_multi(dsts, srcs, sizes, 1, int(ctas), stream_ptr()), "gr_peer_copy_multi")
+    if n > main:
+        dst.view(-1).view(torch.uint8)[main:].copy_(src.view(-1).view(torch.uint8)[main:], non_blocking=True)
+
+
 def degree_lut(max_deg: int, power: float) -> np.ndarray:
     """``np.power(max(deg,1).astype(float32), power)`` for deg = 0..max_deg — the host numpy is
     the source of Â's values in the reference (graph_builder.py:114-119, 130)."""

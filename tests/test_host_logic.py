@@ -179,3 +179,19 @@ def test_later_stages_refuse_cpu_inputs():
     p.grad = torch.ones(8)
     assert not fused_clip_adam_supported(torch.optim.Adam([p]))          # CPU tensors: stock path only
     assert not fused_clip_adam_supported(torch.optim.SGD([p], lr=0.1))
+
+
+def test_sm_copy_argument_checks_need_no_gpu():
+    """sm_copy validates its operands before it touches the library: pageable host memory, size mismatches, strided
+    views and a copy without a CUDA side are refused (the kernel stores to / loads from PINNED host memory)."""
+    import pytest
+    import torch
+
+    import gnn_recommendations_b200 as g
+    a, b = torch.zeros(64), torch.zeros(64)
+    with pytest.raises(ValueError, match="pinned"):
+        g.sm_copy(a, b)
+    with pytest.raises(ValueError, match="size"):
+        g.sm_copy(torch.zeros(32), b)
+    with pytest.raises(ValueError, match="contiguous"):
+        g.sm_copy(torch.zeros(8, 16)[:, ::2], torch.zeros(64))
