@@ -529,3 +529,21 @@ def test_spmm_routed_peer_stores(tiny_ref):
         rows = want[k * blk: min((k + 1) * blk, csr.n_rows)]
         assert torch.equal(bufs[k][slot * blk: slot * blk + rows.shape[0]], rows)
         assert torch.isnan(bufs[k][: slot * blk]).all()            # nothing else touched
+
+
+def test_sm_copy_between_pinned_host_and_device():
+    """sm_copy (gr_peer_copy_multi on the current stream): device -> pinned host and back, byte-exact, including a
+    size that is no multiple of 16 bytes (the tail goes through copy_) and a side stream."""
+    for n in (1 << 20, (1 << 20) + 3, 5):
+        src = torch.arange(n, dtype=torch.int32, device=DEV)
+        host = torch.empty(n, dtype=torch.int32, pin_memory=True)
+        host.fill_(-1)
+        g.sm_copy(host, src, 8)
+        torch.cuda.synchronize()
+        assert torch.equal(host, src.cpu()), n
+        back = torch.zeros(n, dtype=torch.int32, device=DEV)
+        st = torch.cuda.Stream(priority=-1)
+        with torch.cuda.stream(st):
+            g.sm_copy(back, host, 8)
+        st.synchronize()
+        assert torch.equal(back, src), n
