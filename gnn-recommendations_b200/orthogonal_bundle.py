@@ -145,14 +145,20 @@ class OrthogonalBundleGNN(BaseRecommender):
     def _edge_csr(self, edge_index: torch.Tensor) -> NormAdjCSR:
         """The edge list of the edge-list mode as a CSR: row = destination, one entry of value 1 per edge, in edge
         order (a stable sort by destination), so the SpMM's storage-order chain adds the source rows in the order
-        ``index_add_`` does (parallel_transport.py:49-50, model.py:218-222).  Cached per edge_index tensor."""
-        key = (edge_index.data_ptr(), tuple(edge_index.shape), str(edge_index.device))
-        hit = getattr(self, "_edge_cache", None)
-        if hit is not None and hit[0] == key:
-            return hit[1]
+        ``index_add_`` does (parallel_transport.py:49-50, model.py:218-222).  The last one is cached, keyed by
+        CONTENT (shape + two position-weighted checksums: a new tensor at a recycled address must not hit)."""
         dev = self.user_embedding.weight.device
         ei = edge_index.to(dev)
         n = self.n_users + self.n_items
+        if ei.dim() != 2 or ei.shape[0] != 2:
+            raise ValueError("edge_index must have shape [2, num_edges]")
+        if ei.numel() and (int(ei.min()) < 0 or int(ei.max()) >= n):
+            raise ValueError("edge_index holds node ids outside [0, n_users + n_items)")
+        w = torch.arange(1, ei.shape[1] + 1, device=dev, dtype=torch.int64)
+        key = (tuple(ei.shape), int((ei[0] * w).sum()), int((ei[1] * w).sum()))
+        hit = getattr(self, "_edge_cache", None)
+        if hit is not None and hit[0] == key:
+            return hit[1]
         order = torch.sort(ei[1], stable=True).indices                      # plumbing: once per edge list
         coo = torch.sparse_coo_tensor(torch.stack([ei[1][order], ei[0][order]]),
                                       torch.ones(ei.shape[1], dtype=torch.float32, device=dev), (n, n))

@@ -215,6 +215,42 @@ def gs_forward(adj_coo, user_w, item_w, conn_skew, conn_perm, local_skew, local_
     return xf[:nu], xf[nu:]
 
 
+def gs_forward_edge_index(edge_index: torch.Tensor, user_w, item_w, conn_skew, conn_perm, local_skew, local_perm,
+                          layer_weights, residual_alpha: float, return_layers: bool = False):
+    """OrthogonalBundleGNN.forward in its EDGE-LIST mode (use_edge_index=True, dropout 0; model.py:159-222):
+    per layer x_j <- sum over edges (i -> j) of W_conn x_i, written as the reference writes it —
+    ``x[src] @ W_conn.t()`` then ``index_add_`` over the destinations (parallel_transport.py:27-50) — or, without
+    parallel transport (conn_skew None), the plain ``index_add_`` of x[src] (model.py:218-222); then
+    g = (t @ W_orth)[:, perm_g], x = (1-a) g + a x0, out = sum_l softmax(layer_weights)_l x_l.
+    ``return_layers``: the per-layer outputs WITHOUT the residual (get_layer_embeddings, model.py:306-356)."""
+    src, dst = edge_index
+    x0 = torch.cat([user_w, item_w], dim=0)
+
+    def transport(x, l):
+        xs = x[src]
+        if conn_skew is not None:
+            xs = torch.mm(xs, block_orthogonal(conn_skew[l])[:, conn_perm[l]].t())
+        agg = torch.zeros_like(x)
+        agg.index_add_(0, dst, xs)
+        return agg
+
+    if return_layers:
+        x, layers = x0, [x0.clone()]
+        for l in range(len(local_skew)):
+            x = (transport(x, l) @ block_orthogonal(local_skew[l]))[:, local_perm[l]]
+            layers.append(x.clone())
+        return layers
+    x, outs = x0, [x0]
+    for l in range(len(local_skew)):
+        g = (transport(x, l) @ block_orthogonal(local_skew[l]))[:, local_perm[l]]
+        x = (1 - residual_alpha) * g + residual_alpha * x0
+        outs.append(x)
+    w = F.softmax(layer_weights, dim=0)
+    xf = sum([wi * e for wi, e in zip(w, outs)])
+    nu = user_w.shape[0]
+    return xf[:nu], xf[nu:]
+
+
 # --------------------------------------------------------------------------------------
 # 3. BPR sampling and step  (src/training/trainer.py:146-197, 237-279; losses.py:28-53)
 # --------------------------------------------------------------------------------------

@@ -151,6 +151,28 @@ def test_group_shuffle_forward(tiny, tiny_adj):
     np.testing.assert_allclose(ie.numpy(), tiny["gs/out_item"], rtol=1e-6, atol=1e-8)
 
 
+@pytest.mark.parametrize("tag,transport", [("pt", True), ("nopt", False)])
+def test_group_shuffle_edge_list_mode(tiny, tag, transport):
+    """The oracle's edge-list restatement (parallel_transport.py:5-52, model.py:159-222) against the unmodified
+    reference run on the same edge list (tests/golden/gs_edge.npz): embeddings and per-layer embeddings bit for bit
+    (same torch CPU ops in the same order)."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "gs_edge.npz"))
+    conn = [[t(tiny[f"gs/connection_layers.{l}.skew_params.{k}"]) for k in range(8)] for l in range(3)] if transport else None
+    cperm = [t(tiny[f"gs/connection_layers.{l}.shuffle_perm"]) for l in range(3)] if transport else None
+    loc = [[t(tiny[f"gs/local_transform_layers.{l}.skew_params.{k}"]) for k in range(8)] for l in range(3)]
+    lperm = [t(tiny[f"gs/local_transform_layers.{l}.perm"]) for l in range(3)]
+    args = (t(z["edge_index"]), t(tiny["gs/user_embedding.weight"]), t(tiny["gs/item_embedding.weight"]), conn, cperm,
+            loc, lperm, t(tiny["gs/layer_weights"]), 0.1)
+    ue, ie = po.gs_forward_edge_index(*args)
+    np.testing.assert_allclose(ue.numpy(), z[f"{tag}/out_user"], rtol=1e-6, atol=1e-6 * np.abs(z[f"{tag}/out_user"]).max())
+    np.testing.assert_allclose(ie.numpy(), z[f"{tag}/out_item"], rtol=1e-6, atol=1e-6 * np.abs(z[f"{tag}/out_item"]).max())
+    layers = po.gs_forward_edge_index(*args, return_layers=True)
+    for l, x in enumerate(layers):
+        want = z[f"{tag}/layers"][l]
+        np.testing.assert_allclose(x.numpy(), want, rtol=1e-6, atol=1e-6 * max(1.0, np.abs(want).max()))
+
+
 def test_parameter_count_kats(tiny):
     # /root/reference/problems.md:95-124: extra (non-embedding) parameters
     def extra(prefix):
