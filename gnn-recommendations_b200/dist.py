@@ -760,7 +760,7 @@ def _propagate_user_owner_steps(a_u: NormAdjCSR, a_i: NormAdjCSR, ex, xu0: torch
     pending = []                                     # copy streams with work the main stream has not waited for
 
     copy_mode = os.environ.get("GR_UO_COPY", "sm")
-    copy_ctas = int(os.environ.get("GR_UO_COPY_CTAS", "40"))    # 8 B200s, C5 ms/step: 16 CTAs 71.2, 24 61.1, 32 50.0, 64 52.3, 128 59.2
+    copy_ctas = int(os.environ.get("GR_UO_COPY_CTAS", "32"))    # 8 B200s, C5 ms/step: 16 CTAs 71.2, 24 61.1, 32 50.0, 64 52.3, 128 59.2
 
     def fan_out(copies):
         """copies: (peer k, dst ptr, src ptr, bytes), issued after what main has enqueued so far: 'sm' = one small
